@@ -1,0 +1,144 @@
+/*
+ * yacht_gpu.h -- C ABI of libyachtgpu: the B200 (sm_100a) replacement for YACHT's data-parallel
+ * hot path.  Plain C types only: no CUDA, torch or C++ types cross this boundary.
+ *
+ * What each entry point replaces in the reference (KoslickiLab/YACHT, paths relative to the
+ * reference root; the train core is src/cpp/main.cpp, the run-side compute is
+ * src/yacht/hypothesis_recovery_src.py):
+ *
+ *   ygpu_load_sketches      the in-memory result of read_sketches()            main.cpp:89-124
+ *                           (vector<vector<hash_t>> sketches, :51) as one flat
+ *                           uint64 array + CSR offsets; genome id = file-list
+ *                           line index (:127-139)
+ *   ygpu_build_index        compute_index_from_sketches()                      main.cpp:215-246
+ *   ygpu_pairwise_flag      compute_intersection_matrix[_by_sketches]()        main.cpp:249-366
+ *                           counts (:252-262) fused with threshold/emit (:274-308)
+ *   ygpu_row_partition      the contiguous row chunks per thread / per pass    main.cpp:338-349
+ *                           (here: work-balanced row ranges per GPU)
+ *   ygpu_sample_overlap     `sourmash scripts multisearch ... -t 0`            hypothesis_recovery_src.py:93-113
+ *                           (which reference genomes share >= 1 hash with the sample)
+ *   ygpu_exclusive_hashes   get_exclusive_hashes()                             hypothesis_recovery_src.py:116-206
+ *   ygpu_hyp_test           single_hyp_test() + get_alt_mut_rate()             hypothesis_recovery_src.py:209-306
+ *
+ * Conventions: every function returns 0 on success and a negative ygpu_status otherwise; the
+ * text of the last error is available from ygpu_last_error().  The caller owns every input
+ * buffer; the library owns every output buffer until ygpu_free().  One context drives one GPU;
+ * calls on one context are not re-entrant.  There is NO CPU fallback: without a CUDA device
+ * ygpu_ctx_create fails with YGPU_ERR_NO_DEVICE.
+ */
+#ifndef YACHT_GPU_H
+#define YACHT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ygpu_ctx ygpu_ctx;
+
+typedef enum {
+    YGPU_OK = 0,
+    YGPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run   */
+    YGPU_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed                       */
+    YGPU_ERR_ARG = -3,         /* invalid argument                                           */
+    YGPU_ERR_STATE = -4,       /* call order violated (e.g. pairwise before build_index)     */
+    YGPU_ERR_NOMEM = -5        /* host or device allocation failed                           */
+} ygpu_status;
+
+/* One flagged ORDERED pair: genome i is contained in genome j with `count` shared hashes
+ * (count == intersectionMatrix[i][j], main.cpp:258) and count / |S_i| >= threshold (:297-303). */
+typedef struct {
+    int32_t i;
+    int32_t j;
+    int32_t count;
+} ygpu_pair;
+
+/* The three banner statistics of main.cpp:242-244 plus the workload counts of SURVEY.md 8(d). */
+typedef struct {
+    uint64_t n_hashes;      /* T  = sum of sketch sizes                                        */
+    uint64_t n_distinct;    /* U  = "Total number of distinct hashes"                          */
+    uint64_t n_singleton;   /*      "... that appear in only one sketch"                       */
+    uint64_t n_index;       /* U2 = "Size of the index"                                        */
+    uint64_t n_postings;    /* P  = sum of posting lengths L over hashes with L >= 2           */
+    uint64_t n_increments;  /* W  = sum of L^2 (the ++ operations the reference performs)      */
+    uint64_t n_row_items;   /* entries of the per-genome work lists (implementation detail)    */
+    uint32_t max_sketch;    /* largest sketch size                                             */
+    uint32_t has_duplicates;/* 1 if some sketch holds the same hash twice                      */
+} ygpu_index_stats;
+
+/* Device timings (CUDA events on the context's stream) accumulated since ygpu_reset_timers(). */
+typedef struct {
+    double ms_h2d;          /* ygpu_load_sketches host->device copies                          */
+    double ms_sort;         /* K2a: (hash, genome) radix sort                                  */
+    double ms_index;        /* K2b: run detection, posting compaction, per-genome work lists   */
+    double ms_count;        /* K3+K4: pairwise shared-hash count fused with threshold/compact  */
+    double ms_d2h;          /* pair-list device->host copy                                     */
+    double ms_sample;       /* K5: sample membership + exclusive-hash reduction                */
+    double ms_stats;        /* K6: binomial statistics                                         */
+    uint64_t n_count_launches;   /* launches of the K3+K4 kernel                               */
+    uint64_t n_kernel_launches;  /* launches of all kernels of this library                    */
+} ygpu_timings;
+
+/* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */
+typedef struct {
+    uint32_t n_overlap;     /* |S_g  intersect  sample|  (multisearch: containment > 0 <=> n_overlap > 0) */
+    uint32_t nontrivial;    /* 1 if the genome takes part in the exclusive-hash computation    */
+    uint32_t n_exclusive;   /* hashes of g found in no other nontrivial genome                 */
+    uint32_t n_match;       /* ... of which are present in the sample                          */
+} ygpu_genome_counts;
+
+/* One row of single_hyp_test's 8-tuple (hypothesis_recovery_src.py:297-306). */
+typedef struct {
+    int32_t in_sample_est;
+    int32_t _pad;
+    double p_val;
+    int64_t num_exclusive_kmers;
+    int64_t num_exclusive_kmers_coverage;
+    int64_t num_matches;
+    double acceptance_threshold_with_coverage;
+    double actual_confidence_with_coverage;
+    double alt_confidence_mut_rate_with_coverage;
+} ygpu_hyp_row;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int ygpu_device_count(void);
+int ygpu_ctx_create(ygpu_ctx** out, int device);
+void ygpu_ctx_destroy(ygpu_ctx* ctx);
+const char* ygpu_last_error(const ygpu_ctx* ctx);      /* ctx may be NULL: last create error   */
+void ygpu_free(void* p);                               /* release a library-owned host buffer  */
+int ygpu_reset_timers(ygpu_ctx* ctx);
+int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out);
+
+/* ---- train path ---------------------------------------------------------------------------- */
+/* hashes[offsets[g] .. offsets[g+1]) is sketch g (any order, duplicates allowed).  HOST pointers;
+ * copied to the device (pinned staging is the caller's choice).                                 */
+int ygpu_load_sketches(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* offsets, uint32_t n_genomes);
+/* Same, but DEVICE pointers on ctx's device; the arrays are copied device-to-device.            */
+int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n_genomes);
+int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats /* may be NULL */);
+/* Flag ordered pairs whose query genome (member i) OR target lies in rows [row_begin,row_end):
+ * the unordered pair {a<b} is evaluated once by the owner of row a, and both directions (a,b)
+ * and (b,a) are tested against `threshold` exactly as main.cpp:296-303 does.  The union over a
+ * partition of [0,n) into row ranges is the full pair list.  *out is sorted by (i,j).            */
+int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end,
+                       ygpu_pair** out, uint64_t* n_out);
+/* bounds[0..nparts] : contiguous row ranges of (nearly) equal pairwise-count work.               */
+int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds);
+
+/* ---- run path ------------------------------------------------------------------------------ */
+/* sample: HOST pointer to the sample sketch hashes (any order).  Fills counts[n_genomes].
+ * Step 1 (multisearch -t 0): n_overlap.  Step 2 (get_exclusive_hashes): among the genomes with
+ * n_overlap > 0 (or, if `mask` is not NULL, the genomes with mask[g] != 0), the number of hashes
+ * exclusive to each genome and how many of those are in the sample.                              */
+int ygpu_exclusive_hashes(ygpu_ctx* ctx, const uint64_t* sample, uint64_t n_sample,
+                          const uint8_t* mask /* may be NULL */, ygpu_genome_counts* counts);
+/* rows[c * n + r] = single_hyp_test((n_exclusive[r], n_match[r]), ksize, significance, ani, cov[c]) */
+int ygpu_hyp_test(ygpu_ctx* ctx, const int64_t* n_exclusive, const int64_t* n_match, uint64_t n,
+                  int ksize, double significance, double ani_thresh, const double* min_coverage,
+                  int n_cov, ygpu_hyp_row* rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YACHT_GPU_H */

@@ -1,0 +1,91 @@
+"""GPU parity of the train hot path (K2 index build, K3+K4 count/flag) against the CPU oracle.
+
+Bar: bit-exact on shared-hash counts, flagged ordered pairs and index statistics.
+All calls go through the C ABI (ctypes on libyachtgpu.so).
+"""
+import numpy as np
+import pytest
+
+from oracle import train_oracle as to
+from yacht_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+THR = 0.95 ** 31
+
+
+def _pairs_tuple(p):
+    return [(int(a), int(b), int(c)) for a, b, c in zip(p["i"], p["j"], p["count"])]
+
+
+def _check(ctx, db, thr):
+    ctx.load_sketches(db.hashes, db.offsets)
+    st = ctx.build_index()
+    got = ctx.pairwise_flag(thr)
+    ref = to.oracle_train(db.hashes, db.offsets, thr)
+    assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index)
+    assert st["n_postings"] == ref.n_postings
+    assert st["n_increments"] == ref.n_increments
+    assert _pairs_tuple(got) == _pairs_tuple(ref.pairs)
+    return st, got
+
+
+def test_edge_set(gpu_ctx):
+    # SURVEY.md appendix B hand-made set: identical twins, an empty sketch, duplicates inside a sketch
+    parts = [np.arange(1, 11), np.arange(1, 11), np.zeros(0), np.array([1, 2, 3, 4, 5] + list(range(100, 107))),
+             np.array([7, 7, 7, 200])]
+    db = synth.from_sketches([np.asarray(p, dtype=np.uint64) for p in parts])
+    st, got = _check(gpu_ctx, db, 0.4)
+    assert st["has_duplicates"] == 1
+    assert len(got) == 8
+    _check(gpu_ctx, db, 0.0)
+    _check(gpu_ctx, db, 1.0)
+
+
+def test_empty_and_trivial(gpu_ctx):
+    db = synth.from_sketches([np.zeros(0, dtype=np.uint64)] * 3)
+    _check(gpu_ctx, db, 0.5)
+    db = synth.from_sketches([np.array([5, 9], dtype=np.uint64)])
+    _check(gpu_ctx, db, 0.5)
+    db = synth.from_sketches([])
+    gpu_ctx.load_sketches(db.hashes, db.offsets)
+    gpu_ctx.build_index()
+    assert len(gpu_ctx.pairwise_flag(0.1)) == 0
+
+
+def test_full_range_hashes(gpu_ctx):
+    big = np.array([0, 1, 2**63, 2**64 - 1], dtype=np.uint64)
+    db = synth.from_sketches([big, big[1:], big[:2], np.array([2**64 - 1], dtype=np.uint64)])
+    _check(gpu_ctx, db, 0.0)
+    _check(gpu_ctx, db, 0.5)
+
+
+@pytest.mark.parametrize("n,seed,mean", [(300, 1, 600), (1000, 7, 600), (2000, 11, 1500)])
+def test_synthetic_flagged_pairs(gpu_ctx, n, seed, mean):
+    db = synth.make_reference_db(n, seed, mean_size=mean, sd_size=mean / 3)
+    _check(gpu_ctx, db, THR)
+
+
+@pytest.mark.parametrize("n,seed", [(400, 3)])
+def test_synthetic_all_counts(gpu_ctx, n, seed):
+    # threshold 0 emits every ordered pair with a non-zero count: the whole count matrix
+    db = synth.make_reference_db(n, seed, mean_size=500, sd_size=100)
+    _check(gpu_ctx, db, 0.0)
+
+
+def test_row_ranges_union(gpu_ctx):
+    db = synth.make_reference_db(1000, 5, mean_size=600, sd_size=200)
+    gpu_ctx.load_sketches(db.hashes, db.offsets)
+    gpu_ctx.build_index()
+    full = gpu_ctx.pairwise_flag(THR)
+    b = gpu_ctx.row_partition(4)
+    assert b[0] == 0 and b[-1] == db.n and all(b[k] <= b[k + 1] for k in range(4))
+    parts = [gpu_ctx.pairwise_flag(THR, int(b[k]), int(b[k + 1])) for k in range(4)]
+    merged = np.sort(np.concatenate(parts), order=["i", "j"])
+    assert _pairs_tuple(merged) == _pairs_tuple(full)
+
+
+def test_skewed_long_postings(gpu_ctx):
+    # conserved-core hashes present in many genomes: long posting lists, touched-list overflow
+    db = synth.make_reference_db(6000, 9, mean_size=60, sd_size=10, min_size=20, core_hashes=6, core_lo=0.7, core_hi=0.95)
+    _check(gpu_ctx, db, 0.05)

@@ -1,0 +1,210 @@
+"""ctypes binding of libyachtgpu.so (the C ABI declared in include/yacht_gpu.h).
+
+This is the only place the Python host layer touches device code.  There is no CPU fallback:
+if the shared library is missing, or no B200 is visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libyachtgpu.so")
+
+# every symbol include/yacht_gpu.h declares (tests check the library exports each of them)
+ABI_SYMBOLS = [
+    "ygpu_device_count", "ygpu_ctx_create", "ygpu_ctx_destroy", "ygpu_last_error", "ygpu_free",
+    "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
+    "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_row_partition", "ygpu_exclusive_hashes",
+    "ygpu_hyp_test",
+]
+
+
+class YgpuError(RuntimeError):
+    pass
+
+
+class IndexStats(ctypes.Structure):
+    _fields_ = [("n_hashes", ctypes.c_uint64), ("n_distinct", ctypes.c_uint64), ("n_singleton", ctypes.c_uint64),
+                ("n_index", ctypes.c_uint64), ("n_postings", ctypes.c_uint64), ("n_increments", ctypes.c_uint64),
+                ("n_row_items", ctypes.c_uint64), ("max_sketch", ctypes.c_uint32), ("has_duplicates", ctypes.c_uint32)]
+
+    def as_dict(self) -> dict:
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [("ms_h2d", ctypes.c_double), ("ms_sort", ctypes.c_double), ("ms_index", ctypes.c_double),
+                ("ms_count", ctypes.c_double), ("ms_d2h", ctypes.c_double), ("ms_sample", ctypes.c_double),
+                ("ms_stats", ctypes.c_double), ("n_count_launches", ctypes.c_uint64),
+                ("n_kernel_launches", ctypes.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {k: (float(getattr(self, k)) if t is ctypes.c_double else int(getattr(self, k))) for k, t in self._fields_}
+
+
+PAIR_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("count", "<i4")])
+GENOME_COUNTS_DTYPE = np.dtype([("n_overlap", "<u4"), ("nontrivial", "<u4"), ("n_exclusive", "<u4"), ("n_match", "<u4")])
+HYP_ROW_DTYPE = np.dtype([
+    ("in_sample_est", "<i4"), ("_pad", "<i4"), ("p_val", "<f8"), ("num_exclusive_kmers", "<i8"),
+    ("num_exclusive_kmers_coverage", "<i8"), ("num_matches", "<i8"),
+    ("acceptance_threshold_with_coverage", "<f8"), ("actual_confidence_with_coverage", "<f8"),
+    ("alt_confidence_mut_rate_with_coverage", "<f8"),
+])
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libyachtgpu.so from the package directory (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YgpuError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C yacht_b200/csrc). There is no CPU fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
+    lib.ygpu_device_count.restype = ctypes.c_int
+    lib.ygpu_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    lib.ygpu_ctx_destroy.argtypes = [vp]
+    lib.ygpu_ctx_destroy.restype = None
+    lib.ygpu_last_error.argtypes = [vp]
+    lib.ygpu_last_error.restype = ctypes.c_char_p
+    lib.ygpu_free.argtypes = [vp]
+    lib.ygpu_free.restype = None
+    lib.ygpu_reset_timers.argtypes = [vp]
+    lib.ygpu_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
+    lib.ygpu_load_sketches.argtypes = [vp, vp, vp, u32]
+    lib.ygpu_load_sketches_device.argtypes = [vp, vp, vp, u32]
+    lib.ygpu_build_index.argtypes = [vp, ctypes.POINTER(IndexStats)]
+    lib.ygpu_pairwise_flag.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    lib.ygpu_row_partition.argtypes = [vp, u32, vp]
+    lib.ygpu_exclusive_hashes.argtypes = [vp, vp, u64, vp, vp]
+    lib.ygpu_hyp_test.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, ctypes.c_double, vp, ctypes.c_int, vp]
+    for name in ABI_SYMBOLS:
+        getattr(lib, name)  # AttributeError here means the .so does not match include/yacht_gpu.h
+    _lib = lib
+    return lib
+
+
+class GpuContext:
+    """One GPU's worth of the hot path: resident sketches, inverted index, pair flagging, run stats."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.ygpu_ctx_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            msg = self.lib.ygpu_last_error(None)
+            raise YgpuError(f"ygpu_ctx_create(device={device}) failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+        self.device = device
+        self.n = 0
+        self._keep = None
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.ygpu_last_error(self.h)
+            raise YgpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.ygpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset_timers(self) -> None:
+        self._check(self.lib.ygpu_reset_timers(self.h), "ygpu_reset_timers")
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self.lib.ygpu_get_timings(self.h, ctypes.byref(t)), "ygpu_get_timings")
+        return t.as_dict()
+
+    # -- train path ---------------------------------------------------------------------------
+    def load_sketches(self, hashes: np.ndarray, offsets: np.ndarray) -> None:
+        """Host arrays (numpy uint64) -> device.  hashes[offsets[g]:offsets[g+1]] is sketch g."""
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        self._check(self.lib.ygpu_load_sketches(self.h, hashes.ctypes.data, offsets.ctypes.data, n), "ygpu_load_sketches")
+        self.n = n
+
+    def load_sketches_device(self, d_hashes_ptr: int, d_offsets_ptr: int, n: int) -> None:
+        """Device pointers (e.g. torch tensors' data_ptr() on this context's device)."""
+        self._check(self.lib.ygpu_load_sketches_device(self.h, d_hashes_ptr, d_offsets_ptr, n), "ygpu_load_sketches_device")
+        self.n = n
+
+    def build_index(self) -> dict:
+        st = IndexStats()
+        self._check(self.lib.ygpu_build_index(self.h, ctypes.byref(st)), "ygpu_build_index")
+        return st.as_dict()
+
+    def pairwise_flag(self, threshold: float, row_begin: int = 0, row_end: Optional[int] = None) -> np.ndarray:
+        """Flagged ordered pairs (structured array i, j, count), sorted by (i, j)."""
+        if row_end is None:
+            row_end = self.n
+        out = ctypes.c_void_p()
+        n_out = ctypes.c_uint64()
+        self._check(self.lib.ygpu_pairwise_flag(self.h, float(threshold), int(row_begin), int(row_end),
+                                                ctypes.byref(out), ctypes.byref(n_out)), "ygpu_pairwise_flag")
+        try:
+            k = int(n_out.value)
+            if k == 0:
+                return np.zeros(0, dtype=PAIR_DTYPE)
+            buf = ctypes.string_at(out, k * PAIR_DTYPE.itemsize)
+            return np.frombuffer(buf, dtype=PAIR_DTYPE).copy()
+        finally:
+            self.lib.ygpu_free(out)
+
+    def row_partition(self, nparts: int) -> np.ndarray:
+        b = np.zeros(nparts + 1, dtype=np.uint32)
+        self._check(self.lib.ygpu_row_partition(self.h, int(nparts), b.ctypes.data), "ygpu_row_partition")
+        return b
+
+    # -- run path -----------------------------------------------------------------------------
+    def exclusive_hashes(self, sample: np.ndarray, mask: Optional[np.ndarray] = None) -> np.ndarray:
+        sample = np.ascontiguousarray(sample, dtype=np.uint64)
+        counts = np.zeros(self.n, dtype=GENOME_COUNTS_DTYPE)
+        mptr = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mask.shape[0] != self.n:
+                raise ValueError("mask must have one entry per loaded genome")
+            mptr = mask.ctypes.data
+        self._check(self.lib.ygpu_exclusive_hashes(self.h, sample.ctypes.data, sample.shape[0], mptr,
+                                                   counts.ctypes.data), "ygpu_exclusive_hashes")
+        return counts
+
+    def hyp_test(self, n_exclusive: Sequence[int], n_match: Sequence[int], ksize: int, significance: float,
+                 ani_thresh: float, min_coverage: Sequence[float]) -> np.ndarray:
+        """rows[c, r] = single_hyp_test((n_exclusive[r], n_match[r]), ksize, significance, ani, cov[c])."""
+        ne = np.ascontiguousarray(n_exclusive, dtype=np.int64)
+        nm = np.ascontiguousarray(n_match, dtype=np.int64)
+        cov = np.ascontiguousarray(min_coverage, dtype=np.float64)
+        rows = np.zeros((cov.shape[0], ne.shape[0]), dtype=HYP_ROW_DTYPE)
+        self._check(self.lib.ygpu_hyp_test(self.h, ne.ctypes.data, nm.ctypes.data, ne.shape[0], int(ksize),
+                                           float(significance), float(ani_thresh), cov.ctypes.data, cov.shape[0],
+                                           rows.ctypes.data), "ygpu_hyp_test")
+        return rows
+
+
+def device_count() -> int:
+    return int(load_library().ygpu_device_count())

@@ -1,0 +1,788 @@
+// libyachtgpu -- train path: context, sketch residency, inverted index (K2), pairwise
+// shared-hash count fused with threshold + compaction (K3+K4).  sm_100a only.
+//
+// Reference behaviour being replaced: KoslickiLab/YACHT src/cpp/main.cpp
+//   compute_index_from_sketches            :215-246  -> ygpu_build_index
+//   compute_intersection_matrix_by_sketches:249-312  -> ygpu_pairwise_flag
+// This is a new design, not a translation: the reference walks an unordered_map per query hash
+// and increments a dense N x N int matrix on the host; here the index is a radix-sorted
+// (hash, genome) array whose equal-hash runs ARE the posting lists, every genome gets a compact
+// list of "the postings that follow me in my run" (upper triangle only: M is symmetric), and one
+// CTA per query genome accumulates its row in shared memory and emits only the pairs that pass
+// the containment threshold.
+#include "common.cuh"
+
+#include <cub/cub.cuh>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+static std::string g_create_err;
+
+int ygpu_fail(ygpu_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+
+int ygpu_temp_reserve(ygpu_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->temp_bytes) return 0;
+    if (ctx->d_temp) cudaFree(ctx->d_temp);
+    ctx->d_temp = nullptr;
+    ctx->temp_bytes = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    YG_CUDA(ctx, cudaMalloc(&ctx->d_temp, want));
+    ctx->temp_bytes = want;
+    return 0;
+}
+
+template <typename T>
+static int dev_alloc(ygpu_ctx* ctx, T** p, uint64_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(%llu bytes): %s",
+                         (unsigned long long)(count * sizeof(T)), cudaGetErrorString(e));
+    }
+    return 0;
+}
+template <typename T>
+static void dev_free(T** p) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+static float elapsed(ygpu_ctx* ctx, int a, int b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+    return ms;
+}
+
+// ============================================================================================
+// context
+// ============================================================================================
+extern "C" int ygpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int ygpu_ctx_create(ygpu_ctx** out, int device) {
+    if (!out) return ygpu_fail(nullptr, YGPU_ERR_ARG, "ygpu_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return ygpu_fail(nullptr, YGPU_ERR_NO_DEVICE,
+                         "no CUDA device available (%s); libyachtgpu has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev)
+        return ygpu_fail(nullptr, YGPU_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    ygpu_ctx* ctx = new (std::nothrow) ygpu_ctx();
+    if (!ctx) return ygpu_fail(nullptr, YGPU_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        delete ctx;
+        return ygpu_fail(nullptr, YGPU_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete ctx;
+        return ygpu_fail(nullptr, YGPU_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        delete ctx;
+        return ygpu_fail(nullptr, YGPU_ERR_NO_DEVICE,
+                         "device %d is sm_%d%d; libyachtgpu is built for sm_100a (B200) only", device,
+                         prop.major, prop.minor);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return ygpu_fail(nullptr, YGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (cudaMalloc(&ctx->d_scalars, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        ygpu_ctx_destroy(ctx);
+        return ygpu_fail(nullptr, YGPU_ERR_NOMEM, "cudaMalloc(scalars) failed");
+    }
+    *out = ctx;
+    return 0;
+}
+
+static void release_index(ygpu_ctx* ctx) {
+    dev_free(&ctx->d_skey); dev_free(&ctx->d_sgid); dev_free(&ctx->d_flag); dev_free(&ctx->d_cpos);
+    dev_free(&ctx->d_post); dev_free(&ctx->d_rem); dev_free(&ctx->d_row_ptr); dev_free(&ctx->d_row_items);
+    dev_free(&ctx->d_row_work);
+    ctx->indexed = false;
+    ctx->P = 0; ctx->n_items = 0;
+}
+
+static void release_sketches(ygpu_ctx* ctx) {
+    release_index(ctx);
+    dev_free(&ctx->d_hashes); dev_free(&ctx->d_offsets); dev_free(&ctx->d_sizes); dev_free(&ctx->d_gid);
+    ctx->loaded = false;
+    ctx->n = 0; ctx->T = 0;
+}
+
+extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release_sketches(ctx);
+    ygpu_run_release(ctx);
+    dev_free(&ctx->d_out_key); dev_free(&ctx->d_out_cnt); dev_free(&ctx->d_out_key2); dev_free(&ctx->d_out_cnt2);
+    if (ctx->d_temp) cudaFree(ctx->d_temp);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* ygpu_last_error(const ygpu_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" void ygpu_free(void* p) { free(p); }
+
+extern "C" int ygpu_reset_timers(ygpu_ctx* ctx) {
+    if (!ctx) return YGPU_ERR_ARG;
+    ctx->tm = ygpu_timings{};
+    return 0;
+}
+
+extern "C" int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out) {
+    if (!ctx || !out) return YGPU_ERR_ARG;
+    *out = ctx->tm;
+    return 0;
+}
+
+// ============================================================================================
+// sketch residency
+// ============================================================================================
+// one CTA per genome (grid-stride): genome id of every hash slot + sketch sizes
+__global__ void __launch_bounds__(256) k_expand_gid(const uint64_t* __restrict__ offsets, uint32_t n,
+                                                     uint32_t* __restrict__ gid, uint32_t* __restrict__ sizes) {
+    for (uint32_t g = blockIdx.x; g < n; g += gridDim.x) {
+        const uint64_t b = offsets[g], e = offsets[g + 1];
+        if (threadIdx.x == 0) sizes[g] = (uint32_t)(e - b);
+        for (uint64_t p = b + threadIdx.x; p < e; p += blockDim.x) gid[p] = g;
+    }
+}
+
+static int finish_load(ygpu_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sizes, n));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_gid, ctx->T));
+    if (n) {
+        int grid = (int)std::min<uint32_t>(n, (uint32_t)ctx->num_sms * 16);
+        k_expand_gid<<<grid, 256, 0, ctx->stream>>>(ctx->d_offsets, n, ctx->d_gid, ctx->d_sizes);
+        ctx->tm.n_kernel_launches++;
+        YG_CUDA(ctx, cudaGetLastError());
+    }
+    YG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->loaded = true;
+    return 0;
+}
+
+static int load_common(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* offsets, uint32_t n, bool from_device) {
+    if (!ctx) return YGPU_ERR_ARG;
+    if (!offsets || (n > 0 && !hashes && false)) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches: NULL offsets");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    release_sketches(ctx);
+    uint64_t T = 0;
+    if (from_device) {
+        YG_CUDA(ctx, cudaMemcpy(&T, offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    } else {
+        T = offsets[n];
+        for (uint32_t g = 0; g < n; g++)
+            if (offsets[g + 1] < offsets[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+        if (offsets[0] != 0) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets[0] must be 0");
+    }
+    if (T >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)T);
+    if (n >= (1u << 31)) return ygpu_fail(ctx, YGPU_ERR_ARG, "too many genomes");
+    if (T > 0 && !hashes) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches: NULL hashes");
+    ctx->n = n;
+    ctx->T = T;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_hashes, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
+    cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (T) YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_hashes, hashes, T * sizeof(uint64_t), kind, ctx->stream));
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), kind, ctx->stream));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    YG_CHECK(finish_load(ctx));
+    ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
+    return 0;
+}
+
+extern "C" int ygpu_load_sketches(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* offsets, uint32_t n) {
+    return load_common(ctx, hashes, offsets, n, false);
+}
+extern "C" int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n) {
+    return load_common(ctx, d_hashes, d_offsets, n, true);
+}
+
+// ============================================================================================
+// K2: inverted index
+// ============================================================================================
+enum { SC_HEADS = 0, SC_SINGLE = 1, SC_DUPS = 2, SC_W = 3, SC_OUT = 4, SC_UNIT = 5, SC_MAXKEY = 6 };
+
+template <int BS>
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {
+    __shared__ unsigned long long sh[BS / 32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = 0;
+    if (w == 0) {
+        v = (l < BS / 32) ? sh[l] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;  // valid in thread 0
+}
+
+// flag[s] = 1 iff sorted slot s lies in a run (equal hashes) of length >= 2.  Also counts the
+// distinct hashes, the singletons (the three banner lines of main.cpp:242-244) and in-sketch
+// duplicates (same hash twice in one genome).
+__global__ void __launch_bounds__(256) k_flag_runs(const uint64_t* __restrict__ key, const uint32_t* __restrict__ sgid,
+                                                    uint64_t T, uint8_t* __restrict__ flag,
+                                                    unsigned long long* __restrict__ scal) {
+    unsigned long long heads = 0, singles = 0, dups = 0;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < T; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = key[s];
+        const bool peq = s > 0 && key[s - 1] == k;
+        const bool neq = s + 1 < T && key[s + 1] == k;
+        flag[s] = (peq || neq) ? 1 : 0;
+        heads += !peq;
+        singles += (!peq && !neq);
+        if (peq && sgid[s - 1] == sgid[s]) dups++;
+    }
+    heads = block_sum<256>(heads);
+    singles = block_sum<256>(singles);
+    dups = block_sum<256>(dups);
+    if (threadIdx.x == 0) {
+        if (heads) atomicAdd(&scal[SC_HEADS], heads);
+        if (singles) atomicAdd(&scal[SC_SINGLE], singles);
+        if (dups) atomicAdd(&scal[SC_DUPS], dups);
+    }
+}
+
+// first slot e > s with key[e] != key[s] (exponential probe, then bisection)
+__device__ __forceinline__ uint64_t run_end(const uint64_t* __restrict__ key, uint64_t s, uint64_t T) {
+    const uint64_t k = key[s];
+    uint64_t lo = s, step = 1, hi = s + 1;
+    while (hi < T && key[hi] == k) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > T) hi = T;
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (key[mid] == k) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+struct FlagToU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint8_t& f) const { return (uint32_t)f; }
+};
+
+// every kept slot: copy its genome id into the compact posting array, record how many postings
+// follow it in its run (that is the work row `g` does for this hash: upper triangle only), and
+// histogram non-empty work items per genome.
+__global__ void __launch_bounds__(256) k_post_compact(const uint64_t* __restrict__ key, const uint32_t* __restrict__ sgid,
+                                                       const uint8_t* __restrict__ flag, const uint32_t* __restrict__ cpos,
+                                                       uint64_t T, uint32_t* __restrict__ post, uint32_t* __restrict__ rem,
+                                                       unsigned long long* __restrict__ row_cnt,
+                                                       unsigned long long* __restrict__ row_work,
+                                                       unsigned long long* __restrict__ scal) {
+    unsigned long long w = 0;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < T; s += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[s]) continue;
+        const uint32_t g = sgid[s];
+        const uint32_t c = cpos[s];
+        const uint64_t e = run_end(key, s, T);
+        const uint32_t r = (uint32_t)(e - s - 1);
+        post[c] = g;
+        rem[c] = r;
+        w += 2ull * r + 1ull;  // sum over the members of a run of (2*rem+1) == L^2
+        if (r) {
+            atomicAdd(&row_cnt[g], 1ull);
+            atomicAdd(&row_work[g], (unsigned long long)r);
+        }
+    }
+    w = block_sum<256>(w);
+    if (threadIdx.x == 0 && w) atomicAdd(&scal[SC_W], w);
+}
+
+__global__ void __launch_bounds__(256) k_items_scatter(const uint32_t* __restrict__ post, const uint32_t* __restrict__ rem,
+                                                        uint64_t P, const uint64_t* __restrict__ row_ptr,
+                                                        unsigned long long* __restrict__ row_fill,
+                                                        uint64_t* __restrict__ row_items) {
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < P; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = rem[c];
+        if (!r) continue;
+        const uint32_t g = post[c];
+        const unsigned long long k = atomicAdd(&row_fill[g], 1ull);
+        row_items[row_ptr[g] + k] = ((uint64_t)(c + 1) << 32) | (uint64_t)r;
+    }
+}
+
+static int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8) {
+    uint64_t blocks = (work + bs - 1) / bs;
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
+    if (!ctx) return YGPU_ERR_ARG;
+    if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "build_index: no sketches loaded");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    release_index(ctx);
+    const uint64_t T = ctx->T;
+    const uint32_t n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    ygpu_index_stats S{};
+    S.n_hashes = T;
+
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_ptr, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_work, n));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_ptr, 0, ((uint64_t)n + 1) * sizeof(uint64_t), st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_work, 0, std::max<uint64_t>(n, 1) * sizeof(uint64_t), st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
+
+    if (T == 0 || n == 0) {
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (n) {
+            std::vector<uint32_t> sz(n);
+            YG_CUDA(ctx, cudaMemcpy(sz.data(), ctx->d_sizes, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        }
+        ctx->stats = S;
+        ctx->indexed = true;
+        if (stats) *stats = S;
+        return 0;
+    }
+
+    // ---- K2a: stable radix sort of (hash, genome id); equal-hash runs become posting lists in
+    //      ascending genome order (slots are generated genome-major, the sort is stable).
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_skey, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sgid, T));
+    uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        ctx->tm.n_kernel_launches += 2;
+    }
+    uint64_t maxkey = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    int end_bit = 1;
+    while (end_bit < 64 && (maxkey >> end_bit) != 0) end_bit++;
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
+                                                     (int64_t)T, 0, end_bit, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
+                                                     (int64_t)T, 0, end_bit, st));
+        ctx->tm.n_kernel_launches += 2 + (end_bit + 7) / 8;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+
+    // ---- K2b: runs -> compact postings + per-genome work lists
+    YG_CHECK(dev_alloc(ctx, &ctx->d_flag, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_cpos, T + 1));
+    k_flag_runs<<<grid_for(ctx, T, 256), 256, 0, st>>>(ctx->d_skey, ctx->d_sgid, T, ctx->d_flag, ctx->d_scalars);
+    YG_CUDA(ctx, cudaGetLastError());
+    {
+        cub::TransformInputIterator<uint32_t, FlagToU32, const uint8_t*> it(ctx->d_flag, FlagToU32());
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, it, ctx->d_cpos, (int64_t)T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, it, ctx->d_cpos, (int64_t)T, st));
+        ctx->tm.n_kernel_launches += 3;
+    }
+    uint32_t last_cpos = 0;
+    uint8_t last_flag = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(&last_cpos, ctx->d_cpos + (T - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(&last_flag, ctx->d_flag + (T - 1), sizeof(uint8_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t P = (uint64_t)last_cpos + last_flag;
+    ctx->P = P;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_post, P));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_rem, P));
+    unsigned long long* d_row_cnt = nullptr;
+    YG_CHECK(dev_alloc(ctx, &d_row_cnt, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaMemsetAsync(d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    if (P) {
+        k_post_compact<<<grid_for(ctx, T, 256), 256, 0, st>>>(ctx->d_skey, ctx->d_sgid, ctx->d_flag, ctx->d_cpos, T,
+                                                              ctx->d_post, ctx->d_rem, d_row_cnt,
+                                                              (unsigned long long*)ctx->d_row_work, ctx->d_scalars);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+    }
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
+        ctx->tm.n_kernel_launches += 2;
+    }
+    unsigned long long sc[16];
+    uint64_t n_items = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(&n_items, ctx->d_row_ptr + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_items = n_items;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, n_items));
+    if (n_items) {
+        YG_CUDA(ctx, cudaMemsetAsync(d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+        k_items_scatter<<<grid_for(ctx, P, 256), 256, 0, st>>>(ctx->d_post, ctx->d_rem, P, ctx->d_row_ptr, d_row_cnt,
+                                                               ctx->d_row_items);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(d_row_cnt);
+    ctx->tm.n_kernel_launches += 1;  // k_flag_runs
+    ctx->tm.ms_sort += elapsed(ctx, 0, 1);
+    ctx->tm.ms_index += elapsed(ctx, 1, 2);
+
+    // sorted keys / flags / scan are only needed while building (the run path re-sorts with its
+    // own mask); release them so an 85k-genome index leaves HBM to the count kernel's output.
+    dev_free(&ctx->d_flag);
+    dev_free(&ctx->d_cpos);
+    dev_free(&ctx->d_rem);
+
+    std::vector<uint32_t> sz(n);
+    YG_CUDA(ctx, cudaMemcpy(sz.data(), ctx->d_sizes, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint32_t mx = 0;
+    for (uint32_t v : sz) mx = std::max(mx, v);
+
+    S.n_distinct = sc[SC_HEADS];
+    S.n_singleton = sc[SC_SINGLE];
+    S.n_index = S.n_distinct - S.n_singleton;
+    S.n_postings = P;
+    S.n_increments = sc[SC_W];
+    S.n_row_items = n_items;
+    S.max_sketch = mx;
+    S.has_duplicates = sc[SC_DUPS] ? 1u : 0u;
+    ctx->stats = S;
+    ctx->indexed = true;
+    if (stats) *stats = S;
+    return 0;
+}
+
+// ============================================================================================
+// K3 + K4: pairwise shared-hash count (row-wise integer SpGEMM over the inverted index, upper
+// triangle) fused with the containment threshold and compaction of the flagged ordered pairs.
+// ============================================================================================
+#define K3_THREADS 256
+#define K3_TOUCH_CAP 4096      // distinct columns tracked per (row, tile) before falling back to a dense scan
+#define K3_LONG_CAP 256        // posting segments longer than K3_LONG_LEN are expanded by the whole CTA
+#define K3_LONG_LEN 64
+
+struct K3Params {
+    const uint64_t* row_ptr;
+    const uint64_t* row_items;
+    const uint32_t* post;
+    const uint32_t* sizes;
+    uint32_t n;
+    uint32_t row_begin, row_end;
+    uint32_t tile_w;       // columns per tile
+    uint32_t n_tiles;
+    double thr;
+    uint64_t* out_key;     // (i << 32) | j
+    uint32_t* out_cnt;
+    uint64_t out_cap;
+    unsigned long long* scal;  // SC_OUT = pairs emitted, SC_UNIT = work-unit ticket
+};
+
+// warp-aggregated append: one atomic per warp-instruction instead of one per lane
+__device__ __forceinline__ void emit_pair(const K3Params& p, uint32_t i, uint32_t j, uint32_t cnt) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&p.scal[SC_OUT], (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot < p.out_cap) {
+        p.out_key[slot] = ((uint64_t)i << 32) | (uint64_t)j;
+        p.out_cnt[slot] = cnt;
+    }
+}
+
+// the reference's test for one unordered pair {i<j} with `cnt` shared hashes, both directions
+// (main.cpp:277-303).  The "union" is evaluated modulo 2^64 exactly as size_t + size_t - int is.
+__device__ __forceinline__ void test_pair(const K3Params& p, uint32_t i, uint32_t j, uint32_t cnt) {
+    const uint32_t ni = p.sizes[i], nj = p.sizes[j];
+    if (ni == 0 || nj == 0) return;
+    const uint64_t uni = (uint64_t)ni + (uint64_t)nj - (uint64_t)(int64_t)(int32_t)cnt;
+    if (uni == 0) return;
+    const double m = 1.0 * (double)(int32_t)cnt;
+    const double cij = m / (double)ni;
+    const double cji = m / (double)nj;
+    if (!(cij < p.thr)) emit_pair(p, i, j, cnt);
+    if (!(cji < p.thr)) emit_pair(p, j, i, cnt);
+}
+
+template <bool U16>
+__device__ __forceinline__ uint32_t acc_add(uint32_t* acc, uint32_t col) {
+    if (U16) {
+        const uint32_t sh = (col & 1u) << 4;
+        const uint32_t old = atomicAdd(&acc[col >> 1], 1u << sh);
+        return (old >> sh) & 0xffffu;
+    } else {
+        return atomicAdd(&acc[col], 1u);
+    }
+}
+template <bool U16>
+__device__ __forceinline__ uint32_t acc_take(uint32_t* acc, uint32_t col) {
+    if (U16) {
+        const uint32_t sh = (col & 1u) << 4;
+        const uint32_t old = atomicAnd(&acc[col >> 1], ~(0xffffu << sh));
+        return (old >> sh) & 0xffffu;
+    } else {
+        const uint32_t v = acc[col];
+        acc[col] = 0;
+        return v;
+    }
+}
+
+template <bool U16>
+__global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t acc_words = U16 ? (p.tile_w + 1) / 2 : p.tile_w;
+    uint32_t* acc = smem;                               // [acc_words] dense row accumulator
+    uint32_t* touched = acc + acc_words;                // [K3_TOUCH_CAP]
+    uint64_t* longq = (uint64_t*)(touched + K3_TOUCH_CAP + (acc_words & 1u));  // 8-byte aligned
+    __shared__ uint32_t s_nt, s_nlong;
+    __shared__ unsigned long long s_unit;
+
+    for (uint32_t c = threadIdx.x; c < acc_words; c += K3_THREADS) acc[c] = 0;
+    if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
+    __syncthreads();
+
+    const unsigned long long n_units = (unsigned long long)(p.row_end - p.row_begin) * p.n_tiles;
+    for (;;) {
+        if (threadIdx.x == 0) s_unit = atomicAdd(&p.scal[SC_UNIT], 1ull);
+        __syncthreads();
+        const unsigned long long unit = s_unit;
+        if (unit >= n_units) break;
+        const uint32_t row = p.row_begin + (uint32_t)(unit / p.n_tiles);
+        const uint32_t tile = (uint32_t)(unit % p.n_tiles);
+        const uint32_t c0 = tile * p.tile_w;
+        const uint32_t c1 = min(p.n, c0 + p.tile_w);
+        const uint64_t ib = p.row_ptr[row], ie = p.row_ptr[row + 1];
+        // upper triangle: only columns > row matter
+        if (c1 > row + 1 && ie > ib) {
+            // ---- accumulate -----------------------------------------------------------------
+            for (uint64_t it = ib + threadIdx.x; it < ie; it += K3_THREADS) {
+                const uint64_t item = p.row_items[it];
+                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)item;
+                if (len > K3_LONG_LEN) {
+                    const uint32_t q = atomicAdd(&s_nlong, 1u);
+                    if (q < K3_LONG_CAP) { longq[q] = item; continue; }
+                }
+                for (uint32_t e = 0; e < len; e++) {
+                    const uint32_t g = p.post[start + e];
+                    if (g <= row || g < c0 || g >= c1) continue;   // g == row: duplicate hash inside the sketch
+                    if (acc_add<U16>(acc, g - c0) == 0) {
+                        const uint32_t k = atomicAdd(&s_nt, 1u);
+                        if (k < K3_TOUCH_CAP) touched[k] = g;
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t nlong = min(s_nlong, (uint32_t)K3_LONG_CAP);
+            for (uint32_t q = 0; q < nlong; q++) {
+                const uint64_t item = longq[q];
+                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)item;
+                for (uint32_t e = threadIdx.x; e < len; e += K3_THREADS) {
+                    const uint32_t g = p.post[start + e];
+                    if (g <= row || g < c0 || g >= c1) continue;
+                    if (acc_add<U16>(acc, g - c0) == 0) {
+                        const uint32_t k = atomicAdd(&s_nt, 1u);
+                        if (k < K3_TOUCH_CAP) touched[k] = g;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- threshold + compaction (K4), and reset of the accumulator ---------------------
+            const uint32_t nt = s_nt;
+            if (nt <= K3_TOUCH_CAP) {
+                for (uint32_t k = threadIdx.x; k < nt; k += K3_THREADS) {
+                    const uint32_t g = touched[k];
+                    const uint32_t cnt = acc_take<U16>(acc, g - c0);
+                    test_pair(p, row, g, cnt);
+                }
+            } else {
+                const uint32_t w = c1 - c0;
+                for (uint32_t c = threadIdx.x; c < w; c += K3_THREADS) {
+                    const uint32_t cnt = acc_take<U16>(acc, c);
+                    if (cnt) test_pair(p, row, c0 + c, cnt);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack_pairs(const uint64_t* __restrict__ key, const uint32_t* __restrict__ cnt,
+                                                     uint64_t n, ygpu_pair* __restrict__ out) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t kk = key[k];
+        ygpu_pair pr;
+        pr.i = (int32_t)(kk >> 32);
+        pr.j = (int32_t)(kk & 0xffffffffu);
+        pr.count = (int32_t)cnt[k];
+        out[k] = pr;
+    }
+}
+
+static int ensure_out(ygpu_ctx* ctx, uint64_t cap) {
+    if (cap <= ctx->out_cap) return 0;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_out_key, cap));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_out_cnt, cap));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_out_key2, cap));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_out_cnt2, cap));
+    ctx->out_cap = cap;
+    return 0;
+}
+
+extern "C" int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end,
+                                  ygpu_pair** out, uint64_t* n_out) {
+    if (!ctx || !out || !n_out) return YGPU_ERR_ARG;
+    *out = nullptr;
+    *n_out = 0;
+    if (!ctx->indexed) return ygpu_fail(ctx, YGPU_ERR_STATE, "pairwise_flag: build_index first");
+    if (row_begin > row_end || row_end > ctx->n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad row range [%u,%u) of %u", row_begin, row_end, ctx->n);
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = ctx->n;
+    uint64_t npairs = 0;
+
+    if (ctx->n_items && row_end > row_begin) {
+        // ---- accumulator geometry -------------------------------------------------------------
+        const uint32_t fixed = K3_TOUCH_CAP * 4 + K3_LONG_CAP * 8 + 64;
+        const uint32_t budget = (uint32_t)ctx->smem_optin - fixed - 1024;
+        const bool u16_ok = !ctx->stats.has_duplicates && ctx->stats.max_sketch <= 65535u;
+        bool use_u16 = false;
+        uint32_t tile_w = n;
+        if ((uint64_t)n * 4 > budget) {
+            if (u16_ok && (uint64_t)n * 2 <= budget) use_u16 = true;
+            else if (u16_ok) { use_u16 = true; tile_w = (budget / 2) & ~1u; }
+            else tile_w = budget / 4;
+        }
+        const uint32_t n_tiles = (n + tile_w - 1) / tile_w;
+        const uint32_t acc_words = use_u16 ? (tile_w + 1) / 2 : tile_w;
+        const size_t smem = (size_t)(acc_words + (acc_words & 1u)) * 4 + fixed;
+        auto kern = use_u16 ? k3_count_flag<true> : k3_count_flag<false>;
+        YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K3_THREADS, smem));
+        if (occ < 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "k3_count_flag does not fit: smem %zu", smem);
+        const unsigned long long units = (unsigned long long)(row_end - row_begin) * n_tiles;
+        const int grid = (int)std::min<unsigned long long>((unsigned long long)ctx->num_sms * occ, units);
+
+        uint64_t cap = std::max<uint64_t>(ctx->out_cap, std::max<uint64_t>(1u << 20, 8ull * n));
+        for (int attempt = 0; attempt < 2; attempt++) {
+            YG_CHECK(ensure_out(ctx, cap));
+            K3Params p;
+            p.row_ptr = ctx->d_row_ptr; p.row_items = ctx->d_row_items; p.post = ctx->d_post; p.sizes = ctx->d_sizes;
+            p.n = n; p.row_begin = row_begin; p.row_end = row_end; p.tile_w = tile_w; p.n_tiles = n_tiles;
+            p.thr = threshold; p.out_key = ctx->d_out_key; p.out_cnt = ctx->d_out_cnt; p.out_cap = ctx->out_cap;
+            p.scal = ctx->d_scalars;
+            YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_OUT], 0, 2 * sizeof(unsigned long long), st));
+            YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+            kern<<<grid, K3_THREADS, smem, st>>>(p);
+            YG_CUDA(ctx, cudaGetLastError());
+            YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+            unsigned long long cnt = 0;
+            YG_CUDA(ctx, cudaMemcpyAsync(&cnt, &ctx->d_scalars[SC_OUT], sizeof cnt, cudaMemcpyDeviceToHost, st));
+            YG_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->tm.ms_count += elapsed(ctx, 0, 1);
+            ctx->tm.n_count_launches++;
+            ctx->tm.n_kernel_launches++;
+            npairs = cnt;
+            if (npairs <= ctx->out_cap) break;
+            if (attempt == 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair buffer overflow after resize");
+            cap = npairs + 1024;
+        }
+    }
+
+    ygpu_pair* host = (ygpu_pair*)malloc(std::max<uint64_t>(npairs, 1) * sizeof(ygpu_pair));
+    if (!host) return ygpu_fail(ctx, YGPU_ERR_NOMEM, "malloc(%llu pairs)", (unsigned long long)npairs);
+    if (npairs) {
+        // order by (i, j): the reference emits row-major (main.cpp:274-275)
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
+                                                     ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st));
+        int rc = ygpu_temp_reserve(ctx, tb + npairs * sizeof(ygpu_pair) + 256);
+        if (rc) { free(host); return rc; }
+        tb = ctx->temp_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
+                                                        ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st);
+        if (e != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair sort: %s", cudaGetErrorString(e)); }
+        ygpu_pair* d_pairs = nullptr;
+        if (cudaMalloc(&d_pairs, npairs * sizeof(ygpu_pair)) != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(pairs)"); }
+        k_pack_pairs<<<grid_for(ctx, npairs, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, npairs, d_pairs);
+        ctx->tm.n_kernel_launches += 10;
+        cudaEventRecord(ctx->ev[2], st);
+        e = cudaMemcpyAsync(host, d_pairs, npairs * sizeof(ygpu_pair), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ctx->ev[3], st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_pairs);
+        if (e != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair copy: %s", cudaGetErrorString(e)); }
+        ctx->tm.ms_d2h += elapsed(ctx, 2, 3);
+    }
+    *out = host;
+    *n_out = npairs;
+    return 0;
+}
+
+extern "C" int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds) {
+    if (!ctx || !bounds || nparts == 0) return YGPU_ERR_ARG;
+    if (!ctx->indexed) return ygpu_fail(ctx, YGPU_ERR_STATE, "row_partition: build_index first");
+    const uint32_t n = ctx->n;
+    std::vector<uint64_t> work(n);
+    if (n) YG_CUDA(ctx, cudaMemcpy(work.data(), ctx->d_row_work, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    // cost model: increments + a per-row constant (launching / scanning a row is not free)
+    long double total = 0;
+    for (uint32_t g = 0; g < n; g++) total += (long double)work[g] + 64.0L;
+    bounds[0] = 0;
+    long double acc = 0;
+    uint32_t part = 1;
+    for (uint32_t g = 0; g < n && part < nparts; g++) {
+        acc += (long double)work[g] + 64.0L;
+        while (part < nparts && acc >= total * part / nparts) bounds[part++] = g + 1;
+    }
+    while (part < nparts) bounds[part++] = n;
+    bounds[nparts] = n;
+    return 0;
+}

@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: genome-pair containments per second of the
+`yacht train` hot path (inverted-index build + pairwise shared-hash count + threshold/compaction)
+on a synthetic GTDB-representatives-shaped reference database (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's CPU core (oracle/_ref)
+    torchrun ... bench.py --gpus N ...                             # N > 1: one rank per GPU (NCCL)
+
+One "step" = one pass of the hot path over the whole database:
+  value : sketches already resident in HBM -> ygpu_build_index + ygpu_pairwise_flag (+ NCCL gather
+          of the pair lists when N > 1); timed with CUDA events on the library's stream.
+  e2e   : the same through the C ABI starting from pinned HOST buffers (H2D of all sketches inside
+          the timed region) and ending with the flagged pair list on the host (D2H).
+N > 1 is STRONG scaling: the same database, query rows sharded across ranks by work, index
+replicated, compacted pair lists all-gathered over NCCL (north_star's partitioning).
+
+Only the cpu_baseline leg and --impl reference execute anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KSIZE = 31
+ANI = 0.95
+THR = ANI ** KSIZE
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for l in self.proc.stdout:
+            self.lines.append(l.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(genomes: int, seed: int):
+    from yacht_b200 import synth
+    t0 = time.time()
+    db = synth.make_reference_db(genomes, seed)
+    return db, time.time() - t0
+
+
+def independent_counts_torch(d_hashes, torch):
+    """T, U2, P, W from the input alone (sort + run-length with torch ops, not with the library)."""
+    s, _ = torch.sort(d_hashes)
+    _, cnt = torch.unique_consecutive(s, return_counts=True)
+    shared = cnt[cnt >= 2].to(torch.int64)
+    return dict(T=int(d_hashes.numel()), U=int(cnt.numel()), U2=int(shared.numel()), P=int(shared.sum().item()),
+                W=int((shared * shared).sum().item()))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference core (oracle/_ref) -- or the oracle port when that binary is absent -- on a
+# bounded sample of the same workload.  Throughput counts the phases that correspond to the GPU
+# arm's e2e step (host buffers -> pair list + retained set): index + matrix + greedy; its JSON
+# ingest phase is reported separately.
+# ------------------------------------------------------------------------------------------------
+def cpu_arm_setup(db, n_sample: int):
+    from oracle import train_oracle as to
+    tmp = tempfile.mkdtemp(prefix="yacht_cpu_arm_")
+    sub = db.subset(range(n_sample))
+    to.write_sig_dir(sub.hashes, sub.offsets, tmp)
+    if to.reference_available():
+        binary, kind = to.REF_BIN, "reference"
+    else:
+        to.build()
+        binary, kind = to.PORT_BIN, "port"
+    return tmp, binary, kind
+
+
+def cpu_arm_step(tmp: str, binary: str, cores: int):
+    from oracle import train_oracle as to
+    for f in os.listdir(tmp):
+        if f.endswith(".txt"):
+            os.remove(os.path.join(tmp, f))
+    out, wall = to.run_core_binary(binary, os.path.join(tmp, "training_sig_files.tsv"), tmp, THR, threads=cores, passes=1)
+    ph = to.parse_phase_times(out)
+    return ph, wall
+
+
+def choose_cpu_sample(db, budget_s: float) -> int:
+    # measured: ~8 ms of reference-core time per 5k-hash genome (index build
+    # dominates: ~1.2-1.5 us per hash, single-threaded)
+    per_genome = 8e-3 * (float(db.offsets[-1]) / max(db.n, 1)) / 5000.0
+    return int(max(100, min(db.n, budget_s / max(per_genome, 1e-6))))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    db, gen_s = make_workload(args.genomes, args.seed)
+    cores = os.cpu_count() or 1
+    budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))
+    n_s = args.cpu_sample or choose_cpu_sample(db, budget)
+    tmp, binary, kind = cpu_arm_setup(db, n_s)
+    try:
+        for _ in range(args.warmup):
+            cpu_arm_step(tmp, binary, cores)
+        tot = 0.0
+        phases = []
+        for _ in range(args.steps):
+            ph, wall = cpu_arm_step(tmp, binary, cores)
+            phases.append(ph)
+            t = (ph.get("index_ms", 0) + ph.get("matrix_ms", 0) + ph.get("greedy_ms", 0)) / 1e3 if ph else wall
+            tot += t
+        per = tot / max(args.steps, 1)
+        pairs = n_s * (n_s - 1)
+        val = pairs / per if per > 0 else 0.0
+        sample = (f"first {n_s} of {db.n} genomes (file order), all-vs-all, {os.path.basename(binary)} -t {cores} -p 1; "
+                  f"time = its own index+matrix+greedy phase timers (JSON read phase excluded)")
+        line = {"impl": "reference", "metric": "ref-pair containments/s (yacht train hot path)", "value": val, "unit": "pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 (+f64 threshold)",
+                "data": "synthetic", "config": workload_config(args, db),
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
+                                 "phases_ms_last": phases[-1] if phases else {}},
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def workload_config(args, db):
+    T = int(db.offsets[-1])
+    return {"workload": f"synthetic GTDB-representatives-shaped reference DB (BASELINE.json configs[2]): {db.n} genomes, "
+                        f"{T} hashes (mean {T / max(db.n, 1):.0f}/genome), planted ANI clusters, seed {args.seed}; "
+                        f"all-vs-all train hot path, k={KSIZE}, ani_thresh={ANI}",
+            "genomes": db.n, "hashes": T, "seed": args.seed, "containment_threshold": THR,
+            "parallelism": f"rows sharded over {args.gpus} GPU(s) by work, index replicated",
+            "l2": f"inputs {8 * T / 1e9:.2f} GB > L2 {L2_BYTES / 1e6:.0f} MB: no flush needed" if 8 * T > L2_BYTES
+                  else "inputs fit L2: an L2 flush (write of 256 MB) runs before every timed step"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from yacht_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    db, gen_s = make_workload(args.genomes, args.seed)
+    n, T = db.n, int(db.offsets[-1])
+    lib = _lib.load_library()
+    ctx = _lib.GpuContext(local)
+
+    # pinned host staging for the e2e arm
+    hp = lib.ygpu_host_alloc(max(T, 1) * 8)
+    if not hp:
+        raise SystemExit("ygpu_host_alloc failed")
+    pinned = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_uint64)), shape=(max(T, 1),))[:T]
+    pinned[:] = db.hashes
+    offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+
+    # device-resident copy (torch owns it; the library copies device-to-device once, outside the timed region)
+    d_hashes = torch.from_numpy(db.hashes.view(np.int64)).to(dev)
+    d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    counts = independent_counts_torch(d_hashes, torch) if rank == 0 else None
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if 8 * T <= L2_BYTES else None
+
+    def gather_pairs(n_r: int, to_host: bool):
+        """pair lists -> every rank (NCCL all-gather of counts, then of the padded lists)."""
+        if world == 1:
+            if to_host:
+                buf = np.empty(n_r, dtype=_lib.PAIR_DTYPE)
+                ctx.pairs_copy(buf.ctypes.data, False)
+                return buf
+            return n_r
+        cnt = torch.tensor([n_r], dtype=torch.int64, device=dev)
+        allc = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt)
+        sizes = allc.tolist()
+        m = max(max(sizes), 1)
+        mine = torch.zeros(m * 3, dtype=torch.int32, device=dev)
+        if n_r:
+            ctx.pairs_copy(mine.data_ptr(), True)
+        allp = torch.empty(world * m * 3, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, mine)
+        if to_host:
+            parts = [allp[r * m * 3:(r * m + sizes[r]) * 3] for r in range(world)]
+            flat = torch.cat(parts).cpu().numpy()
+            return flat.view(_lib.PAIR_DTYPE)
+        torch.cuda.synchronize()   # the NCCL gather runs on torch's stream: finish it inside the timed step
+        return sum(sizes)
+
+    def step_resident():
+        ctx.build_index()
+        b = ctx.row_partition(world)
+        n_r = ctx.pairwise_flag_device(THR, int(b[rank]), int(b[rank + 1]))
+        return gather_pairs(n_r, False)
+
+    def step_e2e():
+        ctx.load_sketches(pinned, offsets)
+        ctx.build_index()
+        b = ctx.row_partition(world)
+        n_r = ctx.pairwise_flag_device(THR, int(b[rank]), int(b[rank + 1]))
+        return gather_pairs(n_r, True)
+
+    def timed(fn, reload_first: bool):
+        if reload_first:
+            ctx.load_sketches_device(d_hashes.data_ptr(), d_offsets.data_ptr(), n)
+        for _ in range(args.warmup):
+            if flush_buf is not None:
+                flush_buf.fill_(1)
+            fn()
+        barrier()
+        ctx.reset_timers()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        total_ms = 0.0
+        wall0 = time.perf_counter()
+        res = None
+        for _ in range(args.steps):
+            if flush_buf is not None:
+                flush_buf.fill_(1)
+                torch.cuda.synchronize()
+            ctx.mark(0)
+            res = fn()
+            ctx.mark(1)
+            total_ms += ctx.elapsed_ms(0, 1)
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        tm = ctx.timings()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, tm, clocks, res, wall / args.steps
+
+    ms_res, tm_res, clocks, n_flagged, wall_res = timed(step_resident, True)
+    ms_e2e, tm_e2e, clocks_e2e, pairs_host, wall_e2e = timed(step_e2e, False)
+
+    if rank == 0:
+        pairs_total = n * (n - 1)
+        F = int(len(pairs_host))
+        peak, peak_src = load_peaks()
+        # ---- roofline of the pairwise-count kernel (K3+K4): SURVEY.md 8(d) algorithmic bytes -----------
+        launches = max(tm_res["n_count_launches"], 1)
+        k3_ms = tm_res["ms_count"] / launches
+        share = 1.0 / world   # rows are split by work; rank 0 sees ~1/world of T and W
+        B_train = (8 * counts["T"] + 4 * counts["W"]) * share + 12 * F * share
+        ach = B_train / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
+        steps = args.steps
+        idx_ms = (tm_res["ms_sort"] + tm_res["ms_index"]) / steps
+        B_index = 12 * counts["T"] * 2 * 7 + 4 * counts["P"] + 8 * counts["U2"]
+        ach_idx = B_index / (idx_ms * 1e-3) / 1e9 if idx_ms > 0 else 0.0
+        line = {
+            "metric": "ref-pair containments/s (yacht train hot path)", "value": pairs_total / (ms_res * 1e-3), "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 (+f64 threshold)",
+            "data": "synthetic", "config": workload_config(args, db),
+            "e2e": {"value": pairs_total / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 8 * T + 8 * (n + 1), "d2h_bytes_per_step": 12 * F,
+                    "phases_ms": {k: tm_e2e[k] / steps for k in ("ms_h2d", "ms_sort", "ms_index", "ms_count", "ms_pairsort", "ms_d2h")}},
+            "gpu_launches": int(tm_res["n_kernel_launches"]),
+            "library_launches": int(tm_res["n_library_launches"]),
+            "clocks": clocks,
+            "roofline": {"kernel": "k3_count_flag (pairwise shared-hash count + threshold/compaction)", "bound": "hbm",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "algorithmic_bytes": B_train, "formula": "8*T + 4*W + 12*F (SURVEY.md 8d), x rank share",
+                         "ms_per_launch": k3_ms, "share_of_step": k3_ms / ms_res if ms_res else None, "peak_source": peak_src},
+            "roofline_index": {"kernel": "K2: radix sort of (hash, genome) [CUB] + run/posting/work-list kernels", "bound": "hbm",
+                               "achieved": ach_idx, "peak": peak, "unit": "GB/s", "frac": ach_idx / peak,
+                               "algorithmic_bytes": B_index, "formula": "12*T*2*7 + 4*P + 8*U2 (SURVEY.md 8d)",
+                               "ms_per_step": idx_ms, "share_of_step": idx_ms / ms_res if ms_res else None},
+            "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},
+            "workload_counts": dict(counts, F=F, genomes=n), "wall_ms_per_step": wall_res * 1e3, "gen_seconds": gen_s,
+        }
+        # ---- CPU baseline: bounded sample on this box's host cores -------------------------------------
+        if not args.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                n_s = args.cpu_sample or choose_cpu_sample(db, 15.0)
+                tmp, binary, kind = cpu_arm_setup(db, n_s)
+                try:
+                    ph, wall = cpu_arm_step(tmp, binary, cores)
+                finally:
+                    shutil.rmtree(tmp, ignore_errors=True)
+                t = (ph.get("index_ms", 0) + ph.get("matrix_ms", 0) + ph.get("greedy_ms", 0)) / 1e3 if ph else wall
+                line["cpu_baseline"] = {"value": n_s * (n_s - 1) / max(t, 1e-9), "unit": "pairs/s", "cores": cores, "kind": kind,
+                                        "sample": f"first {n_s} of {n} genomes (file order), all-vs-all, {os.path.basename(binary)} "
+                                                  f"-t {cores} -p 1; time = its index+matrix+greedy phase timers",
+                                        "phases_ms": ph, "wall_s": wall}
+            except Exception as e:  # the baseline must never take the GPU numbers down with it
+                line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+
+    lib.ygpu_host_free(hp)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=85205, help="BASELINE.json configs[2]: GTDB-rs214-representatives shape")
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="genomes in the CPU sample (0 = size for ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

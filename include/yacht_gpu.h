@@ -15,9 +15,10 @@
  *                           counts (:252-262) fused with threshold/emit (:274-308)
  *   ygpu_row_partition      the contiguous row chunks per thread / per pass    main.cpp:338-349
  *                           (here: work-balanced row ranges per GPU)
- *   ygpu_sample_overlap     `sourmash scripts multisearch ... -t 0`            hypothesis_recovery_src.py:93-113
- *                           (which reference genomes share >= 1 hash with the sample)
- *   ygpu_exclusive_hashes   get_exclusive_hashes()                             hypothesis_recovery_src.py:116-206
+ *   ygpu_exclusive_hashes   `sourmash scripts multisearch ... -t 0`            hypothesis_recovery_src.py:93-113
+ *                           (which reference genomes share >= 1 hash with the
+ *                           sample: counts[g].n_overlap > 0), followed by
+ *                           get_exclusive_hashes()                             hypothesis_recovery_src.py:116-206
  *   ygpu_hyp_test           single_hyp_test() + get_alt_mut_rate()             hypothesis_recovery_src.py:209-306
  *
  * Conventions: every function returns 0 on success and a negative ygpu_status otherwise; the
@@ -73,11 +74,13 @@ typedef struct {
     double ms_sort;         /* K2a: (hash, genome) radix sort                                  */
     double ms_index;        /* K2b: run detection, posting compaction, per-genome work lists   */
     double ms_count;        /* K3+K4: pairwise shared-hash count fused with threshold/compact  */
+    double ms_pairsort;     /* ordering of the flagged pairs by (i, j)                         */
     double ms_d2h;          /* pair-list device->host copy                                     */
     double ms_sample;       /* K5: sample membership + exclusive-hash reduction                */
     double ms_stats;        /* K6: binomial statistics                                         */
     uint64_t n_count_launches;   /* launches of the K3+K4 kernel                               */
-    uint64_t n_kernel_launches;  /* launches of all kernels of this library                    */
+    uint64_t n_kernel_launches;  /* launches of this library's own hand-written kernels         */
+    uint64_t n_library_launches; /* launches it asked CUB for (radix sort / scan / reduce passes) */
 } ygpu_timings;
 
 /* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */
@@ -107,8 +110,17 @@ int ygpu_ctx_create(ygpu_ctx** out, int device);
 void ygpu_ctx_destroy(ygpu_ctx* ctx);
 const char* ygpu_last_error(const ygpu_ctx* ctx);      /* ctx may be NULL: last create error   */
 void ygpu_free(void* p);                               /* release a library-owned host buffer  */
+/* Page-locked host staging buffers (cudaHostAlloc) so ygpu_load_sketches copies at full PCIe
+ * rate; plain malloc'ed memory is accepted too, just slower.  NULL on failure.               */
+void* ygpu_host_alloc(uint64_t bytes);
+void ygpu_host_free(void* p);
 int ygpu_reset_timers(ygpu_ctx* ctx);
 int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out);
+/* CUDA-event stopwatch on the context's stream (slots 0..3): time a whole step from outside.    */
+int ygpu_mark(ygpu_ctx* ctx, int slot);
+int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
+/* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel.      */
+int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- train path ---------------------------------------------------------------------------- */
 /* hashes[offsets[g] .. offsets[g+1]) is sketch g (any order, duplicates allowed).  HOST pointers;
@@ -123,6 +135,11 @@ int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats /* may be NULL */);
  * partition of [0,n) into row ranges is the full pair list.  *out is sorted by (i,j).            */
 int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end,
                        ygpu_pair** out, uint64_t* n_out);
+/* Same computation, but the sorted pair list stays on the device; ygpu_pairs_copy() then copies
+ * n_out * sizeof(ygpu_pair) bytes to a host (dst_is_device = 0) or device (1) buffer -- the
+ * multi-GPU gather hands NCCL the device copy.                                                   */
+int ygpu_pairwise_flag_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end, uint64_t* n_out);
+int ygpu_pairs_copy(ygpu_ctx* ctx, void* dst, int dst_is_device);
 /* bounds[0..nparts] : contiguous row ranges of (nearly) equal pairwise-count work.               */
 int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds);
 

@@ -17,8 +17,9 @@ LIB_PATH = os.path.join(PKG_DIR, "libyachtgpu.so")
 # every symbol include/yacht_gpu.h declares (tests check the library exports each of them)
 ABI_SYMBOLS = [
     "ygpu_device_count", "ygpu_ctx_create", "ygpu_ctx_destroy", "ygpu_last_error", "ygpu_free",
-    "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
-    "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_row_partition", "ygpu_exclusive_hashes",
+    "ygpu_host_alloc", "ygpu_host_free", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
+    "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
+    "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test",
 ]
 
@@ -38,9 +39,9 @@ class IndexStats(ctypes.Structure):
 
 class Timings(ctypes.Structure):
     _fields_ = [("ms_h2d", ctypes.c_double), ("ms_sort", ctypes.c_double), ("ms_index", ctypes.c_double),
-                ("ms_count", ctypes.c_double), ("ms_d2h", ctypes.c_double), ("ms_sample", ctypes.c_double),
+                ("ms_count", ctypes.c_double), ("ms_pairsort", ctypes.c_double), ("ms_d2h", ctypes.c_double), ("ms_sample", ctypes.c_double),
                 ("ms_stats", ctypes.c_double), ("n_count_launches", ctypes.c_uint64),
-                ("n_kernel_launches", ctypes.c_uint64)]
+                ("n_kernel_launches", ctypes.c_uint64), ("n_library_launches", ctypes.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: (float(getattr(self, k)) if t is ctypes.c_double else int(getattr(self, k))) for k, t in self._fields_}
@@ -77,6 +78,10 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_last_error.restype = ctypes.c_char_p
     lib.ygpu_free.argtypes = [vp]
     lib.ygpu_free.restype = None
+    lib.ygpu_host_alloc.argtypes = [u64]
+    lib.ygpu_host_alloc.restype = vp
+    lib.ygpu_host_free.argtypes = [vp]
+    lib.ygpu_host_free.restype = None
     lib.ygpu_reset_timers.argtypes = [vp]
     lib.ygpu_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.ygpu_load_sketches.argtypes = [vp, vp, vp, u32]
@@ -84,6 +89,11 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_build_index.argtypes = [vp, ctypes.POINTER(IndexStats)]
     lib.ygpu_pairwise_flag.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.ygpu_row_partition.argtypes = [vp, u32, vp]
+    lib.ygpu_pairwise_flag_device.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(u64)]
+    lib.ygpu_pairs_copy.argtypes = [vp, vp, ctypes.c_int]
+    lib.ygpu_mark.argtypes = [vp, ctypes.c_int]
+    lib.ygpu_elapsed_ms.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.ygpu_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
     lib.ygpu_exclusive_hashes.argtypes = [vp, vp, u64, vp, vp]
     lib.ygpu_hyp_test.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, ctypes.c_double, vp, ctypes.c_int, vp]
     for name in ABI_SYMBOLS:
@@ -173,6 +183,29 @@ class GpuContext:
             return np.frombuffer(buf, dtype=PAIR_DTYPE).copy()
         finally:
             self.lib.ygpu_free(out)
+
+    def pairwise_flag_device(self, threshold: float, row_begin: int = 0, row_end: Optional[int] = None) -> int:
+        """Same as pairwise_flag but the pairs stay on the device; returns how many there are."""
+        if row_end is None:
+            row_end = self.n
+        n_out = ctypes.c_uint64()
+        self._check(self.lib.ygpu_pairwise_flag_device(self.h, float(threshold), int(row_begin), int(row_end),
+                                                       ctypes.byref(n_out)), "ygpu_pairwise_flag_device")
+        return int(n_out.value)
+
+    def pairs_copy(self, dst_ptr: int, dst_is_device: bool) -> None:
+        self._check(self.lib.ygpu_pairs_copy(self.h, dst_ptr, 1 if dst_is_device else 0), "ygpu_pairs_copy")
+
+    def mark(self, slot: int) -> None:
+        self._check(self.lib.ygpu_mark(self.h, slot), "ygpu_mark")
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = ctypes.c_double()
+        self._check(self.lib.ygpu_elapsed_ms(self.h, a, b, ctypes.byref(ms)), "ygpu_elapsed_ms")
+        return float(ms.value)
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self.lib.ygpu_set_option(self.h, name.encode(), int(value)), "ygpu_set_option")
 
     def row_partition(self, nparts: int) -> np.ndarray:
         b = np.zeros(nparts + 1, dtype=np.uint32)

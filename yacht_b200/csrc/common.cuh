@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <unordered_map>
 #include "../../include/yacht_gpu.h"
 
 struct ygpu_ctx {
@@ -24,6 +25,7 @@ struct ygpu_ctx {
 
     // ---- inverted index (K2 output) ---------------------------------------------------------
     bool indexed = false;
+    bool sorted = false;            // d_skey / d_sgid valid
     uint64_t* d_skey = nullptr;     // [T]   hashes sorted ascending
     uint32_t* d_sgid = nullptr;     // [T]   genome id of each sorted hash (ascending inside a run)
     uint8_t* d_flag = nullptr;      // [T]   1 if the sorted slot belongs to a run of length >= 2
@@ -35,9 +37,11 @@ struct ygpu_ctx {
     uint64_t* d_row_ptr = nullptr;  // [n+1] CSR over row_items
     uint64_t* d_row_items = nullptr;// [n_items] (first posting slot << 32) | count  -- per query genome
     uint64_t* d_row_work = nullptr; // [n]   increments row i performs (sum of counts)
+    unsigned long long* d_row_cnt = nullptr;  // [n+1] build scratch
     ygpu_index_stats stats = {};
 
     // ---- scratch ------------------------------------------------------------------------------
+    std::unordered_map<void*, size_t> caps;   // capacity (bytes) of every dev_alloc'ed buffer, keyed by member address
     void* d_temp = nullptr;         // CUB temp storage (grown on demand)
     size_t temp_bytes = 0;
     unsigned long long* d_scalars = nullptr;  // [16] device counters
@@ -46,6 +50,12 @@ struct ygpu_ctx {
     uint64_t* d_out_key2 = nullptr;
     uint32_t* d_out_cnt2 = nullptr;
     uint64_t out_cap = 0;
+    ygpu_pair* d_pairs = nullptr;   // sorted flagged pairs of the last pairwise call
+    uint64_t pairs_cap = 0;
+    uint64_t n_pairs = 0;
+    uint32_t force_tile_w = 0;      // test hook: cap the accumulator tile width (0 = automatic)
+
+    void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
 
     ygpu_timings tm = {};
 };
@@ -67,6 +77,7 @@ int ygpu_fail(ygpu_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 int ygpu_temp_reserve(ygpu_ctx* ctx, size_t bytes);
+int ygpu_sort_sketches(ygpu_ctx* ctx);   // K2a (yacht_gpu.cu)
 
 // run path (run_kernels.cu)
 void ygpu_run_release(ygpu_ctx* ctx);

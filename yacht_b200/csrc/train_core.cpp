@@ -1,0 +1,420 @@
+// run_yacht_train_core -- B200 drop-in for the reference executable of the same name
+// (KoslickiLab/YACHT src/cpp/main.cpp, launched by src/yacht/utils.py:143-147).
+//
+// Same command line, same files, same stdout banners:
+//   run_yacht_train_core [-t T] [-c C] [-p P] file_list working_directory output_filename
+//     (main.cpp:142-184; -t/-p keep their meaning for how the pair lines are split over
+//      <working_directory>/<pass>_<thread:03d>.txt, :265-271,338-349)
+//   output_filename: the selected sketch paths, one per line, greedy visit order (:412-418)
+//
+// This file is the HOST layer only: argument parsing, sketch ingest (sig_scan.hpp), the greedy
+// near-duplicate removal (inherently sequential, main.cpp:371-420) and the file writers.  The
+// inverted index, the pairwise shared-hash counts and the threshold/compaction run on the GPU(s)
+// behind the C ABI of include/yacht_gpu.h; there is no CPU implementation of them here, and the
+// program exits non-zero if no B200 is available.
+//
+// Multi-GPU: every visible device (or the first YACHT_NUM_GPUS of them) gets the full sketch set
+// and builds the index (replicated), then flags the pairs of its own work-balanced row range;
+// the per-device pair lists are merged on the host.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "../../include/yacht_gpu.h"
+#include "sig_scan.hpp"
+
+namespace {
+
+struct Arguments {
+    std::string file_list, working_directory, output_filename;
+    int number_of_threads = 1;
+    int num_of_passes = 1;
+    double containment_threshold = 0.9;
+};
+
+const char* kVersion = "1.0";
+
+void usage(const char* prog) {
+    std::cout << "Usage: " << prog << " [--help] [--version] [--threads VAR] [--passes VAR] "
+              << "[--containment_threshold VAR] file_list working_directory output_filename\n\n"
+              << "Positional arguments:\n"
+              << "  file_list                    file containing list of files to be processed \n"
+              << "  working_directory            working directory (where temp files are generated) \n"
+              << "  output_filename              output filename (where the reduced ref filenames will be written) \n\n"
+              << "Optional arguments:\n"
+              << "  -h, --help                   shows help message and exits \n"
+              << "  -v, --version                prints version information and exits \n"
+              << "  -t, --threads                number of threads [nargs=0..1] [default: 1]\n"
+              << "  -p, --passes                 number of passes [nargs=0..1] [default: 1]\n"
+              << "  -c, --containment_threshold  containment threshold [nargs=0..1] [default: 0.9]\n";
+}
+
+bool parse_int(const char* s, int* out) {
+    errno = 0;
+    char* e = nullptr;
+    const long v = strtol(s, &e, 10);
+    if (e == s || *e != 0 || errno == ERANGE || v < INT32_MIN || v > INT32_MAX) return false;
+    *out = (int)v;
+    return true;
+}
+
+bool parse_double(const char* s, double* out) {
+    errno = 0;
+    char* e = nullptr;
+    const double v = strtod(s, &e);  // the reference's argparse also ends in strtod (argparse.hpp:370-392)
+    if (e == s || *e != 0) return false;
+    *out = v;
+    return true;
+}
+
+// returns 0 = go on, 1 = error (exit 1), 2 = help/version shown (exit 0)
+int parse_arguments(int argc, char** argv, Arguments& a) {
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; i++) {
+        const std::string s = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::cerr << "Too few arguments for '" << name << "'." << std::endl; return nullptr; }
+            return argv[++i];
+        };
+        if (s == "-h" || s == "--help") { usage(argv[0]); return 2; }
+        if (s == "-v" || s == "--version") { std::cout << kVersion << std::endl; return 2; }
+        if (s == "-t" || s == "--threads") {
+            const char* v = need("-t");
+            if (!v || !parse_int(v, &a.number_of_threads)) { std::cerr << "invalid value for --threads" << std::endl; return 1; }
+        } else if (s == "-p" || s == "--passes") {
+            const char* v = need("-p");
+            if (!v || !parse_int(v, &a.num_of_passes)) { std::cerr << "invalid value for --passes" << std::endl; return 1; }
+        } else if (s == "-c" || s == "--containment_threshold") {
+            const char* v = need("-c");
+            if (!v || !parse_double(v, &a.containment_threshold)) { std::cerr << "invalid value for --containment_threshold" << std::endl; return 1; }
+        } else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9') && s[1] != '.') {
+            std::cerr << "Unknown argument: " << s << std::endl;
+            return 1;
+        } else {
+            pos.push_back(s);
+        }
+    }
+    if (pos.size() < 3) {
+        static const char* names[3] = {"file_list", "working_directory", "output_filename"};
+        std::cerr << names[pos.size()] << ": 1 argument(s) expected. 0 provided." << std::endl;
+        return 1;
+    }
+    if (pos.size() > 3) { std::cerr << "Maximum number of positional arguments exceeded" << std::endl; return 1; }
+    a.file_list = pos[0];
+    a.working_directory = pos[1];
+    a.output_filename = pos[2];
+    // same validation and messages as main.cpp:172-182
+    if (a.number_of_threads < 1) { std::cerr << "number of threads must be at least 1" << std::endl; return 1; }
+    if (a.num_of_passes < 1) { std::cerr << "number of passes must be at least 1" << std::endl; return 1; }
+    if (a.containment_threshold < 0.0 || a.containment_threshold > 1.0) {
+        std::cerr << "containment threshold must be between 0.0 and 1.0" << std::endl;
+        return 1;
+    }
+    return 0;
+}
+
+void show_arguments(const Arguments& a) {  // main.cpp:187-199
+    using std::cout; using std::endl;
+    cout << "Working with the following parameters:" << endl;
+    cout << "**************************************" << endl;
+    cout << "*" << endl;
+    cout << "*    file_list: " << a.file_list << endl;
+    cout << "*    working_directory: " << a.working_directory << endl;
+    cout << "*    output_filename: " << a.output_filename << endl;
+    cout << "*    number_of_threads: " << a.number_of_threads << endl;
+    cout << "*    num_of_passes: " << a.num_of_passes << endl;
+    cout << "*    containment_threshold: " << a.containment_threshold << endl;
+    cout << "*" << endl;
+    cout << "**************************************" << endl;
+}
+
+// ---- ingest: file list -> flat pinned hash array + offsets ------------------------------------
+struct Ingest {
+    std::vector<std::string> names;
+    uint64_t* hashes = nullptr;      // pinned (ygpu_host_alloc) or malloc
+    bool pinned = false;
+    std::vector<uint64_t> offsets;   // n + 1
+    std::vector<int> empty_ids;
+    bool fatal = false;
+    std::string fatal_msg;
+};
+
+constexpr uint32_t kFilesPerBlock = 32;
+
+void read_sketches(Ingest& in, int threads) {
+    const uint32_t n = (uint32_t)in.names.size();
+    const uint32_t nblocks = (n + kFilesPerBlock - 1) / kFilesPerBlock;
+    std::vector<std::vector<uint64_t>> block_hashes(nblocks);
+    std::vector<uint32_t> sizes(n, 0);
+    std::atomic<uint32_t> next{0};
+    std::mutex mu;
+    auto worker = [&]() {
+        std::vector<char> buf;
+        for (;;) {
+            const uint32_t b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            std::vector<uint64_t>& out = block_hashes[b];
+            const uint32_t f0 = b * kFilesPerBlock, f1 = std::min(n, f0 + kFilesPerBlock);
+            for (uint32_t f = f0; f < f1; f++) {
+                const size_t before = out.size();
+                std::string why;
+                const sigscan::Status st = sigscan::read_mins(in.names[f], buf, out, &why);
+                if (st == sigscan::CANNOT_OPEN) {
+                    std::cerr << "Could not open the file!" << std::endl;  // main.cpp:69
+                    out.resize(before);
+                } else if (st == sigscan::MALFORMED) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!in.fatal) { in.fatal = true; in.fatal_msg = in.names[f] + ": " + why; }
+                    out.resize(before);
+                }
+                sizes[f] = (uint32_t)(out.size() - before);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    const int nt = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(nblocks, 1)));
+    for (int t = 0; t < nt; t++) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+
+    in.offsets.assign((size_t)n + 1, 0);
+    for (uint32_t f = 0; f < n; f++) {
+        in.offsets[f + 1] = in.offsets[f] + sizes[f];
+        if (sizes[f] == 0) in.empty_ids.push_back((int)f);
+    }
+    const uint64_t T = in.offsets[n];
+    in.hashes = (uint64_t*)ygpu_host_alloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
+    in.pinned = in.hashes != nullptr;
+    if (!in.hashes) in.hashes = (uint64_t*)malloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
+    std::atomic<uint32_t> nextb{0};
+    auto copier = [&]() {
+        for (;;) {
+            const uint32_t b = nextb.fetch_add(1);
+            if (b >= nblocks) break;
+            const uint64_t dst = in.offsets[(size_t)b * kFilesPerBlock];
+            if (!block_hashes[b].empty())
+                memcpy(in.hashes + dst, block_hashes[b].data(), block_hashes[b].size() * sizeof(uint64_t));
+            std::vector<uint64_t>().swap(block_hashes[b]);
+        }
+    };
+    pool.clear();
+    for (int t = 0; t < nt; t++) pool.emplace_back(copier);
+    for (auto& t : pool) t.join();
+}
+
+struct DeviceResult {
+    int rc = 0;
+    std::string err;
+    ygpu_pair* pairs = nullptr;
+    uint64_t n_pairs = 0;
+    ygpu_index_stats stats{};
+    ygpu_timings tm{};
+};
+
+int64_t ms_since(std::chrono::high_resolution_clock::time_point t0) {
+    return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Arguments args;
+    const int pa = parse_arguments(argc, argv, args);
+    if (pa == 2) return 0;
+    if (pa == 1) {
+        std::cout << "Usage: " << argv[0] << " -h" << std::endl;  // main.cpp:434
+        return 1;
+    }
+    show_arguments(args);
+
+    int ndev = ygpu_device_count();
+    if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) ndev = std::min(ndev, v); }
+    if (ndev < 1) {
+        std::cerr << "run_yacht_train_core: no CUDA device available; this build has no CPU path" << std::endl;
+        return 3;
+    }
+
+    // ---- read ----------------------------------------------------------------------------------
+    auto t_read = std::chrono::high_resolution_clock::now();
+    std::cout << "Reading all sketches in filelist using all " << args.number_of_threads << " threads..." << std::endl;
+    Ingest in;
+    {
+        std::ifstream fl(args.file_list);
+        if (!fl.is_open()) std::cerr << "Could not open the filelist: " << args.file_list << std::endl;  // main.cpp:131
+        std::string line;
+        while (std::getline(fl, line)) in.names.push_back(line);
+    }
+    const uint32_t n = (uint32_t)in.names.size();
+    std::cout << "Total number of sketches to read: " << n << std::endl;
+    read_sketches(in, args.number_of_threads);
+    if (in.fatal) {
+        std::cerr << "run_yacht_train_core: cannot parse signature " << in.fatal_msg << std::endl;
+        return 4;
+    }
+    std::cout << "All sketches read" << std::endl;
+    std::cout << "Number of empty sketches: " << in.empty_ids.size() << std::endl;  // main.cpp:202-212
+    if (!in.empty_ids.empty()) {
+        std::cout << "Empty sketch ids: ";
+        for (int i : in.empty_ids) std::cout << i << " ";
+        std::cout << std::endl;
+    }
+    std::cout << "Time taken to read all sketches: " << ms_since(t_read) << " milliseconds" << std::endl;
+
+    // ---- index + pairwise on the GPU(s) ----------------------------------------------------------
+    auto t_index = std::chrono::high_resolution_clock::now();
+    std::cout << "Building index from sketches..." << std::endl;
+    ndev = std::max(1, std::min<int>(ndev, (int)std::max<uint32_t>(n, 1)));
+    std::vector<ygpu_ctx*> ctxs(ndev, nullptr);
+    std::vector<DeviceResult> res(ndev);
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev; d++)
+            th.emplace_back([&, d]() {
+                DeviceResult& r = res[d];
+                r.rc = ygpu_ctx_create(&ctxs[d], d);
+                if (r.rc) { r.err = ygpu_last_error(nullptr); return; }
+                r.rc = ygpu_load_sketches(ctxs[d], in.hashes, in.offsets.data(), n);
+                if (!r.rc) r.rc = ygpu_build_index(ctxs[d], &r.stats);
+                if (r.rc) r.err = ygpu_last_error(ctxs[d]);
+            });
+        for (auto& t : th) t.join();
+    }
+    for (int d = 0; d < ndev; d++)
+        if (res[d].rc) {
+            std::cerr << "run_yacht_train_core: GPU " << d << ": " << res[d].err << std::endl;
+            return 5;
+        }
+    const ygpu_index_stats& S = res[0].stats;
+    std::cout << "Total number of distinct hashes: " << S.n_distinct << std::endl;                                       // main.cpp:242
+    std::cout << "Total number of distinct hashes that appear in only one sketch: " << S.n_singleton << std::endl;      // :243
+    std::cout << "Size of the index: " << S.n_index << std::endl;                                                       // :244
+    std::cout << "Time taken to build index: " << ms_since(t_index) << " milliseconds" << std::endl;
+
+    auto t_mat = std::chrono::high_resolution_clock::now();
+    std::cout << "Computing intersection matrix..." << std::endl;
+    std::vector<uint32_t> bounds(ndev + 1, 0);
+    if (ygpu_row_partition(ctxs[0], (uint32_t)ndev, bounds.data())) {
+        std::cerr << "run_yacht_train_core: " << ygpu_last_error(ctxs[0]) << std::endl;
+        return 5;
+    }
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev; d++)
+            th.emplace_back([&, d]() {
+                DeviceResult& r = res[d];
+                r.rc = ygpu_pairwise_flag(ctxs[d], args.containment_threshold, bounds[d], bounds[d + 1], &r.pairs, &r.n_pairs);
+                if (r.rc) r.err = ygpu_last_error(ctxs[d]);
+                ygpu_get_timings(ctxs[d], &r.tm);
+            });
+        for (auto& t : th) t.join();
+    }
+    for (int d = 0; d < ndev; d++)
+        if (res[d].rc) {
+            std::cerr << "run_yacht_train_core: GPU " << d << ": " << res[d].err << std::endl;
+            return 5;
+        }
+    // merge the per-device lists (each is sorted by (i, j); ranges interleave because the owner of
+    // row a also reports (b, a))
+    uint64_t F = 0;
+    for (auto& r : res) F += r.n_pairs;
+    std::vector<ygpu_pair> pairs;
+    pairs.reserve(F);
+    for (auto& r : res) {
+        pairs.insert(pairs.end(), r.pairs, r.pairs + r.n_pairs);
+        ygpu_free(r.pairs);
+        r.pairs = nullptr;
+    }
+    if (ndev > 1)
+        std::sort(pairs.begin(), pairs.end(), [](const ygpu_pair& a, const ygpu_pair& b) {
+            return a.i != b.i ? a.i < b.i : a.j < b.j;
+        });
+
+    // ---- pair files: same file partition as main.cpp:318,338-349, same line format as :305 --------
+    std::vector<std::vector<int>> similars(n);
+    {
+        const int P = args.num_of_passes, Tn = args.number_of_threads;
+        const int per_pass = (int)std::ceil(1.0 * n / P);
+        size_t k = 0;
+        for (int pass = 0; pass < P; pass++) {
+            const int ps = pass * per_pass;
+            const int pe = (pass == P - 1) ? (int)n : (pass + 1) * per_pass;
+            const int n_this = pe - ps;
+            const int chunk = n_this / Tn;
+            for (int t = 0; t < Tn; t++) {
+                const int re = (t == Tn - 1) ? pe : ps + (t + 1) * chunk;
+                std::string id = std::to_string(t);
+                while (id.size() < 3) id = "0" + id;
+                const std::string fn = args.working_directory + "/" + std::to_string(pass) + "_" + id + ".txt";
+                std::ofstream outfile(fn);
+                while (k < pairs.size() && pairs[k].i < re) {
+                    const ygpu_pair& pr = pairs[k++];
+                    const size_t ni = in.offsets[pr.i + 1] - in.offsets[pr.i];
+                    const size_t nj = in.offsets[pr.j + 1] - in.offsets[pr.j];
+                    const int m = pr.count;
+                    // the reference's expressions, operand types included (main.cpp:296-298)
+                    const double jaccard = 1.0 * m / (ni + nj - m);
+                    const double c_ij = 1.0 * m / ni;
+                    const double c_ji = 1.0 * m / nj;
+                    outfile << pr.i << "," << pr.j << "," << jaccard << "," << c_ij << "," << c_ji << std::endl;
+                    similars[pr.i].push_back(pr.j);
+                }
+                outfile.close();
+            }
+            std::cout << "Pass " << pass + 1 << "/" << P << " done." << std::endl;
+        }
+    }
+    std::cout << "Time taken to compute intersection matrix: " << ms_since(t_mat) << " milliseconds" << std::endl;
+
+    // ---- greedy near-duplicate removal (main.cpp:371-420), on the host -----------------------------
+    auto t_train = std::chrono::high_resolution_clock::now();
+    std::cout << "Starting yacht train..." << std::endl;
+    std::cout << "Starting yacht train..." << std::endl;
+    // Same element type, same initial order (file-list order), same comparator and the same
+    // std::sort as the reference, so genomes of equal size are visited in the same order.
+    std::vector<std::pair<int, int>> genome_id_size_pairs(n);
+    for (uint32_t g = 0; g < n; g++) genome_id_size_pairs[g] = {(int)g, (int)(in.offsets[g + 1] - in.offsets[g])};
+    std::sort(genome_id_size_pairs.begin(), genome_id_size_pairs.end(),
+              [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second < b.second; });
+    std::vector<bool> excluded(n, false);
+    std::vector<int> selected;
+    for (uint32_t v = 0; v < n; v++) {
+        const int g = genome_id_size_pairs[v].first;
+        const int size_this = genome_id_size_pairs[v].second;
+        bool keep = true;
+        for (int o : similars[g]) {
+            if (excluded[o]) continue;
+            if ((int)(in.offsets[o + 1] - in.offsets[o]) >= size_this) { keep = false; break; }
+        }
+        if (keep) selected.push_back(g);
+        else excluded[g] = true;
+    }
+    std::cout << "Writing to output file.." << std::endl;
+    {
+        std::ofstream outfile(args.output_filename);
+        for (int g : selected) outfile << in.names[g] << std::endl;
+        outfile.close();
+    }
+    std::cout << "Time taken to do yacht train: " << ms_since(t_train) << " milliseconds" << std::endl;
+
+    // extra (not in the reference): device-side timings, for apples-to-apples phase accounting
+    for (int d = 0; d < ndev; d++) {
+        const ygpu_timings& t = res[d].tm;
+        std::cout << "[gpu " << d << "] rows [" << bounds[d] << "," << bounds[d + 1] << ") h2d " << t.ms_h2d << " ms, sort "
+                  << t.ms_sort << " ms, index " << t.ms_index << " ms, count+flag " << t.ms_count << " ms, d2h " << t.ms_d2h
+                  << " ms, pairs " << res[d].n_pairs << std::endl;
+    }
+    for (auto* c : ctxs) ygpu_ctx_destroy(c);
+    if (in.pinned) ygpu_host_free(in.hashes); else free(in.hashes);
+    return 0;
+}

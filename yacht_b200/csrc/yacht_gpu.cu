@@ -45,22 +45,31 @@ int ygpu_temp_reserve(ygpu_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+// Capacity-tracked device buffers: a buffer is reused when it is already large enough, so that
+// repeated steps (bench loops, multi-sample runs) do not pay cudaMalloc/cudaFree -- which
+// synchronise the device and cost milliseconds per GB -- inside the hot path.
 template <typename T>
 static int dev_alloc(ygpu_ctx* ctx, T** p, uint64_t count) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    const size_t bytes = count * sizeof(T);
+    auto it = ctx->caps.find((void*)p);
+    if (*p && it != ctx->caps.end() && it->second >= bytes) return 0;
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    const size_t want = bytes + (bytes >> 4) + 256;
+    cudaError_t e = cudaMalloc((void**)p, want);
     if (e != cudaSuccess) {
         *p = nullptr;
-        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(%llu bytes): %s",
-                         (unsigned long long)(count * sizeof(T)), cudaGetErrorString(e));
+        ctx->caps.erase((void*)p);
+        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)want, cudaGetErrorString(e));
     }
+    ctx->caps[(void*)p] = want;
     return 0;
 }
 template <typename T>
-static void dev_free(T** p) {
+static void dev_free(ygpu_ctx* ctx, T** p) {
     if (*p) cudaFree(*p);
     *p = nullptr;
+    ctx->caps.erase((void*)p);
 }
 
 static float elapsed(ygpu_ctx* ctx, int a, int b) {
@@ -124,19 +133,24 @@ extern "C" int ygpu_ctx_create(ygpu_ctx** out, int device) {
     return 0;
 }
 
-static void release_index(ygpu_ctx* ctx) {
-    dev_free(&ctx->d_skey); dev_free(&ctx->d_sgid); dev_free(&ctx->d_flag); dev_free(&ctx->d_cpos);
-    dev_free(&ctx->d_post); dev_free(&ctx->d_rem); dev_free(&ctx->d_row_ptr); dev_free(&ctx->d_row_items);
-    dev_free(&ctx->d_row_work);
+static void release_index(ygpu_ctx* ctx) {   // invalidate only: the buffers are kept for reuse
+    ctx->sorted = false;
     ctx->indexed = false;
     ctx->P = 0; ctx->n_items = 0;
 }
 
 static void release_sketches(ygpu_ctx* ctx) {
     release_index(ctx);
-    dev_free(&ctx->d_hashes); dev_free(&ctx->d_offsets); dev_free(&ctx->d_sizes); dev_free(&ctx->d_gid);
     ctx->loaded = false;
     ctx->n = 0; ctx->T = 0;
+}
+
+static void free_all(ygpu_ctx* ctx) {
+    dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
+    dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
+    dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
+    dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
+    dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
 }
 
 extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
@@ -144,8 +158,9 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     release_sketches(ctx);
+    free_all(ctx);
     ygpu_run_release(ctx);
-    dev_free(&ctx->d_out_key); dev_free(&ctx->d_out_cnt); dev_free(&ctx->d_out_key2); dev_free(&ctx->d_out_cnt2);
+    if (ctx->d_pairs) cudaFree(ctx->d_pairs);
     if (ctx->d_temp) cudaFree(ctx->d_temp);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -158,6 +173,13 @@ extern "C" const char* ygpu_last_error(const ygpu_ctx* ctx) {
 }
 
 extern "C" void ygpu_free(void* p) { free(p); }
+
+extern "C" void* ygpu_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void ygpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int ygpu_reset_timers(ygpu_ctx* ctx) {
     if (!ctx) return YGPU_ERR_ARG;
@@ -348,6 +370,47 @@ static int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8) {
     return (int)std::max<uint64_t>(1, std::min(blocks, cap));
 }
 
+// K2a: stable radix sort of (hash, genome id); equal-hash runs become posting lists in ascending
+// genome order (slots are generated genome-major and the sort is stable).  Kept resident: the
+// run path (K5) walks the same sorted array.
+int ygpu_sort_sketches(ygpu_ctx* ctx) {
+    if (ctx->sorted) return 0;
+    const uint64_t T = ctx->T;
+    cudaStream_t st = ctx->stream;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_skey, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sgid, T));
+    if (T) {
+        uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
+        {
+            size_t tb = 0;
+            YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+            YG_CHECK(ygpu_temp_reserve(ctx, tb));
+            tb = ctx->temp_bytes;
+            YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+            ctx->tm.n_library_launches += 2;
+        }
+        uint64_t maxkey = 0;
+        YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        int end_bit = 1;
+        while (end_bit < 64 && (maxkey >> end_bit) != 0) end_bit++;
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
+                                                     (int64_t)T, 0, end_bit, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
+                                                     (int64_t)T, 0, end_bit, st));
+        ctx->tm.n_library_launches += 2 + (end_bit + 7) / 8;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_sort += elapsed(ctx, 2, 3);
+    ctx->sorted = true;
+    return 0;
+}
+
 extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
     if (!ctx) return YGPU_ERR_ARG;
     if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "build_index: no sketches loaded");
@@ -377,35 +440,8 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
         return 0;
     }
 
-    // ---- K2a: stable radix sort of (hash, genome id); equal-hash runs become posting lists in
-    //      ascending genome order (slots are generated genome-major, the sort is stable).
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_skey, T));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_sgid, T));
-    uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
-    {
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-        ctx->tm.n_kernel_launches += 2;
-    }
-    uint64_t maxkey = 0;
-    YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
-    int end_bit = 1;
-    while (end_bit < 64 && (maxkey >> end_bit) != 0) end_bit++;
-    {
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
-                                                     (int64_t)T, 0, end_bit, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_hashes, ctx->d_skey, ctx->d_gid, ctx->d_sgid,
-                                                     (int64_t)T, 0, end_bit, st));
-        ctx->tm.n_kernel_launches += 2 + (end_bit + 7) / 8;
-    }
+    // ---- K2a: stable radix sort of (hash, genome id)
+    YG_CHECK(ygpu_sort_sketches(ctx));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
 
     // ---- K2b: runs -> compact postings + per-genome work lists
@@ -420,7 +456,7 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
         YG_CHECK(ygpu_temp_reserve(ctx, tb));
         tb = ctx->temp_bytes;
         YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, it, ctx->d_cpos, (int64_t)T, st));
-        ctx->tm.n_kernel_launches += 3;
+        ctx->tm.n_library_launches += 2;
     }
     uint32_t last_cpos = 0;
     uint8_t last_flag = 0;
@@ -431,8 +467,8 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
     ctx->P = P;
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, P));
     YG_CHECK(dev_alloc(ctx, &ctx->d_rem, P));
-    unsigned long long* d_row_cnt = nullptr;
-    YG_CHECK(dev_alloc(ctx, &d_row_cnt, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    unsigned long long* d_row_cnt = ctx->d_row_cnt;
     YG_CUDA(ctx, cudaMemsetAsync(d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
     if (P) {
         k_post_compact<<<grid_for(ctx, T, 256), 256, 0, st>>>(ctx->d_skey, ctx->d_sgid, ctx->d_flag, ctx->d_cpos, T,
@@ -447,7 +483,7 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
         YG_CHECK(ygpu_temp_reserve(ctx, tb));
         tb = ctx->temp_bytes;
         YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
-        ctx->tm.n_kernel_launches += 2;
+        ctx->tm.n_library_launches += 2;
     }
     unsigned long long sc[16];
     uint64_t n_items = 0;
@@ -465,16 +501,12 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
     }
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(d_row_cnt);
     ctx->tm.n_kernel_launches += 1;  // k_flag_runs
-    ctx->tm.ms_sort += elapsed(ctx, 0, 1);
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
 
     // sorted keys / flags / scan are only needed while building (the run path re-sorts with its
     // own mask); release them so an 85k-genome index leaves HBM to the count kernel's output.
-    dev_free(&ctx->d_flag);
-    dev_free(&ctx->d_cpos);
-    dev_free(&ctx->d_rem);
+    // (d_flag / d_cpos / d_rem are scratch of the build; they stay allocated for the next build)
 
     std::vector<uint32_t> sz(n);
     YG_CUDA(ctx, cudaMemcpy(sz.data(), ctx->d_sizes, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -675,11 +707,10 @@ static int ensure_out(ygpu_ctx* ctx, uint64_t cap) {
     return 0;
 }
 
-extern "C" int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end,
-                                  ygpu_pair** out, uint64_t* n_out) {
-    if (!ctx || !out || !n_out) return YGPU_ERR_ARG;
-    *out = nullptr;
+// count + flag + sort on the device; the sorted pairs stay resident in ctx->d_pairs
+static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end, uint64_t* n_out) {
     *n_out = 0;
+    ctx->n_pairs = 0;
     if (!ctx->indexed) return ygpu_fail(ctx, YGPU_ERR_STATE, "pairwise_flag: build_index first");
     if (row_begin > row_end || row_end > ctx->n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad row range [%u,%u) of %u", row_begin, row_end, ctx->n);
     YG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -699,6 +730,7 @@ extern "C" int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_
             else if (u16_ok) { use_u16 = true; tile_w = (budget / 2) & ~1u; }
             else tile_w = budget / 4;
         }
+        if (ctx->force_tile_w && ctx->force_tile_w < tile_w) tile_w = ctx->force_tile_w;   // test hook
         const uint32_t n_tiles = (n + tile_w - 1) / tile_w;
         const uint32_t acc_words = use_u16 ? (tile_w + 1) / 2 : tile_w;
         const size_t smem = (size_t)(acc_words + (acc_words & 1u)) * 4 + fixed;
@@ -735,35 +767,90 @@ extern "C" int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_
             cap = npairs + 1024;
         }
     }
-
-    ygpu_pair* host = (ygpu_pair*)malloc(std::max<uint64_t>(npairs, 1) * sizeof(ygpu_pair));
-    if (!host) return ygpu_fail(ctx, YGPU_ERR_NOMEM, "malloc(%llu pairs)", (unsigned long long)npairs);
     if (npairs) {
         // order by (i, j): the reference emits row-major (main.cpp:274-275)
+        YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
         size_t tb = 0;
         YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
                                                      ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st));
-        int rc = ygpu_temp_reserve(ctx, tb + npairs * sizeof(ygpu_pair) + 256);
-        if (rc) { free(host); return rc; }
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
         tb = ctx->temp_bytes;
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
-                                                        ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st);
-        if (e != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair sort: %s", cudaGetErrorString(e)); }
-        ygpu_pair* d_pairs = nullptr;
-        if (cudaMalloc(&d_pairs, npairs * sizeof(ygpu_pair)) != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(pairs)"); }
-        k_pack_pairs<<<grid_for(ctx, npairs, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, npairs, d_pairs);
-        ctx->tm.n_kernel_launches += 10;
-        cudaEventRecord(ctx->ev[2], st);
-        e = cudaMemcpyAsync(host, d_pairs, npairs * sizeof(ygpu_pair), cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(ctx->ev[3], st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFree(d_pairs);
-        if (e != cudaSuccess) { free(host); return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair copy: %s", cudaGetErrorString(e)); }
-        ctx->tm.ms_d2h += elapsed(ctx, 2, 3);
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
+                                                     ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st));
+        ctx->tm.n_library_launches += 10;
+        if (npairs > ctx->pairs_cap) {
+            if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+            ctx->d_pairs = nullptr; ctx->pairs_cap = 0;
+            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs, (npairs + 1024) * sizeof(ygpu_pair)));
+            ctx->pairs_cap = npairs + 1024;
+        }
+        k_pack_pairs<<<grid_for(ctx, npairs, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, npairs, ctx->d_pairs);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+        YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->tm.ms_pairsort += elapsed(ctx, 2, 3);
     }
+    ctx->n_pairs = npairs;
+    *n_out = npairs;
+    return 0;
+}
+
+extern "C" int ygpu_pairwise_flag_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end, uint64_t* n_out) {
+    if (!ctx || !n_out) return YGPU_ERR_ARG;
+    return pairwise_device(ctx, threshold, row_begin, row_end, n_out);
+}
+
+extern "C" int ygpu_pairs_copy(ygpu_ctx* ctx, void* dst, int dst_is_device) {
+    if (!ctx || (!dst && ctx->n_pairs)) return YGPU_ERR_ARG;
+    if (!ctx->n_pairs) return 0;
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    YG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_pairs, ctx->n_pairs * sizeof(ygpu_pair),
+                                 dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!dst_is_device) ctx->tm.ms_d2h += elapsed(ctx, 2, 3);
+    return 0;
+}
+
+extern "C" int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end,
+                                  ygpu_pair** out, uint64_t* n_out) {
+    if (!ctx || !out || !n_out) return YGPU_ERR_ARG;
+    *out = nullptr;
+    *n_out = 0;
+    uint64_t npairs = 0;
+    YG_CHECK(pairwise_device(ctx, threshold, row_begin, row_end, &npairs));
+    ygpu_pair* host = (ygpu_pair*)malloc(std::max<uint64_t>(npairs, 1) * sizeof(ygpu_pair));
+    if (!host) return ygpu_fail(ctx, YGPU_ERR_NOMEM, "malloc(%llu pairs)", (unsigned long long)npairs);
+    const int rc = ygpu_pairs_copy(ctx, host, 0);
+    if (rc) { free(host); return rc; }
     *out = host;
     *n_out = npairs;
     return 0;
+}
+
+// CUDA-event stopwatch on the context's stream (the stream every kernel of this library is
+// launched on), for callers that time whole steps from outside.
+extern "C" int ygpu_mark(ygpu_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot > 3) return YGPU_ERR_ARG;
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[4 + slot], ctx->stream));
+    return 0;
+}
+extern "C" int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms) {
+    if (!ctx || !ms || slot_a < 0 || slot_a > 3 || slot_b < 0 || slot_b > 3) return YGPU_ERR_ARG;
+    YG_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + slot_b]));
+    float f = 0.f;
+    YG_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev[4 + slot_a], ctx->ev[4 + slot_b]));
+    *ms = (double)f;
+    return 0;
+}
+extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return YGPU_ERR_ARG;
+    if (!strcmp(name, "force_tile_w")) { ctx->force_tile_w = (uint32_t)value; return 0; }
+    return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 
 extern "C" int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds) {

@@ -203,7 +203,7 @@ def workload_config(args, db):
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
-    from yacht_b200 import _lib
+    from yacht_b200 import _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,20 +249,20 @@ def run_b200_arm(args):
                 ctx.pairs_copy(buf.ctypes.data, False)
                 return buf
             return n_r
+        mine = torch.zeros(max(n_r, 1) * 3, dtype=torch.int32, device=dev)
+        if n_r:
+            ctx.pairs_copy(mine.data_ptr(), True)
+        if to_host:
+            return sharding.all_gather_pairs(mine, n_r, world)      # NCCL all-gather, merged + ordered on the host
         cnt = torch.tensor([n_r], dtype=torch.int64, device=dev)
         allc = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, cnt)
         sizes = allc.tolist()
         m = max(max(sizes), 1)
-        mine = torch.zeros(m * 3, dtype=torch.int32, device=dev)
-        if n_r:
-            ctx.pairs_copy(mine.data_ptr(), True)
+        padded = torch.zeros(m * 3, dtype=torch.int32, device=dev)
+        padded[: 3 * n_r] = mine[: 3 * n_r]
         allp = torch.empty(world * m * 3, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allp, mine)
-        if to_host:
-            parts = [allp[r * m * 3:(r * m + sizes[r]) * 3] for r in range(world)]
-            flat = torch.cat(parts).cpu().numpy()
-            return flat.view(_lib.PAIR_DTYPE)
+        dist.all_gather_into_tensor(allp, padded)
         torch.cuda.synchronize()   # the NCCL gather runs on torch's stream: finish it inside the timed step
         return sum(sizes)
 

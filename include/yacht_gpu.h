@@ -6,6 +6,7 @@
  * reference root; the train core is src/cpp/main.cpp, the run-side compute is
  * src/yacht/hypothesis_recovery_src.py):
  *
+ *   ygpu_read_signatures    read_min_hashes() / read_sketches()                main.cpp:62-124
  *   ygpu_load_sketches      the in-memory result of read_sketches()            main.cpp:89-124
  *                           (vector<vector<hash_t>> sketches, :51) as one flat
  *                           uint64 array + CSR offsets; genome id = file-list
@@ -20,6 +21,7 @@
  *                           sample: counts[g].n_overlap > 0), followed by
  *                           get_exclusive_hashes()                             hypothesis_recovery_src.py:116-206
  *   ygpu_hyp_test           single_hyp_test() + get_alt_mut_rate()             hypothesis_recovery_src.py:209-306
+ *   ygpu_alt_mut_rate       get_alt_mut_rate() on its own                      hypothesis_recovery_src.py:209-230
  *
  * Conventions: every function returns 0 on success and a negative ygpu_status otherwise; the
  * text of the last error is available from ygpu_last_error().  The caller owns every input
@@ -104,6 +106,16 @@ typedef struct {
     double alt_confidence_mut_rate_with_coverage;
 } ygpu_hyp_row;
 
+/* A set of sketches on the host, as ygpu_read_signatures returns it. */
+typedef struct {
+    uint64_t* hashes;       /* [offsets[n_genomes]] page-locked when pinned != 0                */
+    uint64_t* offsets;      /* [n_genomes + 1]                                                  */
+    uint32_t n_genomes;
+    uint32_t n_unreadable;  /* files that could not be opened (they yield empty sketches)       */
+    int32_t pinned;
+    int32_t _pad;
+} ygpu_sketch_set;
+
 /* ---- context ------------------------------------------------------------------------------ */
 int ygpu_device_count(void);
 int ygpu_ctx_create(ygpu_ctx** out, int device);
@@ -121,6 +133,14 @@ int ygpu_mark(ygpu_ctx* ctx, int slot);
 int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel.      */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
+
+/* ---- ingest (host side of the path) ------------------------------------------------------------ */
+/* Parse n sourmash signature files (uncompressed JSON) on `threads` host threads: sketch i =
+ * document[0]["signatures"][0]["mins"] of paths[i] (main.cpp:78); a file that cannot be opened
+ * yields an empty sketch (main.cpp:68-71); malformed JSON is an error (text in errbuf).          */
+int ygpu_read_signatures(const char* const* paths, uint32_t n, int threads, ygpu_sketch_set* out,
+                         char* errbuf, uint64_t errlen);
+void ygpu_sketch_set_free(ygpu_sketch_set* s);
 
 /* ---- train path ---------------------------------------------------------------------------- */
 /* hashes[offsets[g] .. offsets[g+1]) is sketch g (any order, duplicates allowed).  HOST pointers;
@@ -151,6 +171,10 @@ int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds);
 int ygpu_exclusive_hashes(ygpu_ctx* ctx, const uint64_t* sample, uint64_t n_sample,
                           const uint8_t* mask /* may be NULL */, ygpu_genome_counts* counts);
 /* rows[c * n + r] = single_hyp_test((n_exclusive[r], n_match[r]), ksize, significance, ani, cov[c]) */
+/* out[r] = get_alt_mut_rate(nu[r], thresh[r], ksize, significance)  (hypothesis_recovery_src.py:209-230),
+ * -1.0 where scipy's betaincinv returns NaN.                                                      */
+int ygpu_alt_mut_rate(ygpu_ctx* ctx, const int64_t* nu, const int64_t* thresh, uint64_t n, int ksize,
+                      double significance, double* out);
 int ygpu_hyp_test(ygpu_ctx* ctx, const int64_t* n_exclusive, const int64_t* n_match, uint64_t n,
                   int ksize, double significance, double ani_thresh, const double* min_coverage,
                   int n_cov, ygpu_hyp_row* rows);

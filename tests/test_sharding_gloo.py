@@ -1,0 +1,70 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the row sharding + pair-list gather
+(the same code path bench.py and multi-GPU callers use with NCCL on device tensors)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from yacht_b200 import sharding, synth
+from yacht_b200._lib import PAIR_DTYPE
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import train_oracle as to
+        db = synth.make_reference_db(300, 17, mean_size=200, sd_size=60)
+        full = to.oracle_train(db.hashes, db.offsets, 0.3).pairs
+        full3 = np.zeros(len(full), dtype=PAIR_DTYPE)
+        for f in ("i", "j", "count"):
+            full3[f] = full[f]
+        bounds = sharding.split_rows_by_work(db.sizes.astype(np.float64), world)
+        mine = sharding.owned_pairs(full3, int(bounds[rank]), int(bounds[rank + 1]))
+        merged = sharding.all_gather_pairs(mine, len(mine), world)
+        ok = merged.tobytes() == np.sort(full3, order=["i", "j"]).tobytes()
+        # a rank with nothing to report must not break the exchange
+        empty = sharding.all_gather_pairs(mine if rank == 0 else mine[:0], len(mine) if rank == 0 else 0, world)
+        ok = ok and len(empty) == len(sharding.owned_pairs(full3, int(bounds[0]), int(bounds[1])))
+        q.put((rank, bool(ok), len(mine), len(full3)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gather_matches_single_rank():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    assert sum(r[2] for r in res) == res[0][3]      # the shards partition the pair list
+    assert all(r[2] > 0 for r in res)
+
+
+def test_split_rows_by_work_properties():
+    rng = np.random.default_rng(0)
+    for n, parts in [(1000, 8), (5, 8), (0, 3), (97, 1)]:
+        w = rng.integers(0, 1000, size=n).astype(np.float64)
+        b = sharding.split_rows_by_work(w, parts)
+        assert b[0] == 0 and b[-1] == n and np.all(np.diff(b.astype(np.int64)) >= 0)
+        if n >= 100 * parts:
+            loads = [float((w[b[k]:b[k + 1]] + sharding.ROW_CONSTANT).sum()) for k in range(parts)]
+            assert max(loads) < 1.3 * (sum(loads) / parts)

@@ -1,0 +1,30 @@
+"""`python -m yacht_b200 train|run ...` -- the two sub-commands of the reference CLI that sit on the
+hot path (reference src/yacht/__init__.py:54-136); the other sub-commands (sketch, download,
+convert) are out of scope."""
+import argparse
+import sys
+
+from . import make_training_data_from_sketches, run_YACHT
+from .utils import __version__
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(prog="yacht", description="YACHT hot path on B200")
+    parser.add_argument("--version", action="version", version=f"yacht_b200 {__version__}")
+    sub = parser.add_subparsers(dest="command")
+    p_train = sub.add_parser("train", description="Pre-process the reference genomes")
+    make_training_data_from_sketches.add_arguments(p_train)
+    p_train.set_defaults(func=make_training_data_from_sketches.main)
+    p_run = sub.add_parser("run", description="Run the YACHT algorithm")
+    run_YACHT.add_arguments(p_run)
+    p_run.set_defaults(func=run_YACHT.main)
+    args = parser.parse_args(argv)
+    if "func" not in args:
+        parser.print_help(file=sys.stderr)
+        return 1
+    args.func(args)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

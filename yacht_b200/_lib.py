@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libyachtgpu.so")
 # every symbol include/yacht_gpu.h declares (tests check the library exports each of them)
 ABI_SYMBOLS = [
     "ygpu_device_count", "ygpu_ctx_create", "ygpu_ctx_destroy", "ygpu_last_error", "ygpu_free",
-    "ygpu_host_alloc", "ygpu_host_free", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
+    "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test",
@@ -45,6 +45,12 @@ class Timings(ctypes.Structure):
 
     def as_dict(self) -> dict:
         return {k: (float(getattr(self, k)) if t is ctypes.c_double else int(getattr(self, k))) for k, t in self._fields_}
+
+
+class SketchSet(ctypes.Structure):
+    _fields_ = [("hashes", ctypes.POINTER(ctypes.c_uint64)), ("offsets", ctypes.POINTER(ctypes.c_uint64)),
+                ("n_genomes", ctypes.c_uint32), ("n_unreadable", ctypes.c_uint32), ("pinned", ctypes.c_int32),
+                ("_pad", ctypes.c_int32)]
 
 
 PAIR_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("count", "<i4")])
@@ -82,6 +88,11 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_host_alloc.restype = vp
     lib.ygpu_host_free.argtypes = [vp]
     lib.ygpu_host_free.restype = None
+    lib.ygpu_read_signatures.argtypes = [ctypes.POINTER(ctypes.c_char_p), u32, ctypes.c_int, ctypes.POINTER(SketchSet),
+                                         ctypes.c_char_p, u64]
+    lib.ygpu_sketch_set_free.argtypes = [ctypes.POINTER(SketchSet)]
+    lib.ygpu_sketch_set_free.restype = None
+    lib.ygpu_alt_mut_rate.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, vp]
     lib.ygpu_reset_timers.argtypes = [vp]
     lib.ygpu_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.ygpu_load_sketches.argtypes = [vp, vp, vp, u32]
@@ -237,6 +248,35 @@ class GpuContext:
                                            float(significance), float(ani_thresh), cov.ctypes.data, cov.shape[0],
                                            rows.ctypes.data), "ygpu_hyp_test")
         return rows
+
+
+    def alt_mut_rate(self, nu: Sequence[int], thresh: Sequence[int], ksize: int, significance: float = 0.99) -> np.ndarray:
+        a = np.ascontiguousarray(nu, dtype=np.int64)
+        b = np.ascontiguousarray(thresh, dtype=np.int64)
+        out = np.zeros(a.shape[0], dtype=np.float64)
+        self._check(self.lib.ygpu_alt_mut_rate(self.h, a.ctypes.data, b.ctypes.data, a.shape[0], int(ksize),
+                                               float(significance), out.ctypes.data), "ygpu_alt_mut_rate")
+        return out
+
+
+def read_signatures(paths: Sequence[str], threads: int = 1) -> Tuple[np.ndarray, np.ndarray, int]:
+    """Multi-threaded native ingest of uncompressed .sig files -> (hashes, offsets, n_unreadable).
+    Mirrors the reference core's reader (main.cpp:62-124): first record, first sub-signature."""
+    lib = load_library()
+    n = len(paths)
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    ss = SketchSet()
+    err = ctypes.create_string_buffer(2048)
+    rc = lib.ygpu_read_signatures(arr, n, int(threads), ctypes.byref(ss), err, 2048)
+    if rc != 0:
+        raise YgpuError(f"ygpu_read_signatures failed ({rc}): {err.value.decode(errors='replace')}")
+    try:
+        offsets = np.ctypeslib.as_array(ss.offsets, shape=(n + 1,)).copy()
+        T = int(offsets[-1])
+        hashes = np.ctypeslib.as_array(ss.hashes, shape=(max(T, 1),))[:T].copy() if T else np.zeros(0, dtype=np.uint64)
+        return hashes, offsets, int(ss.n_unreadable)
+    finally:
+        lib.ygpu_sketch_set_free(ctypes.byref(ss))
 
 
 def device_count() -> int:

@@ -1,0 +1,100 @@
+// ingest.hpp -- file list -> flat (pinned) uint64 hash array + CSR offsets, on all host cores.
+// Replaces read_sketches / read_sketches_one_chunk of the reference (src/cpp/main.cpp:89-124):
+// same result (sketch i = mins of file i; unreadable file => message + empty sketch, :68-71),
+// but the files are claimed dynamically in small blocks instead of one static chunk per thread,
+// parsed by the purpose-built scanner of sig_scan.hpp, and assembled directly into one
+// page-locked buffer that ygpu_load_sketches can DMA from.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/yacht_gpu.h"
+#include "sig_scan.hpp"
+
+namespace yingest {
+
+struct Ingest {
+    std::vector<std::string> names;
+    uint64_t* hashes = nullptr;      // pinned (ygpu_host_alloc) or malloc
+    bool pinned = false;
+    std::vector<uint64_t> offsets;   // n + 1
+    std::vector<int> empty_ids;
+    bool fatal = false;
+    bool quiet = false;              // library use: do not print the per-file message
+    std::atomic<uint32_t> n_unreadable{0};
+    std::string fatal_msg;
+};
+
+constexpr uint32_t kFilesPerBlock = 32;
+
+inline void read_sketches(Ingest& in, int threads) {
+    const uint32_t n = (uint32_t)in.names.size();
+    const uint32_t nblocks = (n + kFilesPerBlock - 1) / kFilesPerBlock;
+    std::vector<std::vector<uint64_t>> block_hashes(nblocks);
+    std::vector<uint32_t> sizes(n, 0);
+    std::atomic<uint32_t> next{0};
+    std::mutex mu;
+    auto worker = [&]() {
+        std::vector<char> buf;
+        for (;;) {
+            const uint32_t b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            std::vector<uint64_t>& out = block_hashes[b];
+            const uint32_t f0 = b * kFilesPerBlock, f1 = std::min(n, f0 + kFilesPerBlock);
+            for (uint32_t f = f0; f < f1; f++) {
+                const size_t before = out.size();
+                std::string why;
+                const sigscan::Status st = sigscan::read_mins(in.names[f], buf, out, &why);
+                if (st == sigscan::CANNOT_OPEN) {
+                    if (!in.quiet) std::cerr << "Could not open the file!" << std::endl;  // main.cpp:69
+                    in.n_unreadable.fetch_add(1);
+                    out.resize(before);
+                } else if (st == sigscan::MALFORMED) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!in.fatal) { in.fatal = true; in.fatal_msg = in.names[f] + ": " + why; }
+                    out.resize(before);
+                }
+                sizes[f] = (uint32_t)(out.size() - before);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    const int nt = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(nblocks, 1)));
+    for (int t = 0; t < nt; t++) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+
+    in.offsets.assign((size_t)n + 1, 0);
+    for (uint32_t f = 0; f < n; f++) {
+        in.offsets[f + 1] = in.offsets[f] + sizes[f];
+        if (sizes[f] == 0) in.empty_ids.push_back((int)f);
+    }
+    const uint64_t T = in.offsets[n];
+    in.hashes = (uint64_t*)ygpu_host_alloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
+    in.pinned = in.hashes != nullptr;
+    if (!in.hashes) in.hashes = (uint64_t*)malloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
+    std::atomic<uint32_t> nextb{0};
+    auto copier = [&]() {
+        for (;;) {
+            const uint32_t b = nextb.fetch_add(1);
+            if (b >= nblocks) break;
+            const uint64_t dst = in.offsets[(size_t)b * kFilesPerBlock];
+            if (!block_hashes[b].empty())
+                memcpy(in.hashes + dst, block_hashes[b].data(), block_hashes[b].size() * sizeof(uint64_t));
+            std::vector<uint64_t>().swap(block_hashes[b]);
+        }
+    };
+    pool.clear();
+    for (int t = 0; t < nt; t++) pool.emplace_back(copier);
+    for (auto& t : pool) t.join();
+}
+
+
+}  // namespace yingest

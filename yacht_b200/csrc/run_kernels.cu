@@ -302,3 +302,44 @@ extern "C" int ygpu_hyp_test(ygpu_ctx* ctx, const int64_t* n_exclusive, const in
     cleanup();
     return 0;
 }
+
+// get_alt_mut_rate on its own (the reference unit-tests it directly: tests/test_unit.py:11-20)
+__global__ void __launch_bounds__(128) k6_alt_mut_rate(const long long* __restrict__ nu, const long long* __restrict__ thresh,
+                                                        uint64_t n, int ksize, double significance, double* __restrict__ out) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const double x = ystats::betaincinv_int((double)nu[t], (double)thresh[t], significance);
+        double mut = 1.0 - pow(1.0 - x, 1.0 / (double)ksize);
+        if (isnan(mut)) mut = -1.0;
+        out[t] = mut;
+    }
+}
+
+extern "C" int ygpu_alt_mut_rate(ygpu_ctx* ctx, const int64_t* nu, const int64_t* thresh, uint64_t n, int ksize,
+                                 double significance, double* out) {
+    if (!ctx) return YGPU_ERR_ARG;
+    if (n == 0) return 0;
+    if (!nu || !thresh || !out) return ygpu_fail(ctx, YGPU_ERR_ARG, "alt_mut_rate: NULL argument");
+    if (ksize < 1) return ygpu_fail(ctx, YGPU_ERR_ARG, "alt_mut_rate: ksize must be >= 1");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    long long *d_nu = nullptr, *d_th = nullptr;
+    double* d_out = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_nu, n * 8)) != cudaSuccess || (e = cudaMalloc(&d_th, n * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&d_out, n * 8)) != cudaSuccess) {
+        if (d_nu) cudaFree(d_nu);
+        if (d_th) cudaFree(d_th);
+        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "alt_mut_rate: cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(d_nu, nu, n * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_th, thresh, n * 8, cudaMemcpyHostToDevice, st);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->num_sms * 16));
+    k6_alt_mut_rate<<<grid, 128, 0, st>>>(d_nu, d_th, n, ksize, significance, d_out);
+    e = cudaGetLastError();
+    ctx->tm.n_kernel_launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_nu); cudaFree(d_th); cudaFree(d_out);
+    if (e != cudaSuccess) return ygpu_fail(ctx, YGPU_ERR_CUDA, "alt_mut_rate: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -33,7 +33,7 @@
 #include <vector>
 
 #include "../../include/yacht_gpu.h"
-#include "sig_scan.hpp"
+#include "ingest.hpp"
 
 namespace {
 
@@ -140,79 +140,6 @@ void show_arguments(const Arguments& a) {  // main.cpp:187-199
     cout << "**************************************" << endl;
 }
 
-// ---- ingest: file list -> flat pinned hash array + offsets ------------------------------------
-struct Ingest {
-    std::vector<std::string> names;
-    uint64_t* hashes = nullptr;      // pinned (ygpu_host_alloc) or malloc
-    bool pinned = false;
-    std::vector<uint64_t> offsets;   // n + 1
-    std::vector<int> empty_ids;
-    bool fatal = false;
-    std::string fatal_msg;
-};
-
-constexpr uint32_t kFilesPerBlock = 32;
-
-void read_sketches(Ingest& in, int threads) {
-    const uint32_t n = (uint32_t)in.names.size();
-    const uint32_t nblocks = (n + kFilesPerBlock - 1) / kFilesPerBlock;
-    std::vector<std::vector<uint64_t>> block_hashes(nblocks);
-    std::vector<uint32_t> sizes(n, 0);
-    std::atomic<uint32_t> next{0};
-    std::mutex mu;
-    auto worker = [&]() {
-        std::vector<char> buf;
-        for (;;) {
-            const uint32_t b = next.fetch_add(1);
-            if (b >= nblocks) break;
-            std::vector<uint64_t>& out = block_hashes[b];
-            const uint32_t f0 = b * kFilesPerBlock, f1 = std::min(n, f0 + kFilesPerBlock);
-            for (uint32_t f = f0; f < f1; f++) {
-                const size_t before = out.size();
-                std::string why;
-                const sigscan::Status st = sigscan::read_mins(in.names[f], buf, out, &why);
-                if (st == sigscan::CANNOT_OPEN) {
-                    std::cerr << "Could not open the file!" << std::endl;  // main.cpp:69
-                    out.resize(before);
-                } else if (st == sigscan::MALFORMED) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    if (!in.fatal) { in.fatal = true; in.fatal_msg = in.names[f] + ": " + why; }
-                    out.resize(before);
-                }
-                sizes[f] = (uint32_t)(out.size() - before);
-            }
-        }
-    };
-    std::vector<std::thread> pool;
-    const int nt = std::max(1, std::min<int>(threads, (int)std::max<uint32_t>(nblocks, 1)));
-    for (int t = 0; t < nt; t++) pool.emplace_back(worker);
-    for (auto& t : pool) t.join();
-
-    in.offsets.assign((size_t)n + 1, 0);
-    for (uint32_t f = 0; f < n; f++) {
-        in.offsets[f + 1] = in.offsets[f] + sizes[f];
-        if (sizes[f] == 0) in.empty_ids.push_back((int)f);
-    }
-    const uint64_t T = in.offsets[n];
-    in.hashes = (uint64_t*)ygpu_host_alloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
-    in.pinned = in.hashes != nullptr;
-    if (!in.hashes) in.hashes = (uint64_t*)malloc(std::max<uint64_t>(T, 1) * sizeof(uint64_t));
-    std::atomic<uint32_t> nextb{0};
-    auto copier = [&]() {
-        for (;;) {
-            const uint32_t b = nextb.fetch_add(1);
-            if (b >= nblocks) break;
-            const uint64_t dst = in.offsets[(size_t)b * kFilesPerBlock];
-            if (!block_hashes[b].empty())
-                memcpy(in.hashes + dst, block_hashes[b].data(), block_hashes[b].size() * sizeof(uint64_t));
-            std::vector<uint64_t>().swap(block_hashes[b]);
-        }
-    };
-    pool.clear();
-    for (int t = 0; t < nt; t++) pool.emplace_back(copier);
-    for (auto& t : pool) t.join();
-}
-
 struct DeviceResult {
     int rc = 0;
     std::string err;
@@ -248,7 +175,7 @@ int main(int argc, char** argv) {
     // ---- read ----------------------------------------------------------------------------------
     auto t_read = std::chrono::high_resolution_clock::now();
     std::cout << "Reading all sketches in filelist using all " << args.number_of_threads << " threads..." << std::endl;
-    Ingest in;
+    yingest::Ingest in;
     {
         std::ifstream fl(args.file_list);
         if (!fl.is_open()) std::cerr << "Could not open the filelist: " << args.file_list << std::endl;  // main.cpp:131
@@ -257,7 +184,7 @@ int main(int argc, char** argv) {
     }
     const uint32_t n = (uint32_t)in.names.size();
     std::cout << "Total number of sketches to read: " << n << std::endl;
-    read_sketches(in, args.number_of_threads);
+    yingest::read_sketches(in, args.number_of_threads);
     if (in.fatal) {
         std::cerr << "run_yacht_train_core: cannot parse signature " << in.fatal_msg << std::endl;
         return 4;

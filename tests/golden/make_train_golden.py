@@ -83,7 +83,7 @@ def main():
                         abundances=ab, has_abund=np.array([s.abundances is not None for s in sigs]),
                         max_hash=np.array([s.max_hash for s in sigs], dtype=np.uint64),
                         sample_hashes=sample.mins, sample_abundances=sample.abundances,
-                        sample_name=np.array(sample.name), sample_md5=np.array(sample.md5sum),
+                        sample_name=np.array(str(sample.name or "sample")), sample_md5=np.array(sample.md5sum),
                         sample_max_hash=np.array(sample.max_hash, dtype=np.uint64))
     out["fixture20"] = run_ref(db, 0.95 ** 31)
     out["fixture20_thr0"] = run_ref(db, 0.0)

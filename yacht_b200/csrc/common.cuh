@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <unordered_map>
+#include <algorithm>
 #include "../../include/yacht_gpu.h"
 
 struct ygpu_ctx {
@@ -77,7 +78,69 @@ int ygpu_fail(ygpu_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 int ygpu_temp_reserve(ygpu_ctx* ctx, size_t bytes);
+
+// Capacity-tracked device buffers: a buffer is reused when it is already large enough, so that
+// repeated steps (bench loops, multi-sample runs) do not pay cudaMalloc/cudaFree -- which
+// synchronise the device and cost milliseconds per GB -- inside the hot path.
+template <typename T>
+static inline int dev_alloc(ygpu_ctx* ctx, T** p, uint64_t count) {
+    if (count == 0) count = 1;
+    const size_t bytes = count * sizeof(T);
+    auto it = ctx->caps.find((void*)p);
+    if (*p && it != ctx->caps.end() && it->second >= bytes) return 0;
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    const size_t want = bytes + (bytes >> 4) + 256;
+    cudaError_t e = cudaMalloc((void**)p, want);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        ctx->caps.erase((void*)p);
+        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)want, cudaGetErrorString(e));
+    }
+    ctx->caps[(void*)p] = want;
+    return 0;
+}
+template <typename T>
+static inline void dev_free(ygpu_ctx* ctx, T** p) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    ctx->caps.erase((void*)p);
+}
+
+static inline float elapsed(ygpu_ctx* ctx, int a, int b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+    return ms;
+}
+
+// device scalar slots (ctx->d_scalars)
+enum { SC_HEADS = 0, SC_SINGLE = 1, SC_DUPS = 2, SC_W = 3, SC_OUT = 4, SC_UNIT = 5, SC_MAXKEY = 6 };
+
+template <int BS>
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {
+    __shared__ unsigned long long sh[BS / 32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = 0;
+    if (w == 0) {
+        v = (l < BS / 32) ? sh[l] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;  // valid in thread 0
+}
+
+static inline int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8) {
+    uint64_t blocks = (work + bs - 1) / bs;
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+
 int ygpu_sort_sketches(ygpu_ctx* ctx);   // K2a (yacht_gpu.cu)
+// MSD-partition index build (index_msd.cu): *used = 0 when the input does not qualify for it
+int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used);
 
 // run path (run_kernels.cu)
 void ygpu_run_release(ygpu_ctx* ctx);

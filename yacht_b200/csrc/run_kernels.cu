@@ -124,12 +124,6 @@ __global__ void __launch_bounds__(256) k5_exclusive(const uint64_t* __restrict__
     }
 }
 
-static int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8) {
-    uint64_t blocks = (work + bs - 1) / bs;
-    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
-    return (int)std::max<uint64_t>(1, std::min(blocks, cap));
-}
-
 extern "C" int ygpu_exclusive_hashes(ygpu_ctx* ctx, const uint64_t* sample, uint64_t n_sample, const uint8_t* mask,
                                      ygpu_genome_counts* counts) {
     if (!ctx || !counts) return YGPU_ERR_ARG;

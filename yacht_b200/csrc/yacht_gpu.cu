@@ -45,39 +45,6 @@ int ygpu_temp_reserve(ygpu_ctx* ctx, size_t bytes) {
     return 0;
 }
 
-// Capacity-tracked device buffers: a buffer is reused when it is already large enough, so that
-// repeated steps (bench loops, multi-sample runs) do not pay cudaMalloc/cudaFree -- which
-// synchronise the device and cost milliseconds per GB -- inside the hot path.
-template <typename T>
-static int dev_alloc(ygpu_ctx* ctx, T** p, uint64_t count) {
-    if (count == 0) count = 1;
-    const size_t bytes = count * sizeof(T);
-    auto it = ctx->caps.find((void*)p);
-    if (*p && it != ctx->caps.end() && it->second >= bytes) return 0;
-    if (*p) { cudaFree(*p); *p = nullptr; }
-    const size_t want = bytes + (bytes >> 4) + 256;
-    cudaError_t e = cudaMalloc((void**)p, want);
-    if (e != cudaSuccess) {
-        *p = nullptr;
-        ctx->caps.erase((void*)p);
-        return ygpu_fail(ctx, YGPU_ERR_NOMEM, "cudaMalloc(%llu bytes): %s", (unsigned long long)want, cudaGetErrorString(e));
-    }
-    ctx->caps[(void*)p] = want;
-    return 0;
-}
-template <typename T>
-static void dev_free(ygpu_ctx* ctx, T** p) {
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    ctx->caps.erase((void*)p);
-}
-
-static float elapsed(ygpu_ctx* ctx, int a, int b) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
-    return ms;
-}
-
 // ============================================================================================
 // context
 // ============================================================================================
@@ -262,24 +229,6 @@ extern "C" int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes
 // ============================================================================================
 // K2: inverted index
 // ============================================================================================
-enum { SC_HEADS = 0, SC_SINGLE = 1, SC_DUPS = 2, SC_W = 3, SC_OUT = 4, SC_UNIT = 5, SC_MAXKEY = 6 };
-
-template <int BS>
-__device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {
-    __shared__ unsigned long long sh[BS / 32];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    v = 0;
-    if (w == 0) {
-        v = (l < BS / 32) ? sh[l] : 0ull;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    }
-    return v;  // valid in thread 0
-}
-
 // flag[s] = 1 iff sorted slot s lies in a run (equal hashes) of length >= 2.  Also counts the
 // distinct hashes, the singletons (the three banner lines of main.cpp:242-244) and in-sketch
 // duplicates (same hash twice in one genome).
@@ -362,12 +311,6 @@ __global__ void __launch_bounds__(256) k_items_scatter(const uint32_t* __restric
         const unsigned long long k = atomicAdd(&row_fill[g], 1ull);
         row_items[row_ptr[g] + k] = ((uint64_t)(c + 1) << 32) | (uint64_t)r;
     }
-}
-
-static int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8) {
-    uint64_t blocks = (work + bs - 1) / bs;
-    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
-    return (int)std::max<uint64_t>(1, std::min(blocks, cap));
 }
 
 // K2a: stable radix sort of (hash, genome id); equal-hash runs become posting lists in ascending

@@ -98,7 +98,7 @@ def parse_signature_json(text: str, path: str = "") -> List[Signature]:
             mins = np.array(sub.get("mins", []), dtype=np.uint64)
             ab = sub.get("abundances")
             out.append(Signature(
-                name=rec.get("name", "") or rec.get("filename", ""),
+                name=rec.get("name") or rec.get("filename") or "",
                 ksize=int(sub.get("ksize", 0)),
                 mins=mins,
                 abundances=None if ab is None else np.array(ab, dtype=np.int64),

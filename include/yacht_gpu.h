@@ -68,6 +68,8 @@ typedef struct {
     uint64_t n_row_items;   /* entries of the per-genome work lists (implementation detail)    */
     uint32_t max_sketch;    /* largest sketch size                                             */
     uint32_t has_duplicates;/* 1 if some sketch holds the same hash twice                      */
+    uint32_t index_path;    /* 1 = MSD partition + shared-memory grouping, 0 = general sort path */
+    uint32_t _pad;
 } ygpu_index_stats;
 
 /* Device timings (CUDA events on the context's stream) accumulated since ygpu_reset_timers(). */
@@ -131,7 +133,8 @@ int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out);
 /* CUDA-event stopwatch on the context's stream (slots 0..3): time a whole step from outside.    */
 int ygpu_mark(ygpu_ctx* ctx, int slot);
 int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
-/* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel.      */
+/* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel;
+ * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default).   */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

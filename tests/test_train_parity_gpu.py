@@ -18,16 +18,27 @@ def _pairs_tuple(p):
     return [(int(a), int(b), int(c)) for a, b, c in zip(p["i"], p["j"], p["count"])]
 
 
-def _check(ctx, db, thr):
-    ctx.load_sketches(db.hashes, db.offsets)
-    st = ctx.build_index()
-    got = ctx.pairwise_flag(thr)
+def _check(ctx, db, thr, expect_path=None):
+    """Both index builds (1 = MSD partition when the input qualifies, 0 = general sort path) against the oracle."""
     ref = to.oracle_train(db.hashes, db.offsets, thr)
-    assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index)
-    assert st["n_postings"] == ref.n_postings
-    assert st["n_increments"] == ref.n_increments
-    assert _pairs_tuple(got) == _pairs_tuple(ref.pairs)
-    return st, got
+    out = None
+    for path in (1, 0):
+        ctx.set_option("index_path", path)
+        ctx.load_sketches(db.hashes, db.offsets)
+        st = ctx.build_index()
+        got = ctx.pairwise_flag(thr)
+        assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index), (path, st)
+        assert st["n_postings"] == ref.n_postings, (path, st)
+        assert st["n_increments"] == ref.n_increments, (path, st)
+        assert _pairs_tuple(got) == _pairs_tuple(ref.pairs), path
+        if path == 1:
+            out = (st, got)
+            if expect_path is not None:
+                assert st["index_path"] == expect_path, st
+        else:
+            assert st["index_path"] == 0
+    ctx.set_option("index_path", 1)
+    return out
 
 
 def test_edge_set(gpu_ctx):
@@ -86,6 +97,25 @@ def test_row_ranges_union(gpu_ctx):
 
 
 def test_skewed_long_postings(gpu_ctx):
-    # conserved-core hashes present in many genomes: long posting lists, touched-list overflow
+    # conserved-core hashes present in many genomes: long posting lists, touched-list overflow; the
+    # buckets holding them overflow shared memory, so the build falls back to the general path
     db = synth.make_reference_db(6000, 9, mean_size=60, sd_size=10, min_size=20, core_hashes=6, core_lo=0.7, core_hi=0.95)
-    _check(gpu_ctx, db, 0.05)
+    _check(gpu_ctx, db, 0.05, expect_path=0)
+
+
+def test_long_groups_inside_msd_buckets(gpu_ctx):
+    # posting lists of ~1000 genomes that still fit a shared-memory bucket: the CTA-wide group path
+    db = synth.make_reference_db(1500, 10, mean_size=60, sd_size=10, min_size=20, core_hashes=5, core_lo=0.5, core_hi=0.8)
+    st, _ = _check(gpu_ctx, db, 0.05, expect_path=1)
+    assert st["n_postings"] > 3000
+
+
+def test_msd_two_level_partition(gpu_ctx):
+    # enough hashes for two partition levels (d2 > 0) and duplicates inside sketches
+    db = synth.make_reference_db(2500, 12, mean_size=1200, sd_size=300)
+    parts = [db.sketch(g) for g in range(db.n)]
+    parts[3] = np.concatenate([parts[3], parts[3][:40]])          # the same hash twice in one sketch
+    parts[7] = np.concatenate([parts[7], parts[3][:10], parts[3][:10]])
+    db2 = synth.from_sketches(parts)
+    st, _ = _check(gpu_ctx, db2, THR, expect_path=1)
+    assert st["has_duplicates"] == 1

@@ -39,6 +39,14 @@ struct ygpu_ctx {
     uint64_t* d_row_items = nullptr;// [n_items] (first posting slot << 32) | count  -- per query genome
     uint64_t* d_row_work = nullptr; // [n]   increments row i performs (sum of counts)
     unsigned long long* d_row_cnt = nullptr;  // [n+1] build scratch
+    // MSD-partition build (index_msd.cu)
+    uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets
+    uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
+    uint32_t* d_rec_gid = nullptr;  // [I] work records before they are grouped by genome
+    uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
+    int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
+    int msd_fallbacks = 0;
+    int last_index_path = 0;        // which path built the current index
     ygpu_index_stats stats = {};
 
     // ---- scratch ------------------------------------------------------------------------------

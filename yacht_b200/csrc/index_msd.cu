@@ -1,0 +1,611 @@
+// libyachtgpu -- K2 (inverted index) without a full sort: MSD radix partition + in-shared-memory
+// hash grouping.  sm_100a only.
+//
+// Replaces compute_index_from_sketches() of the reference (src/cpp/main.cpp:215-246), which inserts
+// every hash into one unordered_map on one host thread.  What the pairwise kernel needs is weaker
+// than a sorted index: for every hash held by >= 2 genome slots, the list of those genomes
+// (ascending), and for every genome the list of "postings that follow me".  So instead of sorting
+// T (hash, genome) pairs by all 55 significant bits (7 radix passes over 12-byte pairs), this path
+//   1. packs (hash low bits, genome id) into ONE 64-bit word -- the leading d1 hash bits are implied
+//      by the level-1 bucket, so 55 - d1 + ceil(log2 N) bits fit --
+//   2. partitions the words by the leading d1 and then the next d2 hash bits into ~T/1500 final
+//      buckets (two coalesced scatter passes of 8 bytes per element, tile-staged in shared memory),
+//   3. groups equal hashes inside each bucket with a shared-memory hash table (one 16-bit CAS per
+//      element; no ordering of the ~80 % singleton hashes is ever computed), sorts only the members
+//      of shared groups by genome id, and emits compact postings + per-genome work records.
+// Algorithmic HBM traffic: 8T (histogram) + 12T + 8T (scatter 1) + 8T (histogram 2) + 16T (scatter 2)
+// + 8T (bucket read) + O(P) outputs ~= 60 bytes per hash, against ~176 for the 7-pass pair sort.
+//
+// The general path (yacht_gpu.cu, CUB radix sort) remains for inputs this one does not cover:
+// hash width + genome-id width too large to pack, or a final bucket that overflows shared memory
+// (heavily skewed posting lists).  The choice is made per database from the measured bucket
+// histogram -- "chosen by measured posting-list skew".
+#include "common.cuh"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+namespace {
+
+constexpr int SC_TILE = 4096;       // elements per scatter tile (256 threads x 16)
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = SC_TILE / SC_THREADS;
+constexpr int NB_MAX = 2048;        // digits per partition level
+constexpr int BK_CAP = 3840;        // max elements of a final bucket (shared-memory resident)
+constexpr int BK_HS = 8192;         // hash-table slots per bucket (> BK_CAP: never full)
+constexpr int BK_THREADS = 256;
+constexpr int BK_KMAX = 12;         // groups up to this size are ordered by one thread in registers
+constexpr int BK_LONGQ = 304;       // > BK_CAP / (BK_KMAX + 1) = 295: queue of larger groups
+constexpr uint32_t A_TARGET = 1536; // average elements per used final bucket
+
+enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10 };   // extra slots of ctx->d_scalars
+
+struct MsdPlan {
+    int hb, gb, d1, d2, kb1;
+    uint32_t nb1;     // used level-1 buckets
+    uint32_t nfb;     // final buckets (nb1 << d2)
+    uint64_t T;
+};
+
+__device__ __forceinline__ uint32_t digit1_of(uint64_t key, const MsdPlan& p) {
+    return p.d1 ? (uint32_t)(key >> (p.hb - p.d1)) : 0u;
+}
+__device__ __forceinline__ uint64_t pack_entry(uint64_t key, uint32_t gid, const MsdPlan& p) {
+    const uint64_t low = (p.kb1 >= 64) ? key : (key & ((1ull << p.kb1) - 1ull));
+    return (low << p.gb) | (uint64_t)gid;
+}
+__device__ __forceinline__ uint32_t digit2_of(uint64_t e, const MsdPlan& p) {
+    return p.d2 ? (uint32_t)((e >> (p.gb + p.kb1 - p.d2)) & ((1u << p.d2) - 1u)) : 0u;
+}
+
+// ---- level-1 histogram ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k2_hist1(const uint64_t* __restrict__ hashes, const MsdPlan p, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t sh[];
+    for (uint32_t i = threadIdx.x; i < p.nb1; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.T; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[digit1_of(hashes[i], p)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < p.nb1; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// one CTA: bucket bases, tile prefix (for level-2 work units) and cursors from the level-1 histogram
+__global__ void __launch_bounds__(1024) k2_prep1(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ base,
+                                                  uint32_t* __restrict__ tile_start, uint32_t* __restrict__ cursor,
+                                                  unsigned long long* __restrict__ scal) {
+    typedef cub::BlockScan<uint32_t, 1024> Scan;
+    __shared__ typename Scan::TempStorage ts1, ts2;
+    const int per = (NB_MAX + 1023) / 1024;
+    uint32_t h[per], t[per], hs = 0, tsum = 0, mx = 0;
+    for (int k = 0; k < per; k++) {
+        const uint32_t i = threadIdx.x * per + k;
+        h[k] = i < nb ? hist[i] : 0u;
+        t[k] = (h[k] + SC_TILE - 1) / SC_TILE;
+        hs += h[k]; tsum += t[k]; mx = max(mx, h[k]);
+    }
+    uint32_t hoff, toff, htot, ttot;
+    Scan(ts1).ExclusiveSum(hs, hoff, htot);
+    Scan(ts2).ExclusiveSum(tsum, toff, ttot);
+    for (int k = 0; k < per; k++) {
+        const uint32_t i = threadIdx.x * per + k;
+        if (i < nb) { base[i] = hoff; cursor[i] = hoff; tile_start[i] = toff; }
+        hoff += h[k]; toff += t[k];
+    }
+    if (threadIdx.x == 0) { base[nb] = htot; tile_start[nb] = ttot; }
+    if (mx) atomicMax(&scal[SCM_MAXB], (unsigned long long)mx);
+}
+
+// ---- scatter (level 1: raw hashes -> packed words by leading digit; level 2: words -> final buckets)
+struct ScatterArgs {
+    const uint64_t* hashes;      // level 1 input
+    const uint32_t* gid;
+    const uint64_t* in_ent;      // level 2 input
+    uint64_t* out_ent;
+    const uint32_t* base1;       // level 2: level-1 bucket bases
+    const uint32_t* tile_start;  // level 2: prefix of tiles per level-1 bucket ([nb1] = number of units)
+    uint32_t* cursor;            // per output bucket
+    uint32_t* hist2;             // hist2 kernel only
+};
+
+template <int LEVEL>
+__device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& p, uint32_t unit, uint64_t& begin, uint32_t& m,
+                                           uint32_t& b1) {
+    if (LEVEL == 1) {
+        begin = (uint64_t)unit * SC_TILE;
+        if (begin >= p.T) return false;
+        m = (uint32_t)min((uint64_t)SC_TILE, p.T - begin);
+        b1 = 0;
+        return true;
+    }
+    const uint32_t units = a.tile_start[p.nb1];
+    if (unit >= units) return false;
+    // level-1 bucket holding this tile: last b with tile_start[b] <= unit
+    uint32_t lo = 0, hi = p.nb1;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.tile_start[mid] <= unit) lo = mid; else hi = mid;
+    }
+    b1 = lo;
+    const uint32_t k = unit - a.tile_start[lo];
+    const uint32_t bb = a.base1[lo], be = a.base1[lo + 1];
+    begin = (uint64_t)bb + (uint64_t)k * SC_TILE;
+    m = (uint32_t)min((uint64_t)SC_TILE, (uint64_t)be - begin);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPlan p) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t nd = 1u << p.d2;
+    for (uint32_t unit = blockIdx.x;; unit += gridDim.x) {
+        uint64_t begin; uint32_t m, b1;
+        if (!unit_range<2>(a, p, unit, begin, m, b1)) break;
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) atomicAdd(&sh[digit2_of(a.in_ent[begin + i], p)], 1u);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x)
+            if (sh[i]) atomicAdd(&a.hist2[((uint64_t)b1 << p.d2) + i], sh[i]);
+        __syncthreads();
+    }
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t n_units_l1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* stage = (uint64_t*)smem_raw;                         // [SC_TILE]
+    uint32_t* cnt = (uint32_t*)(stage + SC_TILE);                  // [nd]
+    const uint32_t nd = LEVEL == 1 ? p.nb1 : (1u << p.d2);
+    uint32_t* lbase = cnt + nd;                                    // [nd]
+    uint32_t* gbase = lbase + nd;                                  // [nd]
+    uint16_t* sdig = (uint16_t*)(gbase + nd);                      // [SC_TILE]
+    typedef cub::BlockScan<uint32_t, SC_THREADS> Scan;
+    __shared__ typename Scan::TempStorage scan_ts;
+
+    for (uint32_t unit = blockIdx.x;; unit += gridDim.x) {
+        uint64_t begin; uint32_t m, b1;
+        if (LEVEL == 1 && unit >= n_units_l1) break;
+        if (!unit_range<LEVEL>(a, p, unit, begin, m, b1)) break;
+        for (uint32_t i = threadIdx.x; i < nd; i += SC_THREADS) cnt[i] = 0;
+        __syncthreads();
+        uint64_t e[SC_ITEMS];
+        uint16_t dg[SC_ITEMS], rk[SC_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++) {
+            const uint32_t idx = k * SC_THREADS + threadIdx.x;
+            if (idx < m) {
+                if (LEVEL == 1) {
+                    const uint64_t key = a.hashes[begin + idx];
+                    dg[k] = (uint16_t)digit1_of(key, p);
+                    e[k] = pack_entry(key, a.gid[begin + idx], p);
+                } else {
+                    e[k] = a.in_ent[begin + idx];
+                    dg[k] = (uint16_t)digit2_of(e[k], p);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++) {
+            const uint32_t idx = k * SC_THREADS + threadIdx.x;
+            if (idx < m) rk[k] = (uint16_t)atomicAdd(&cnt[dg[k]], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of cnt -> lbase; reserve global space per digit -> gbase
+        {
+            const uint32_t per = (nd + SC_THREADS - 1) / SC_THREADS;
+            const uint32_t d0 = threadIdx.x * per;
+            uint32_t s = 0;
+            for (uint32_t k = 0; k < per; k++) if (d0 + k < nd) s += cnt[d0 + k];
+            uint32_t off;
+            Scan(scan_ts).ExclusiveSum(s, off);
+            for (uint32_t k = 0; k < per; k++) {
+                const uint32_t d = d0 + k;
+                if (d < nd) {
+                    const uint32_t c = cnt[d];
+                    lbase[d] = off;
+                    off += c;
+                    if (c) {
+                        const uint64_t ci = LEVEL == 1 ? (uint64_t)d : (((uint64_t)b1 << p.d2) + d);
+                        gbase[d] = atomicAdd(&a.cursor[ci], c);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++) {
+            const uint32_t idx = k * SC_THREADS + threadIdx.x;
+            if (idx < m) {
+                const uint32_t q = lbase[dg[k]] + rk[k];
+                stage[q] = e[k];
+                sdig[q] = dg[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++) {
+            const uint32_t q = k * SC_THREADS + threadIdx.x;
+            if (q < m) {
+                const uint32_t d = sdig[q];
+                a.out_ent[(uint64_t)gbase[d] + (q - lbase[d])] = stage[q];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- bucket kernel: group equal hashes in shared memory, emit postings + work records ------------
+struct BucketArgs {
+    const uint64_t* ent;
+    const uint32_t* base;        // [nb + 1]
+    uint32_t nb;
+    int gb;
+    uint32_t* post;              // compact postings (genome ids), groups contiguous, ascending inside a group
+    uint32_t* rec_gid;           // work records: the query genome ...
+    uint64_t* rec_item;          // ... and (first following posting << 32) | how many follow
+    unsigned long long* row_cnt;
+    unsigned long long* row_work;
+    unsigned long long* scal;
+};
+
+__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem, uint64_t q) {
+    a.rec_gid[q] = g;
+    a.rec_item[q] = (next_pos << 32) | (uint64_t)rem;
+    atomicAdd(&a.row_cnt[g], 1ull);
+    atomicAdd(&a.row_work[g], (unsigned long long)rem);
+}
+
+__global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* E = (uint64_t*)smem_raw;                               // [BK_CAP]
+    unsigned short* H = (unsigned short*)(E + BK_CAP);               // [BK_HS] head entry of each key's chain
+    unsigned short* nxt = H + BK_HS;                                 // [BK_CAP]
+    unsigned short* longq = nxt + BK_CAP;                            // [BK_LONGQ] head entries of large groups
+    uint32_t* scratch = (uint32_t*)H;                                // [BK_CAP] reused once the chains of large groups are queued
+    typedef cub::BlockScan<uint32_t, BK_THREADS> Scan;
+    __shared__ typename Scan::TempStorage ts1, ts2;
+    __shared__ unsigned long long s_gp, s_gi;
+    __shared__ uint32_t s_nlong, s_cnt;
+    const unsigned short EMPTY = 0xFFFFu;
+    const uint64_t gmask = a.gb ? ((1ull << a.gb) - 1ull) : 0ull;
+
+    unsigned long long st_heads = 0, st_single = 0, st_w = 0, st_dups = 0;
+
+    for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
+        const uint32_t bb = a.base[b];
+        const uint32_t m = a.base[b + 1] - bb;
+        if (m == 0) continue;      // uniform per CTA: no barrier is skipped by only part of the block
+        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) { E[i] = a.ent[(uint64_t)bb + i]; nxt[i] = EMPTY; }
+        for (uint32_t i = threadIdx.x; i < BK_HS / 2; i += BK_THREADS) ((uint32_t*)H)[i] = 0xFFFFFFFFu;
+        if (threadIdx.x == 0) s_nlong = 0;
+        __syncthreads();
+
+        // ---- insert: the slot of a key holds the most recent entry of its chain -------------------
+        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
+            const uint64_t key = E[i] >> a.gb;
+            uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (BK_HS - 1);
+            for (;;) {
+                unsigned short cur = *((volatile unsigned short*)&H[slot]);
+                if (cur == EMPTY) {
+                    const unsigned short old = atomicCAS(&H[slot], EMPTY, (unsigned short)i);
+                    if (old == EMPTY) break;
+                    cur = old;
+                }
+                if ((E[cur] >> a.gb) == key) {
+                    const unsigned short old = atomicCAS(&H[slot], cur, (unsigned short)i);
+                    if (old == cur) { nxt[i] = cur; break; }
+                    continue;    // the chain head moved: retry this slot
+                }
+                slot = (slot + 1) & (BK_HS - 1);
+            }
+        }
+        __syncthreads();
+
+        // ---- pass A: group sizes -> where this CTA's output goes -----------------------------------
+        uint32_t p_t = 0, i_t = 0;
+        for (uint32_t s = threadIdx.x; s < BK_HS; s += BK_THREADS) {
+            const unsigned short head = H[s];
+            if (head == EMPTY) continue;
+            uint32_t L = 0;
+            for (unsigned short j = head; j != EMPTY; j = nxt[j]) L++;
+            st_heads++;
+            if (L == 1) { st_single++; continue; }
+            st_w += (unsigned long long)L * L;
+            if (L > BK_KMAX) {
+                const uint32_t q = atomicAdd(&s_nlong, 1u);
+                longq[q] = head;      // at most BK_CAP / (BK_KMAX + 1) < BK_LONGQ such groups exist
+                continue;
+            }
+            p_t += L;
+            i_t += L - 1;
+        }
+        uint32_t offp, offi, totp, toti;
+        Scan(ts1).ExclusiveSum(p_t, offp, totp);
+        Scan(ts2).ExclusiveSum(i_t, offi, toti);
+        if (threadIdx.x == 0) {
+            s_gp = totp ? atomicAdd(&a.scal[SCM_PCUR], (unsigned long long)totp) : 0ull;
+            s_gi = toti ? atomicAdd(&a.scal[SCM_ICUR], (unsigned long long)toti) : 0ull;
+        }
+        __syncthreads();
+
+        // ---- pass B: order each small group by genome id, write postings + records ------------------
+        {
+            uint64_t pp = s_gp + offp, qq = s_gi + offi;
+            for (uint32_t s = threadIdx.x; s < BK_HS; s += BK_THREADS) {
+                const unsigned short head = H[s];
+                if (head == EMPTY) continue;
+                uint32_t g[BK_KMAX];
+                uint32_t L = 0;
+                for (unsigned short j = head; j != EMPTY; j = nxt[j]) {
+                    if (L < BK_KMAX) g[L] = (uint32_t)(E[j] & gmask);
+                    L++;
+                }
+                if (L < 2 || L > BK_KMAX) continue;
+                for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
+                    const uint32_t v = g[x];
+                    uint32_t y = x;
+                    while (y > 0 && g[y - 1] > v) { g[y] = g[y - 1]; y--; }
+                    g[y] = v;
+                }
+                for (uint32_t x = 0; x < L; x++) {
+                    a.post[pp + x] = g[x];
+                    if (x + 1 < L) {
+                        if (g[x] == g[x + 1]) st_dups++;
+                        emit_member(a, g[x], pp + x + 1, L - x - 1, qq++);
+                    }
+                }
+                pp += L;
+            }
+        }
+        __syncthreads();
+
+        // ---- large groups: the whole CTA gathers, bitonic-sorts and writes one group at a time -------
+        const uint32_t nlong = s_nlong;
+        for (uint32_t lg = 0; lg < nlong; lg++) {
+            const uint64_t key = E[longq[lg]] >> a.gb;
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();                                  // also: every thread has read H before it becomes scratch
+            for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS)
+                if ((E[i] >> a.gb) == key) scratch[atomicAdd(&s_cnt, 1u)] = (uint32_t)(E[i] & gmask);
+            __syncthreads();
+            const uint32_t L = s_cnt;
+            uint32_t n2 = 1;
+            while (n2 < L) n2 <<= 1;
+            for (uint32_t i = L + threadIdx.x; i < n2; i += BK_THREADS) scratch[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            for (uint32_t k = 2; k <= n2; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = threadIdx.x; i < n2; i += BK_THREADS) {
+                        const uint32_t ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint32_t x = scratch[i], y = scratch[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((x > y) == up) { scratch[i] = y; scratch[ixj] = x; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            if (threadIdx.x == 0) {
+                s_gp = atomicAdd(&a.scal[SCM_PCUR], (unsigned long long)L);
+                s_gi = atomicAdd(&a.scal[SCM_ICUR], (unsigned long long)(L - 1));
+            }
+            __syncthreads();
+            const uint64_t pp = s_gp, qq = s_gi;
+            for (uint32_t x = threadIdx.x; x < L; x += BK_THREADS) {
+                const uint32_t gx = scratch[x];
+                a.post[pp + x] = gx;
+                if (x + 1 < L) {
+                    if (gx == scratch[x + 1]) st_dups++;
+                    emit_member(a, gx, pp + x + 1, L - x - 1, qq + x);
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    st_heads = block_sum<BK_THREADS>(st_heads);
+    st_single = block_sum<BK_THREADS>(st_single);
+    st_w = block_sum<BK_THREADS>(st_w);
+    st_dups = block_sum<BK_THREADS>(st_dups);
+    if (threadIdx.x == 0) {
+        if (st_heads) atomicAdd(&a.scal[SC_HEADS], st_heads);
+        if (st_single) atomicAdd(&a.scal[SC_SINGLE], st_single);
+        if (st_w) atomicAdd(&a.scal[SC_W], st_w);
+        if (st_dups) atomicAdd(&a.scal[SC_DUPS], st_dups);
+    }
+}
+
+__global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict__ rec_gid, const uint64_t* __restrict__ rec_item,
+                                                       uint64_t I, const uint64_t* __restrict__ row_ptr,
+                                                       unsigned long long* __restrict__ row_fill, uint64_t* __restrict__ row_items) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < I; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = rec_gid[k];
+        const unsigned long long slot = atomicAdd(&row_fill[g], 1ull);
+        row_items[row_ptr[g] + slot] = rec_item[k];
+    }
+}
+
+int bitlen(uint64_t v) {
+    int b = 0;
+    while (b < 64 && (v >> b) != 0) b++;
+    return b;
+}
+
+}  // namespace
+
+int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
+    *used = 0;
+    const uint64_t T = ctx->T;
+    const uint32_t n = ctx->n;
+    if (T < 2 || n < 2) return 0;
+    cudaStream_t st = ctx->stream;
+
+    // ---- plan -----------------------------------------------------------------------------------
+    uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        ctx->tm.n_library_launches += 2;
+    }
+    uint64_t maxkey = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    MsdPlan p{};
+    p.T = T;
+    p.hb = std::max(1, bitlen(maxkey));
+    p.gb = bitlen((uint64_t)n - 1);
+    auto used_buckets = [&](int D) -> uint64_t { return D == 0 ? 1ull : (maxkey >> (p.hb - D)) + 1ull; };
+    int D = 0;
+    while (D < p.hb && D < 22 && T / used_buckets(D) > A_TARGET) D++;
+    int d1 = D <= 8 ? D : (D + 1) / 2;
+    const int need = p.hb + p.gb - 64;           // packing: hb - d1 + gb <= 64
+    if (need > d1) d1 = need;
+    if (d1 > 11 || d1 > p.hb) return 0;          // does not pack: general path
+    int d2 = D - d1;
+    if (d2 < 0) d2 = 0;
+    if (d2 > 11) return 0;
+    p.d1 = d1; p.d2 = d2; p.kb1 = p.hb - d1;
+    p.nb1 = d1 ? (uint32_t)(maxkey >> (p.hb - d1)) + 1 : 1u;
+    if (p.nb1 > NB_MAX) return 0;
+    p.nfb = p.nb1 << d2;
+
+    // ---- buffers ----------------------------------------------------------------------------------
+    YG_CHECK(dev_alloc(ctx, &ctx->d_ent1, T));
+    if (d2) YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T));
+    const uint64_t aux_words = 3ull * (NB_MAX + 2) + 3ull * ((uint64_t)p.nfb + 2);
+    YG_CHECK(dev_alloc(ctx, &ctx->d_msd_aux, aux_words));
+    uint32_t* hist1 = ctx->d_msd_aux;
+    uint32_t* base1 = hist1 + (NB_MAX + 2);
+    uint32_t* tile_start = base1 + (NB_MAX + 2);
+    uint32_t* hist2 = tile_start + (NB_MAX + 2);
+    uint32_t* base2 = hist2 + ((uint64_t)p.nfb + 2);
+    uint32_t* cursor = base2 + ((uint64_t)p.nfb + 2);      // level-1 cursors first, then reused for level 2
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
+    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_PCUR], 0, 4 * sizeof(unsigned long long), st));
+
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    // ---- level 1 ----------------------------------------------------------------------------------
+    k2_hist1<<<ctx->num_sms * 8, 256, p.nb1 * sizeof(uint32_t), st>>>(ctx->d_hashes, p, hist1);
+    YG_CUDA(ctx, cudaGetLastError());
+    k2_prep1<<<1, 1024, 0, st>>>(hist1, p.nb1, base1, tile_start, cursor, ctx->d_scalars);
+    YG_CUDA(ctx, cudaGetLastError());
+    ScatterArgs a{};
+    a.hashes = ctx->d_hashes; a.gid = ctx->d_gid; a.out_ent = ctx->d_ent1; a.cursor = cursor;
+    a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2;
+    const uint32_t units1 = (uint32_t)((T + SC_TILE - 1) / SC_TILE);
+    {
+        const size_t smem = (size_t)SC_TILE * 8 + (size_t)p.nb1 * 12 + (size_t)SC_TILE * 2;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1>, SC_THREADS, smem));
+        const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
+        k2_scatter<1><<<grid, SC_THREADS, smem, st>>>(a, p, units1);
+        YG_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->tm.n_kernel_launches += 3;
+    const uint64_t* final_ent = ctx->d_ent1;
+    const uint32_t* final_base = base1;
+    // ---- level 2 ----------------------------------------------------------------------------------
+    if (d2) {
+        a.in_ent = ctx->d_ent1; a.out_ent = ctx->d_ent2;
+        const int grid_h = ctx->num_sms * 8;
+        k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p);
+        YG_CUDA(ctx, cudaGetLastError());
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist2, base2, (int64_t)p.nfb + 1, st));
+        size_t tb2 = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb2, hist2, (uint32_t*)&ctx->d_scalars[SCM_MAXB + 1], (int64_t)p.nfb, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, std::max(tb, tb2)));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, hist2, base2, (int64_t)p.nfb + 1, st));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, hist2, (uint32_t*)&ctx->d_scalars[SCM_MAXB + 1], (int64_t)p.nfb, st));
+        ctx->tm.n_library_launches += 4;
+        YG_CUDA(ctx, cudaMemcpyAsync(cursor, base2, ((uint64_t)p.nfb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        a.cursor = cursor;
+        const size_t smem = (size_t)SC_TILE * 8 + (size_t)(1u << d2) * 12 + (size_t)SC_TILE * 2;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2>, SC_THREADS, smem));
+        const int grid = ctx->num_sms * std::max(occ, 1);
+        k2_scatter<2><<<grid, SC_THREADS, smem, st>>>(a, p, 0);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 2;
+        final_ent = ctx->d_ent2;
+        final_base = base2;
+    }
+    // largest final bucket decides whether the shared-memory grouping applies
+    unsigned long long maxb[2] = {0, 0};
+    YG_CUDA(ctx, cudaMemcpyAsync(maxb, &ctx->d_scalars[SCM_MAXB], sizeof maxb, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];
+    if (largest > BK_CAP) {
+        ctx->msd_fallbacks++;
+        return 0;                                   // skewed: the general (sort) path handles it
+    }
+
+    // ---- buckets -> postings + records ---------------------------------------------------------------
+    YG_CHECK(dev_alloc(ctx, &ctx->d_post, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_rec_gid, T));
+    uint64_t* rec_item = nullptr;
+    if (d2) rec_item = ctx->d_ent1;                 // level-1 words are dead once level 2 has run
+    else { YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T)); rec_item = ctx->d_ent2; }
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    BucketArgs b{};
+    b.ent = final_ent; b.base = final_base; b.nb = d2 ? p.nfb : p.nb1; b.gb = p.gb;
+    b.post = ctx->d_post; b.rec_gid = ctx->d_rec_gid; b.rec_item = rec_item;
+    b.row_cnt = ctx->d_row_cnt; b.row_work = (unsigned long long*)ctx->d_row_work; b.scal = ctx->d_scalars;
+    {
+        const size_t smem = (size_t)BK_CAP * 8 + (size_t)BK_HS * 2 + (size_t)BK_CAP * 2 + (size_t)BK_LONGQ * 2;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_bucket, BK_THREADS, smem));
+        const int grid = (int)std::min<uint64_t>(b.nb, (uint64_t)ctx->num_sms * std::max(occ, 1));
+        k2_bucket<<<grid, BK_THREADS, smem, st>>>(b);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+    }
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
+        ctx->tm.n_library_launches += 2;
+    }
+    unsigned long long sc[16];
+    YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
+    ctx->P = P;
+    ctx->n_items = I;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, I));
+    if (I) {
+        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+        k2_rec_scatter<<<grid_for(ctx, I, 256), 256, 0, st>>>(ctx->d_rec_gid, rec_item, I, ctx->d_row_ptr, ctx->d_row_cnt,
+                                                            ctx->d_row_items);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_sort += elapsed(ctx, 0, 1);
+    ctx->tm.ms_index += elapsed(ctx, 1, 2);
+
+    S->n_distinct = sc[SC_HEADS];
+    S->n_singleton = sc[SC_SINGLE];
+    S->n_index = S->n_distinct - S->n_singleton;
+    S->n_postings = P;
+    S->n_increments = sc[SC_W];
+    S->n_row_items = I;
+    S->has_duplicates = sc[SC_DUPS] ? 1u : 0u;
+    *used = 1;
+    return 0;
+}

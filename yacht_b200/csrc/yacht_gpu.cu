@@ -116,6 +116,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
+    dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_rec_gid); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
 }
@@ -383,6 +384,29 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
         return 0;
     }
 
+    // ---- preferred: MSD partition + shared-memory grouping (index_msd.cu) -----------------------------
+    if (ctx->index_path != 0) {
+        int used = 0;
+        YG_CHECK(ygpu_build_index_msd(ctx, &S, &used));
+        if (used) {
+            std::vector<uint32_t> sz(n);
+            YG_CUDA(ctx, cudaMemcpy(sz.data(), ctx->d_sizes, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            uint32_t mx = 0;
+            for (uint32_t v : sz) mx = std::max(mx, v);
+            S.max_sketch = mx;
+            S.index_path = 1;
+            ctx->stats = S;
+            ctx->indexed = true;
+            ctx->last_index_path = 1;
+            if (stats) *stats = S;
+            return 0;
+        }
+        // not applicable (or skewed): the scalars the general path accumulates into start from zero again
+        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
+        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_work, 0, std::max<uint64_t>(n, 1) * sizeof(uint64_t), st));
+    }
+    ctx->last_index_path = 0;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     // ---- K2a: stable radix sort of (hash, genome id)
     YG_CHECK(ygpu_sort_sketches(ctx));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -793,6 +817,7 @@ extern "C" int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms
 extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return YGPU_ERR_ARG;
     if (!strcmp(name, "force_tile_w")) { ctx->force_tile_w = (uint32_t)value; return 0; }
+    if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

@@ -35,14 +35,14 @@ struct ygpu_ctx {
     uint32_t* d_post = nullptr;     // [P]   compacted posting array (genome ids), runs contiguous
     uint32_t* d_rem = nullptr;      // [P]   postings that follow slot c inside its run
     uint64_t n_items = 0;
-    uint64_t* d_row_ptr = nullptr;  // [n+1] CSR over row_items
+    uint64_t* d_row_ptr = nullptr;  // [n+1] CSR over row_items (general path)
+    const uint64_t* d_row_begin = nullptr;  // [n] start of row g's work list in d_row_items (d_row_ptr or d_offsets)
     uint64_t* d_row_items = nullptr;// [n_items] (first posting slot << 32) | count  -- per query genome
     uint64_t* d_row_work = nullptr; // [n]   increments row i performs (sum of counts)
     unsigned long long* d_row_cnt = nullptr;  // [n+1] build scratch
     // MSD-partition build (index_msd.cu)
     uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets
     uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
-    uint32_t* d_rec_gid = nullptr;  // [I] work records before they are grouped by genome
     uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
     int msd_fallbacks = 0;

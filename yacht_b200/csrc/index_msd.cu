@@ -29,16 +29,16 @@
 
 namespace {
 
-constexpr int SC_TILE = 4096;       // elements per scatter tile (256 threads x 16)
-constexpr int SC_THREADS = 256;
+constexpr int SC_TILE = 4096;       // elements per scatter tile (512 threads x 8)
+constexpr int SC_THREADS = 512;
 constexpr int SC_ITEMS = SC_TILE / SC_THREADS;
 constexpr int NB_MAX = 2048;        // digits per partition level
-constexpr int BK_CAP = 3840;        // max elements of a final bucket (shared-memory resident)
-constexpr int BK_HS = 8192;         // hash-table slots per bucket (> BK_CAP: never full)
+constexpr int BK_CAP = 3072;        // max elements of a final bucket (shared-memory resident)
+constexpr int BK_HS = 4096;         // hash-table slots per bucket (> BK_CAP: never full)
 constexpr int BK_THREADS = 256;
 constexpr int BK_KMAX = 12;         // groups up to this size are ordered by one thread in registers
-constexpr int BK_LONGQ = 304;       // > BK_CAP / (BK_KMAX + 1) = 295: queue of larger groups
-constexpr uint32_t A_TARGET = 1536; // average elements per used final bucket
+constexpr int BK_LONGQ = 240;       // > BK_CAP / (BK_KMAX + 1) = 236: queue of larger groups
+constexpr uint32_t A_TARGET = 1200; // average elements per used final bucket
 
 enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10 };   // extra slots of ctx->d_scalars
 
@@ -242,122 +242,115 @@ struct BucketArgs {
     const uint32_t* base;        // [nb + 1]
     uint32_t nb;
     int gb;
-    uint32_t* post;              // compact postings (genome ids), groups contiguous, ascending inside a group
-    uint32_t* rec_gid;           // work records: the query genome ...
-    uint64_t* rec_item;          // ... and (first following posting << 32) | how many follow
-    unsigned long long* row_cnt;
-    unsigned long long* row_work;
+    uint32_t* post;              // [T] postings (genome ids): a bucket writes its groups at the start of its own slice
+    const uint64_t* row_off;     // [n] sketch offsets: row g's work list lives at row_items[row_off[g] ..]
+    uint64_t* row_items;         // [T] (first following posting << 32) | how many follow, per query genome
+    unsigned long long* row_cnt; // [n] items written per row
+    unsigned long long* row_work;// [n] increments per row
     unsigned long long* scal;
 };
 
-__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem, uint64_t q) {
-    a.rec_gid[q] = g;
-    a.rec_item[q] = (next_pos << 32) | (uint64_t)rem;
-    atomicAdd(&a.row_cnt[g], 1ull);
+// one work item for query genome g: "the `rem` postings starting at `next_pos` share a hash with you".
+// A row can receive at most one item per hash it holds, so its slice of row_items never overflows.
+__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem) {
+    const unsigned long long k = atomicAdd(&a.row_cnt[g], 1ull);
+    a.row_items[a.row_off[g] + k] = (next_pos << 32) | (uint64_t)rem;
     atomicAdd(&a.row_work[g], (unsigned long long)rem);
 }
 
 __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* E = (uint64_t*)smem_raw;                               // [BK_CAP]
-    unsigned short* H = (unsigned short*)(E + BK_CAP);               // [BK_HS] head entry of each key's chain
-    unsigned short* nxt = H + BK_HS;                                 // [BK_CAP]
-    unsigned short* longq = nxt + BK_CAP;                            // [BK_LONGQ] head entries of large groups
-    uint32_t* scratch = (uint32_t*)H;                                // [BK_CAP] reused once the chains of large groups are queued
-    typedef cub::BlockScan<uint32_t, BK_THREADS> Scan;
-    __shared__ typename Scan::TempStorage ts1, ts2;
-    __shared__ unsigned long long s_gp, s_gi;
-    __shared__ uint32_t s_nlong, s_cnt;
-    const unsigned short EMPTY = 0xFFFFu;
+    uint64_t* E = (uint64_t*)smem_raw;                               // [BK_CAP] the bucket's packed words
+    uint32_t* H = (uint32_t*)(E + BK_CAP);                           // [BK_HS]  slot -> most recent entry of that key's chain
+    unsigned short* nxt = (unsigned short*)(H + BK_HS);              // [BK_CAP] chain links (towards older entries)
+    unsigned short* slot_of = nxt + BK_CAP;                          // [BK_CAP] slot each entry landed in
+    unsigned short* queue = slot_of + BK_CAP;                        // [BK_CAP / 2] chain heads of groups with >= 2 members
+    unsigned short* longq = queue + BK_CAP / 2;                      // [BK_LONGQ] heads of groups larger than BK_KMAX
+    uint32_t* scratch = H;                                           // [BK_CAP] reused by the large-group path
+    __shared__ uint32_t s_nq, s_nlong, s_cnt, s_pcur;
+    const unsigned short NONE = 0xFFFFu;
+    const uint32_t EMPTY = 0xFFFFFFFFu;
     const uint64_t gmask = a.gb ? ((1ull << a.gb) - 1ull) : 0ull;
 
-    unsigned long long st_heads = 0, st_single = 0, st_w = 0, st_dups = 0;
+    unsigned long long st_heads = 0, st_single = 0, st_w = 0, st_dups = 0, st_p = 0, st_i = 0;
 
     for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
         const uint32_t bb = a.base[b];
         const uint32_t m = a.base[b + 1] - bb;
-        if (m == 0) continue;      // uniform per CTA: no barrier is skipped by only part of the block
-        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) { E[i] = a.ent[(uint64_t)bb + i]; nxt[i] = EMPTY; }
-        for (uint32_t i = threadIdx.x; i < BK_HS / 2; i += BK_THREADS) ((uint32_t*)H)[i] = 0xFFFFFFFFu;
-        if (threadIdx.x == 0) s_nlong = 0;
+        if (m == 0) continue;      // uniform per CTA
+        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) { E[i] = a.ent[(uint64_t)bb + i]; nxt[i] = NONE; }
+        for (uint32_t i = threadIdx.x; i < BK_HS; i += BK_THREADS) H[i] = EMPTY;
+        if (threadIdx.x == 0) { s_nq = 0; s_nlong = 0; s_pcur = 0; }
         __syncthreads();
 
-        // ---- insert: the slot of a key holds the most recent entry of its chain -------------------
+        // ---- insert: one CAS for a new key, one more to push onto an existing key's chain ------------
         for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
             const uint64_t key = E[i] >> a.gb;
             uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (BK_HS - 1);
             for (;;) {
-                unsigned short cur = *((volatile unsigned short*)&H[slot]);
+                uint32_t cur = *((volatile uint32_t*)&H[slot]);
                 if (cur == EMPTY) {
-                    const unsigned short old = atomicCAS(&H[slot], EMPTY, (unsigned short)i);
+                    const uint32_t old = atomicCAS(&H[slot], EMPTY, i);
                     if (old == EMPTY) break;
                     cur = old;
                 }
                 if ((E[cur] >> a.gb) == key) {
-                    const unsigned short old = atomicCAS(&H[slot], cur, (unsigned short)i);
-                    if (old == cur) { nxt[i] = cur; break; }
+                    const uint32_t old = atomicCAS(&H[slot], cur, i);
+                    if (old == cur) { nxt[i] = (unsigned short)cur; break; }
                     continue;    // the chain head moved: retry this slot
                 }
                 slot = (slot + 1) & (BK_HS - 1);
             }
+            slot_of[i] = (unsigned short)slot;
         }
         __syncthreads();
 
-        // ---- pass A: group sizes -> where this CTA's output goes -----------------------------------
-        uint32_t p_t = 0, i_t = 0;
-        for (uint32_t s = threadIdx.x; s < BK_HS; s += BK_THREADS) {
-            const unsigned short head = H[s];
-            if (head == EMPTY) continue;
-            uint32_t L = 0;
-            for (unsigned short j = head; j != EMPTY; j = nxt[j]) L++;
+        // ---- heads: count distinct hashes / singletons, queue the groups that have >= 2 members -------
+        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
+            if (H[slot_of[i]] != i) continue;          // not the head of its chain
             st_heads++;
-            if (L == 1) { st_single++; continue; }
-            st_w += (unsigned long long)L * L;
-            if (L > BK_KMAX) {
-                const uint32_t q = atomicAdd(&s_nlong, 1u);
-                longq[q] = head;      // at most BK_CAP / (BK_KMAX + 1) < BK_LONGQ such groups exist
-                continue;
-            }
-            p_t += L;
-            i_t += L - 1;
-        }
-        uint32_t offp, offi, totp, toti;
-        Scan(ts1).ExclusiveSum(p_t, offp, totp);
-        Scan(ts2).ExclusiveSum(i_t, offi, toti);
-        if (threadIdx.x == 0) {
-            s_gp = totp ? atomicAdd(&a.scal[SCM_PCUR], (unsigned long long)totp) : 0ull;
-            s_gi = toti ? atomicAdd(&a.scal[SCM_ICUR], (unsigned long long)toti) : 0ull;
+            if (nxt[i] == NONE) { st_single++; continue; }
+            queue[atomicAdd(&s_nq, 1u)] = (unsigned short)i;
         }
         __syncthreads();
 
-        // ---- pass B: order each small group by genome id, write postings + records ------------------
-        {
-            uint64_t pp = s_gp + offp, qq = s_gi + offi;
-            for (uint32_t s = threadIdx.x; s < BK_HS; s += BK_THREADS) {
-                const unsigned short head = H[s];
-                if (head == EMPTY) continue;
-                uint32_t g[BK_KMAX];
-                uint32_t L = 0;
-                for (unsigned short j = head; j != EMPTY; j = nxt[j]) {
-                    if (L < BK_KMAX) g[L] = (uint32_t)(E[j] & gmask);
-                    L++;
-                }
-                if (L < 2 || L > BK_KMAX) continue;
-                for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
-                    const uint32_t v = g[x];
-                    uint32_t y = x;
-                    while (y > 0 && g[y - 1] > v) { g[y] = g[y - 1]; y--; }
-                    g[y] = v;
-                }
-                for (uint32_t x = 0; x < L; x++) {
+        // ---- dense pass over the queued groups: order by genome id, claim a slice of the bucket's
+        //      posting region (shared-memory cursor: no grid-wide reservation), write postings + items
+        const uint32_t nq = s_nq;
+        for (uint32_t t = threadIdx.x; t < nq; t += BK_THREADS) {
+            uint32_t g[BK_KMAX];
+            uint32_t L = 0;
+            const unsigned short head = queue[t];
+            for (unsigned short j = head; j != NONE; j = nxt[j]) {
+                if (L < BK_KMAX) g[L] = (uint32_t)(E[j] & gmask);
+                L++;
+            }
+            st_w += (unsigned long long)L * L;
+            if (L > BK_KMAX) { longq[atomicAdd(&s_nlong, 1u)] = head; continue; }
+            for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
+                const uint32_t v = g[x];
+                uint32_t y = x;
+                while (y > 0 && g[y - 1] > v) { g[y] = g[y - 1]; y--; }
+                g[y] = v;
+            }
+            const uint64_t pp = (uint64_t)bb + atomicAdd(&s_pcur, L);
+            st_p += L; st_i += L - 1;
+            // all returning atomics first (independent, so their latencies overlap), then the stores
+            uint32_t k[BK_KMAX];
+#pragma unroll
+            for (uint32_t x = 0; x < BK_KMAX - 1; x++)
+                if (x + 1 < L) k[x] = (uint32_t)atomicAdd(&a.row_cnt[g[x]], 1ull);
+#pragma unroll
+            for (uint32_t x = 0; x < BK_KMAX; x++)
+                if (x < L) {
                     a.post[pp + x] = g[x];
                     if (x + 1 < L) {
                         if (g[x] == g[x + 1]) st_dups++;
-                        emit_member(a, g[x], pp + x + 1, L - x - 1, qq++);
+                        const uint32_t rem = L - x - 1;
+                        a.row_items[a.row_off[g[x]] + k[x]] = ((pp + x + 1) << 32) | (uint64_t)rem;
+                        atomicAdd(&a.row_work[g[x]], (unsigned long long)rem);
                     }
                 }
-                pp += L;
-            }
         }
         __syncthreads();
 
@@ -366,7 +359,7 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
         for (uint32_t lg = 0; lg < nlong; lg++) {
             const uint64_t key = E[longq[lg]] >> a.gb;
             if (threadIdx.x == 0) s_cnt = 0;
-            __syncthreads();                                  // also: every thread has read H before it becomes scratch
+            __syncthreads();                                  // H is dead from here on: it becomes `scratch`
             for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS)
                 if ((E[i] >> a.gb) == key) scratch[atomicAdd(&s_cnt, 1u)] = (uint32_t)(E[i] & gmask);
             __syncthreads();
@@ -387,43 +380,33 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
                     }
                     __syncthreads();
                 }
-            if (threadIdx.x == 0) {
-                s_gp = atomicAdd(&a.scal[SCM_PCUR], (unsigned long long)L);
-                s_gi = atomicAdd(&a.scal[SCM_ICUR], (unsigned long long)(L - 1));
-            }
+            const uint64_t pp = (uint64_t)bb + s_pcur;
             __syncthreads();
-            const uint64_t pp = s_gp, qq = s_gi;
+            if (threadIdx.x == 0) { s_pcur += L; st_p += L; st_i += L - 1; }
             for (uint32_t x = threadIdx.x; x < L; x += BK_THREADS) {
                 const uint32_t gx = scratch[x];
                 a.post[pp + x] = gx;
                 if (x + 1 < L) {
                     if (gx == scratch[x + 1]) st_dups++;
-                    emit_member(a, gx, pp + x + 1, L - x - 1, qq + x);
+                    emit_member(a, gx, pp + x + 1, L - x - 1);
                 }
             }
             __syncthreads();
         }
-        __syncthreads();
     }
     st_heads = block_sum<BK_THREADS>(st_heads);
     st_single = block_sum<BK_THREADS>(st_single);
     st_w = block_sum<BK_THREADS>(st_w);
     st_dups = block_sum<BK_THREADS>(st_dups);
+    st_p = block_sum<BK_THREADS>(st_p);
+    st_i = block_sum<BK_THREADS>(st_i);
     if (threadIdx.x == 0) {
         if (st_heads) atomicAdd(&a.scal[SC_HEADS], st_heads);
         if (st_single) atomicAdd(&a.scal[SC_SINGLE], st_single);
         if (st_w) atomicAdd(&a.scal[SC_W], st_w);
         if (st_dups) atomicAdd(&a.scal[SC_DUPS], st_dups);
-    }
-}
-
-__global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict__ rec_gid, const uint64_t* __restrict__ rec_item,
-                                                       uint64_t I, const uint64_t* __restrict__ row_ptr,
-                                                       unsigned long long* __restrict__ row_fill, uint64_t* __restrict__ row_items) {
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < I; k += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t g = rec_gid[k];
-        const unsigned long long slot = atomicAdd(&row_fill[g], 1ull);
-        row_items[row_ptr[g] + slot] = rec_item[k];
+        if (st_p) atomicAdd(&a.scal[SCM_PCUR], st_p);
+        if (st_i) atomicAdd(&a.scal[SCM_ICUR], st_i);
     }
 }
 
@@ -550,20 +533,17 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
         return 0;                                   // skewed: the general (sort) path handles it
     }
 
-    // ---- buckets -> postings + records ---------------------------------------------------------------
+    // ---- buckets -> postings + per-genome work lists ------------------------------------------------
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, T));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_rec_gid, T));
-    uint64_t* rec_item = nullptr;
-    if (d2) rec_item = ctx->d_ent1;                 // level-1 words are dead once level 2 has run
-    else { YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T)); rec_item = ctx->d_ent2; }
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
     BucketArgs b{};
     b.ent = final_ent; b.base = final_base; b.nb = d2 ? p.nfb : p.nb1; b.gb = p.gb;
-    b.post = ctx->d_post; b.rec_gid = ctx->d_rec_gid; b.rec_item = rec_item;
+    b.post = ctx->d_post; b.row_off = ctx->d_offsets; b.row_items = ctx->d_row_items;
     b.row_cnt = ctx->d_row_cnt; b.row_work = (unsigned long long*)ctx->d_row_work; b.scal = ctx->d_scalars;
     {
-        const size_t smem = (size_t)BK_CAP * 8 + (size_t)BK_HS * 2 + (size_t)BK_CAP * 2 + (size_t)BK_LONGQ * 2;
+        const size_t smem = (size_t)BK_CAP * 8 + (size_t)BK_HS * 4 + (size_t)BK_CAP * 2 * 2 + (size_t)BK_CAP + (size_t)BK_LONGQ * 2;
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_bucket, BK_THREADS, smem));
@@ -572,30 +552,14 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
         YG_CUDA(ctx, cudaGetLastError());
         ctx->tm.n_kernel_launches++;
     }
-    {
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_row_cnt, (unsigned long long*)ctx->d_row_ptr, (int64_t)n + 1, st));
-        ctx->tm.n_library_launches += 2;
-    }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
     ctx->P = P;
     ctx->n_items = I;
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, I));
-    if (I) {
-        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-        k2_rec_scatter<<<grid_for(ctx, I, 256), 256, 0, st>>>(ctx->d_rec_gid, rec_item, I, ctx->d_row_ptr, ctx->d_row_cnt,
-                                                            ctx->d_row_items);
-        YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches++;
-    }
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
 

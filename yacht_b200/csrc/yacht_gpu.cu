@@ -116,7 +116,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
-    dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_rec_gid); dev_free(ctx, &ctx->d_msd_aux);
+    dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
 }
@@ -468,6 +468,7 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
     }
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d_row_begin = ctx->d_row_ptr;   // d_row_cnt (the scatter's fill cursors) now holds each row's item count
     ctx->tm.n_kernel_launches += 1;  // k_flag_runs
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
 
@@ -504,7 +505,8 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
 #define K3_LONG_LEN 64
 
 struct K3Params {
-    const uint64_t* row_ptr;
+    const uint64_t* list_begin;         // [n] start of each row's work list
+    const unsigned long long* row_n;    // [n] its length
     const uint64_t* row_items;
     const uint32_t* post;
     const uint32_t* sizes;
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
         const uint32_t tile = (uint32_t)(unit % p.n_tiles);
         const uint32_t c0 = tile * p.tile_w;
         const uint32_t c1 = min(p.n, c0 + p.tile_w);
-        const uint64_t ib = p.row_ptr[row], ie = p.row_ptr[row + 1];
+        const uint64_t ib = p.list_begin[row], ie = ib + p.row_n[row];
         // upper triangle: only columns > row matter
         if (c1 > row + 1 && ie > ib) {
             // ---- accumulate -----------------------------------------------------------------
@@ -713,7 +715,7 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
         for (int attempt = 0; attempt < 2; attempt++) {
             YG_CHECK(ensure_out(ctx, cap));
             K3Params p;
-            p.row_ptr = ctx->d_row_ptr; p.row_items = ctx->d_row_items; p.post = ctx->d_post; p.sizes = ctx->d_sizes;
+            p.list_begin = ctx->d_row_begin; p.row_n = ctx->d_row_cnt; p.row_items = ctx->d_row_items; p.post = ctx->d_post; p.sizes = ctx->d_sizes;
             p.n = n; p.row_begin = row_begin; p.row_end = row_end; p.tile_w = tile_w; p.n_tiles = n_tiles;
             p.thr = threshold; p.out_key = ctx->d_out_key; p.out_cnt = ctx->d_out_cnt; p.out_cap = ctx->out_cap;
             p.scal = ctx->d_scalars;

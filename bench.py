@@ -266,8 +266,10 @@ def run_b200_arm(args):
         torch.cuda.synchronize()   # the NCCL gather runs on torch's stream: finish it inside the timed step
         return sum(sizes)
 
+    index_stats = {}
+
     def step_resident():
-        ctx.build_index()
+        index_stats.update(ctx.build_index())
         b = ctx.row_partition(world)
         n_r = ctx.pairwise_flag_device(THR, int(b[rank]), int(b[rank + 1]))
         return gather_pairs(n_r, False)
@@ -318,16 +320,36 @@ def run_b200_arm(args):
         pairs_total = n * (n - 1)
         F = int(len(pairs_host))
         peak, peak_src = load_peaks()
-        # ---- roofline of the pairwise-count kernel (K3+K4): SURVEY.md 8(d) algorithmic bytes -----------
+        # ---- rooflines (HBM): algorithmic bytes per launch / CUDA-event duration of that phase -----------
         launches = max(tm_res["n_count_launches"], 1)
-        k3_ms = tm_res["ms_count"] / launches
-        share = 1.0 / world   # rows are split by work; rank 0 sees ~1/world of T and W
-        B_train = (8 * counts["T"] + 4 * counts["W"]) * share + 12 * F * share
-        ach = B_train / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
         steps = args.steps
-        idx_ms = (tm_res["ms_sort"] + tm_res["ms_index"]) / steps
-        B_index = 12 * counts["T"] * 2 * 7 + 4 * counts["P"] + 8 * counts["U2"]
-        ach_idx = B_index / (idx_ms * 1e-3) / 1e9 if idx_ms > 0 else 0.0
+        share = 1.0 / world   # rows are split by work; a rank sees ~1/world of T and W in the count kernel
+        st = index_stats
+        k3_ms = tm_res["ms_count"] / launches
+        part_ms = tm_res["ms_sort"] / steps
+        bucket_ms = tm_res["ms_index"] / steps
+        Tn, Wn, Pn, In = counts["T"], counts["W"], counts["P"], st["n_row_items"]
+        msd = st["index_path"] == 1
+
+        def rl(kernel, nbytes, ms, formula):
+            ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "algorithmic_bytes": nbytes, "formula": formula, "ms_per_launch": ms,
+                    "share_of_step": ms / ms_res if ms_res else None, "peak_source": peak_src}
+
+        rooflines = {
+            "pairwise_count": rl("k3_count_flag (K3+K4: pairwise shared-hash count + threshold/compaction)",
+                                 (8 * Tn + 4 * Wn + 12 * F) * share, k3_ms, "8*T + 4*W + 12*F (SURVEY.md 8d), x rank share"),
+            "index_partition": rl("k2_hist1 + k2_scatter<1> + k2_hist2 + k2_scatter<2> (K2: MSD radix partition)" if msd
+                                  else "CUB DeviceRadixSort of (hash, genome) pairs (general path)",
+                                  52 * Tn if msd else 12 * Tn * 2 * 7, part_ms,
+                                  "8T + (12T+8T) + 8T + (8T+8T) = 52*T" if msd else "12*T*2*7 (SURVEY.md 8d)"),
+            "index_grouping": rl("k2_bucket (K2: shared-memory hash grouping, postings + per-genome work lists)" if msd
+                                 else "k_flag_runs + scan + k_post_compact + k_items_scatter (general path)",
+                                 8 * Tn + 4 * Pn + 8 * In if msd else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
+                                 "8*T + 4*P + 8*I" if msd else "12*T + 4*P + 16*I"),
+        }
+        dominant = max(rooflines.values(), key=lambda r: r["ms_per_launch"])
         line = {
             "metric": "ref-pair containments/s (yacht train hot path)", "value": pairs_total / (ms_res * 1e-3), "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
@@ -339,14 +361,7 @@ def run_b200_arm(args):
             "gpu_launches": int(tm_res["n_kernel_launches"]),
             "library_launches": int(tm_res["n_library_launches"]),
             "clocks": clocks,
-            "roofline": {"kernel": "k3_count_flag (pairwise shared-hash count + threshold/compaction)", "bound": "hbm",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "algorithmic_bytes": B_train, "formula": "8*T + 4*W + 12*F (SURVEY.md 8d), x rank share",
-                         "ms_per_launch": k3_ms, "share_of_step": k3_ms / ms_res if ms_res else None, "peak_source": peak_src},
-            "roofline_index": {"kernel": "K2: radix sort of (hash, genome) [CUB] + run/posting/work-list kernels", "bound": "hbm",
-                               "achieved": ach_idx, "peak": peak, "unit": "GB/s", "frac": ach_idx / peak,
-                               "algorithmic_bytes": B_index, "formula": "12*T*2*7 + 4*P + 8*U2 (SURVEY.md 8d)",
-                               "ms_per_step": idx_ms, "share_of_step": idx_ms / ms_res if ms_res else None},
+            "roofline": dominant, "rooflines": rooflines, "index_path": "msd-partition" if msd else "general-sort",
             "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},
             "workload_counts": dict(counts, F=F, genomes=n), "wall_ms_per_step": wall_res * 1e3, "gen_seconds": gen_s,
         }

@@ -134,7 +134,8 @@ int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out);
 int ygpu_mark(ygpu_ctx* ctx, int slot);
 int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel;
- * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default).   */
+ * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default);
+ * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic).   */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

@@ -26,11 +26,14 @@ def _check(ctx, db, thr, expect_path=None):
         ctx.set_option("index_path", path)
         ctx.load_sketches(db.hashes, db.offsets)
         st = ctx.build_index()
-        got = ctx.pairwise_flag(thr)
         assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index), (path, st)
         assert st["n_postings"] == ref.n_postings, (path, st)
         assert st["n_increments"] == ref.n_increments, (path, st)
-        assert _pairs_tuple(got) == _pairs_tuple(ref.pairs), path
+        for count_kernel in (1, 2):          # dense row accumulator per CTA / one warp per row (hash table)
+            ctx.set_option("count_kernel", count_kernel)
+            got = ctx.pairwise_flag(thr)
+            assert _pairs_tuple(got) == _pairs_tuple(ref.pairs), (path, count_kernel)
+        ctx.set_option("count_kernel", 0)
         if path == 1:
             out = (st, got)
             if expect_path is not None:

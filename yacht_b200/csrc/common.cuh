@@ -47,6 +47,10 @@ struct ygpu_ctx {
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
     int msd_fallbacks = 0;
     int last_index_path = 0;        // which path built the current index
+    int count_kernel = 0;           // 0: automatic, 1: dense row accumulator per CTA, 2: one warp per row (hash table)
+    int last_count_kernel = 0;
+    unsigned long long last_count_overflow_rows = 0;
+    uint32_t* d_ovf_rows = nullptr; // rows the warp kernel deferred to the dense kernel
     ygpu_index_stats stats = {};
 
     // ---- scratch ------------------------------------------------------------------------------
@@ -120,8 +124,14 @@ static inline float elapsed(ygpu_ctx* ctx, int a, int b) {
     return ms;
 }
 
+// ---- work item format v2 (one 64-bit word per (query genome, shared hash)) ------------------------
+//   low 2 bits c = 0 : indirect -- the (item >> 2) & 0x3FFFFFFF postings starting at d_post[item >> 32] follow me
+//   low 2 bits c = 1..3 : inline -- the c genome ids that follow me are in bits [21:2], [41:22], [61:42]
+//                        (20 bits each: used only while genome ids fit 20 bits)
+#define YG_ITEM_INLINE_BITS 20
+
 // device scalar slots (ctx->d_scalars)
-enum { SC_HEADS = 0, SC_SINGLE = 1, SC_DUPS = 2, SC_W = 3, SC_OUT = 4, SC_UNIT = 5, SC_MAXKEY = 6 };
+enum { SC_HEADS = 0, SC_SINGLE = 1, SC_DUPS = 2, SC_W = 3, SC_OUT = 4, SC_UNIT = 5, SC_MAXKEY = 6, SC_OVF = 7 };
 
 template <int BS>
 __device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {

@@ -254,7 +254,7 @@ struct BucketArgs {
 // A row can receive at most one item per hash it holds, so its slice of row_items never overflows.
 __device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem) {
     const unsigned long long k = atomicAdd(&a.row_cnt[g], 1ull);
-    a.row_items[a.row_off[g] + k] = (next_pos << 32) | (uint64_t)rem;
+    a.row_items[a.row_off[g] + k] = (next_pos << 32) | ((uint64_t)rem << 2);      // item format v2, indirect
     atomicAdd(&a.row_work[g], (unsigned long long)rem);
 }
 
@@ -333,7 +333,12 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
                 while (y > 0 && g[y - 1] > v) { g[y] = g[y - 1]; y--; }
                 g[y] = v;
             }
-            const uint64_t pp = (uint64_t)bb + atomicAdd(&s_pcur, L);
+            // Items whose remaining list has <= 3 genomes carry those ids INLINE (item format v2, see
+            // common.cuh): the count kernel then never dereferences d_post for them -- that indirection
+            // was a 32-byte sector per 4-byte posting.  Groups of <= 4 members need no postings at all.
+            const bool can_inline = a.gb <= 20;
+            const bool need_post = !can_inline || L > 4;
+            const uint64_t pp = need_post ? (uint64_t)bb + atomicAdd(&s_pcur, L) : 0ull;
             st_p += L; st_i += L - 1;
             // all returning atomics first (independent, so their latencies overlap), then the stores
             uint32_t k[BK_KMAX];
@@ -343,11 +348,19 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
 #pragma unroll
             for (uint32_t x = 0; x < BK_KMAX; x++)
                 if (x < L) {
-                    a.post[pp + x] = g[x];
+                    if (need_post) a.post[pp + x] = g[x];
                     if (x + 1 < L) {
                         if (g[x] == g[x + 1]) st_dups++;
                         const uint32_t rem = L - x - 1;
-                        a.row_items[a.row_off[g[x]] + k[x]] = ((pp + x + 1) << 32) | (uint64_t)rem;
+                        uint64_t item;
+                        if (can_inline && rem <= 3) {
+                            item = (uint64_t)rem | ((uint64_t)g[x + 1] << 2);
+                            if (rem >= 2) item |= (uint64_t)g[(x + 2) < BK_KMAX ? (x + 2) : 0] << 22;
+                            if (rem >= 3) item |= (uint64_t)g[(x + 3) < BK_KMAX ? (x + 3) : 0] << 42;
+                        } else {
+                            item = ((pp + x + 1) << 32) | ((uint64_t)rem << 2);
+                        }
+                        a.row_items[a.row_off[g[x]] + k[x]] = item;
                         atomicAdd(&a.row_work[g[x]], (unsigned long long)rem);
                     }
                 }

@@ -116,6 +116,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
+    dev_free(ctx, &ctx->d_ovf_rows);
     dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) k_items_scatter(const uint32_t* __restric
         if (!r) continue;
         const uint32_t g = post[c];
         const unsigned long long k = atomicAdd(&row_fill[g], 1ull);
-        row_items[row_ptr[g] + k] = ((uint64_t)(c + 1) << 32) | (uint64_t)r;
+        row_items[row_ptr[g] + k] = ((uint64_t)(c + 1) << 32) | ((uint64_t)r << 2);   // item format v2, indirect
     }
 }
 
@@ -518,7 +519,10 @@ struct K3Params {
     uint64_t* out_key;     // (i << 32) | j
     uint32_t* out_cnt;
     uint64_t out_cap;
-    unsigned long long* scal;  // SC_OUT = pairs emitted, SC_UNIT = work-unit ticket
+    unsigned long long* scal;  // SC_OUT = pairs emitted, SC_UNIT = work-unit ticket, SC_OVF = rows deferred to the dense kernel
+    const uint32_t* row_list;  // dense kernel: explicit rows (the warp kernel's overflow list) instead of [row_begin, row_end)
+    uint32_t n_list;
+    uint32_t* ovf_rows;        // warp kernel: rows whose distinct columns overflow a warp's hash table
 };
 
 // warp-aggregated append: one atomic per warp-instruction instead of one per lane
@@ -574,7 +578,8 @@ __device__ __forceinline__ uint32_t acc_take(uint32_t* acc, uint32_t col) {
 }
 
 template <bool U16>
-__global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
+__global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
+    const uint32_t NT = blockDim.x;   // 256 when several accumulators share an SM, up to 1024 when one CTA owns it
     extern __shared__ uint32_t smem[];
     const uint32_t acc_words = U16 ? (p.tile_w + 1) / 2 : p.tile_w;
     uint32_t* acc = smem;                               // [acc_words] dense row accumulator
@@ -583,17 +588,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
     __shared__ uint32_t s_nt, s_nlong;
     __shared__ unsigned long long s_unit;
 
-    for (uint32_t c = threadIdx.x; c < acc_words; c += K3_THREADS) acc[c] = 0;
+    for (uint32_t c = threadIdx.x; c < acc_words; c += NT) acc[c] = 0;
     if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
     __syncthreads();
 
-    const unsigned long long n_units = (unsigned long long)(p.row_end - p.row_begin) * p.n_tiles;
+    const unsigned long long n_units = (unsigned long long)(p.row_list ? p.n_list : (p.row_end - p.row_begin)) * p.n_tiles;
     for (;;) {
         if (threadIdx.x == 0) s_unit = atomicAdd(&p.scal[SC_UNIT], 1ull);
         __syncthreads();
         const unsigned long long unit = s_unit;
         if (unit >= n_units) break;
-        const uint32_t row = p.row_begin + (uint32_t)(unit / p.n_tiles);
+        const uint32_t ridx = (uint32_t)(unit / p.n_tiles);
+        const uint32_t row = p.row_list ? p.row_list[ridx] : p.row_begin + ridx;
         const uint32_t tile = (uint32_t)(unit % p.n_tiles);
         const uint32_t c0 = tile * p.tile_w;
         const uint32_t c1 = min(p.n, c0 + p.tile_w);
@@ -601,9 +607,21 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
         // upper triangle: only columns > row matter
         if (c1 > row + 1 && ie > ib) {
             // ---- accumulate -----------------------------------------------------------------
-            for (uint64_t it = ib + threadIdx.x; it < ie; it += K3_THREADS) {
+            for (uint64_t it = ib + threadIdx.x; it < ie; it += NT) {
                 const uint64_t item = p.row_items[it];
-                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)item;
+                const uint32_t inl = (uint32_t)item & 3u;
+                if (inl) {                                         // the following genome ids are inside the item
+                    for (uint32_t e = 0; e < inl; e++) {
+                        const uint32_t g = (uint32_t)(item >> (2 + YG_ITEM_INLINE_BITS * e)) & ((1u << YG_ITEM_INLINE_BITS) - 1u);
+                        if (g <= row || g < c0 || g >= c1) continue;
+                        if (acc_add<U16>(acc, g - c0) == 0) {
+                            const uint32_t k = atomicAdd(&s_nt, 1u);
+                            if (k < K3_TOUCH_CAP) touched[k] = g;
+                        }
+                    }
+                    continue;
+                }
+                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
                 if (len > K3_LONG_LEN) {
                     const uint32_t q = atomicAdd(&s_nlong, 1u);
                     if (q < K3_LONG_CAP) { longq[q] = item; continue; }
@@ -621,8 +639,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
             const uint32_t nlong = min(s_nlong, (uint32_t)K3_LONG_CAP);
             for (uint32_t q = 0; q < nlong; q++) {
                 const uint64_t item = longq[q];
-                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)item;
-                for (uint32_t e = threadIdx.x; e < len; e += K3_THREADS) {
+                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
+                for (uint32_t e = threadIdx.x; e < len; e += NT) {
                     const uint32_t g = p.post[start + e];
                     if (g <= row || g < c0 || g >= c1) continue;
                     if (acc_add<U16>(acc, g - c0) == 0) {
@@ -635,14 +653,14 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
             // ---- threshold + compaction (K4), and reset of the accumulator ---------------------
             const uint32_t nt = s_nt;
             if (nt <= K3_TOUCH_CAP) {
-                for (uint32_t k = threadIdx.x; k < nt; k += K3_THREADS) {
+                for (uint32_t k = threadIdx.x; k < nt; k += NT) {
                     const uint32_t g = touched[k];
                     const uint32_t cnt = acc_take<U16>(acc, g - c0);
                     test_pair(p, row, g, cnt);
                 }
             } else {
                 const uint32_t w = c1 - c0;
-                for (uint32_t c = threadIdx.x; c < w; c += K3_THREADS) {
+                for (uint32_t c = threadIdx.x; c < w; c += NT) {
                     const uint32_t cnt = acc_take<U16>(acc, c);
                     if (cnt) test_pair(p, row, c0 + c, cnt);
                 }
@@ -651,6 +669,144 @@ __global__ void __launch_bounds__(K3_THREADS) k3_count_flag(const K3Params p) {
             if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
         }
         __syncthreads();
+    }
+}
+
+// ---- K3 for large N: one WARP per query row, counts in a small per-warp hash table ------------------
+// A dense row accumulator needs N counters (170 KB at 85k genomes => one row in flight per SM, latency
+// bound).  A row only ever touches the few genomes it shares hashes with, so each warp keeps
+// (column, count) pairs in a 512-slot open-addressing table in shared memory: 48 rows in flight per SM,
+// no block-level barrier anywhere.  Rows that touch more distinct columns than the table holds are
+// deferred to the dense kernel through an overflow list.
+#define K3W_THREADS 256
+#define K3W_SLOTS 512
+#define K3W_TOUCH 96
+#define K3W_LONG 64
+#define K3W_EMPTY 0xFFFFFFFFu
+#define K3W_ROWS 8           // rows per ticket (a warp's unit of dynamic scheduling)
+
+struct WarpTable {
+    uint32_t* keys;     // [K3W_SLOTS]
+    uint32_t* cnts;     // [K3W_SLOTS]
+    uint32_t* touched;  // [K3W_TOUCH] slots in first-touch order
+    uint32_t* ctl;      // [0] = distinct columns so far, [1] = overflow flag
+};
+
+__device__ __forceinline__ void wt_insert(const WarpTable& t, uint32_t g) {
+    uint32_t slot = (g * 2654435761u) >> 23;
+    for (int probe = 0; probe < K3W_SLOTS; probe++) {
+        const uint32_t k = *((volatile uint32_t*)&t.keys[slot]);
+        if (k == g) { atomicAdd(&t.cnts[slot], 1u); return; }
+        if (k == K3W_EMPTY) {
+            const uint32_t old = atomicCAS(&t.keys[slot], K3W_EMPTY, g);
+            if (old == K3W_EMPTY) {
+                const uint32_t idx = atomicAdd(&t.ctl[0], 1u);
+                if (idx < K3W_TOUCH) t.touched[idx] = slot;
+                if (idx >= (K3W_SLOTS * 3) / 4) t.ctl[1] = 1;
+                atomicAdd(&t.cnts[slot], 1u);
+                return;
+            }
+            if (old == g) { atomicAdd(&t.cnts[slot], 1u); return; }
+        }
+        slot = (slot + 1) & (K3W_SLOTS - 1);
+    }
+    t.ctl[1] = 1;   // table full
+}
+
+__global__ void __launch_bounds__(K3W_THREADS) k3w_count_flag(const K3Params p) {
+    extern __shared__ uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WORDS = 2 * K3W_SLOTS + K3W_TOUCH + 32;
+    WarpTable t;
+    t.keys = smem + warp * WORDS;
+    t.cnts = t.keys + K3W_SLOTS;
+    t.touched = t.cnts + K3W_SLOTS;
+    t.ctl = t.touched + K3W_TOUCH;
+    for (int i = lane; i < K3W_SLOTS; i += 32) { t.keys[i] = K3W_EMPTY; t.cnts[i] = 0; }
+    if (lane == 0) { t.ctl[0] = 0; t.ctl[1] = 0; }
+    __syncwarp();
+
+    const uint32_t n_rows = p.row_end - p.row_begin;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&p.scal[SC_UNIT], (unsigned long long)K3W_ROWS);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_rows) break;
+        const uint32_t my_idx = (uint32_t)base + lane;
+        const uint32_t my_n = (lane < K3W_ROWS && my_idx < n_rows) ? (uint32_t)p.row_n[p.row_begin + my_idx] : 0u;
+        const uint64_t my_ib = my_n ? p.list_begin[p.row_begin + my_idx] : 0ull;
+        unsigned todo = __ballot_sync(0xffffffffu, my_n > 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t row = p.row_begin + (uint32_t)base + src;
+            const uint32_t nit = __shfl_sync(0xffffffffu, my_n, src);
+            const uint64_t ib = __shfl_sync(0xffffffffu, my_ib, src);
+            // ---- accumulate --------------------------------------------------------------------------
+            for (uint32_t it0 = 0; it0 < nit; it0 += 32) {
+                const uint32_t it = it0 + lane;
+                uint32_t start = 0, len = 0;
+                if (it < nit) {
+                    const uint64_t item = p.row_items[ib + it];
+                    const uint32_t inl = (uint32_t)item & 3u;
+                    if (inl) {                                     // ids inline in the item: no posting read at all
+                        if (*((volatile uint32_t*)&t.ctl[1]) == 0)
+                            for (uint32_t e = 0; e < inl; e++) {
+                                const uint32_t g = (uint32_t)(item >> (2 + YG_ITEM_INLINE_BITS * e)) & ((1u << YG_ITEM_INLINE_BITS) - 1u);
+                                if (g > row) wt_insert(t, g);
+                            }
+                    } else {
+                        start = (uint32_t)(item >> 32);
+                        len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
+                    }
+                }
+                const bool is_long = len > K3W_LONG;
+                if (!is_long && *((volatile uint32_t*)&t.ctl[1]) == 0)
+                    for (uint32_t e = 0; e < len; e++) {
+                        const uint32_t g = p.post[start + e];
+                        if (g > row) wt_insert(t, g);      // g == row: the same hash twice inside the sketch
+                    }
+                unsigned lm = __ballot_sync(0xffffffffu, is_long);
+                while (lm) {
+                    const int s2 = __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    const uint32_t st2 = __shfl_sync(0xffffffffu, start, s2);
+                    const uint32_t ln2 = __shfl_sync(0xffffffffu, len, s2);
+                    if (*((volatile uint32_t*)&t.ctl[1]) == 0)
+                        for (uint32_t e = lane; e < ln2; e += 32) {
+                            const uint32_t g = p.post[st2 + e];
+                            if (g > row) wt_insert(t, g);
+                        }
+                }
+            }
+            __syncwarp();
+            // ---- threshold + compaction, table reset -------------------------------------------------------
+            const uint32_t nt = t.ctl[0];
+            const bool ovf = t.ctl[1] != 0;
+            __syncwarp();
+            if (ovf) {
+                if (lane == 0) p.ovf_rows[atomicAdd(&p.scal[SC_OVF], 1ull)] = row;
+                for (int i = lane; i < K3W_SLOTS; i += 32) { t.keys[i] = K3W_EMPTY; t.cnts[i] = 0; }
+            } else if (nt <= K3W_TOUCH) {
+                for (uint32_t k = lane; k < nt; k += 32) {
+                    const uint32_t slot = t.touched[k];
+                    const uint32_t g = t.keys[slot], c = t.cnts[slot];
+                    t.keys[slot] = K3W_EMPTY; t.cnts[slot] = 0;
+                    test_pair(p, row, g, c);
+                }
+            } else {
+                for (int slot = lane; slot < K3W_SLOTS; slot += 32) {
+                    const uint32_t g = t.keys[slot];
+                    if (g != K3W_EMPTY) {
+                        const uint32_t c = t.cnts[slot];
+                        t.keys[slot] = K3W_EMPTY; t.cnts[slot] = 0;
+                        test_pair(p, row, g, c);
+                    }
+                }
+            }
+            if (lane == 0) { t.ctl[0] = 0; t.ctl[1] = 0; }
+            __syncwarp();
+        }
     }
 }
 
@@ -688,7 +844,7 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
     uint64_t npairs = 0;
 
     if (ctx->n_items && row_end > row_begin) {
-        // ---- accumulator geometry -------------------------------------------------------------
+        // ---- dense accumulator geometry ---------------------------------------------------------
         const uint32_t fixed = K3_TOUCH_CAP * 4 + K3_LONG_CAP * 8 + 64;
         const uint32_t budget = (uint32_t)ctx->smem_optin - fixed - 1024;
         const bool u16_ok = !ctx->stats.has_duplicates && ctx->stats.max_sketch <= 65535u;
@@ -708,28 +864,66 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
         int occ = 0;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K3_THREADS, smem));
         if (occ < 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "k3_count_flag does not fit: smem %zu", smem);
-        const unsigned long long units = (unsigned long long)(row_end - row_begin) * n_tiles;
-        const int grid = (int)std::min<unsigned long long>((unsigned long long)ctx->num_sms * occ, units);
+        // threads per CTA: when shared memory allows only 1-2 row accumulators per SM, give each CTA more
+        // warps so a row's work list is walked with more loads in flight
+        const int k3_threads = occ >= 4 ? 256 : (occ >= 2 ? 512 : 1024);
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, k3_threads, smem));
+        if (occ < 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "k3_count_flag does not fit: smem %zu", smem);
+        // the warp-per-row kernel is selectable (option count_kernel = 2); measured slower than the dense
+        // kernel on cluster-shaped databases (rows carry ~700 work items: one warp walks them too slowly)
+        const bool use_warp = ctx->count_kernel == 2;
+        const size_t smem_w = (size_t)(K3W_THREADS / 32) * (2 * K3W_SLOTS + K3W_TOUCH + 32) * 4;
+        int occ_w = 0;
+        if (use_warp) {
+            YG_CUDA(ctx, cudaFuncSetAttribute(k3w_count_flag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3w_count_flag, K3W_THREADS, smem_w));
+            if (occ_w < 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "k3w_count_flag does not fit");
+            YG_CHECK(dev_alloc(ctx, &ctx->d_ovf_rows, (uint64_t)n + 1));
+        }
 
         uint64_t cap = std::max<uint64_t>(ctx->out_cap, std::max<uint64_t>(1u << 20, 8ull * n));
         for (int attempt = 0; attempt < 2; attempt++) {
             YG_CHECK(ensure_out(ctx, cap));
-            K3Params p;
+            K3Params p{};
             p.list_begin = ctx->d_row_begin; p.row_n = ctx->d_row_cnt; p.row_items = ctx->d_row_items; p.post = ctx->d_post; p.sizes = ctx->d_sizes;
             p.n = n; p.row_begin = row_begin; p.row_end = row_end; p.tile_w = tile_w; p.n_tiles = n_tiles;
             p.thr = threshold; p.out_key = ctx->d_out_key; p.out_cnt = ctx->d_out_cnt; p.out_cap = ctx->out_cap;
-            p.scal = ctx->d_scalars;
+            p.scal = ctx->d_scalars; p.row_list = nullptr; p.n_list = 0; p.ovf_rows = ctx->d_ovf_rows;
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_OUT], 0, 2 * sizeof(unsigned long long), st));
+            YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_OVF], 0, sizeof(unsigned long long), st));
             YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-            kern<<<grid, K3_THREADS, smem, st>>>(p);
-            YG_CUDA(ctx, cudaGetLastError());
+            unsigned long long cnt = 0, novf = 0;
+            if (use_warp) {
+                const unsigned long long chunks = ((unsigned long long)(row_end - row_begin) + K3W_ROWS - 1) / K3W_ROWS;
+                const int grid_w = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)ctx->num_sms * occ_w,
+                                                                                                     (chunks + 7) / 8));
+                k3w_count_flag<<<grid_w, K3W_THREADS, smem_w, st>>>(p);
+                YG_CUDA(ctx, cudaGetLastError());
+                ctx->tm.n_kernel_launches++;
+                YG_CUDA(ctx, cudaMemcpyAsync(&novf, &ctx->d_scalars[SC_OVF], sizeof novf, cudaMemcpyDeviceToHost, st));
+                YG_CUDA(ctx, cudaStreamSynchronize(st));
+                if (novf) {       // rows with too many distinct columns for a warp table: dense kernel on that list
+                    p.row_list = ctx->d_ovf_rows; p.n_list = (uint32_t)novf;
+                    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_UNIT], 0, sizeof(unsigned long long), st));
+                    const int grid = (int)std::min<unsigned long long>((unsigned long long)ctx->num_sms * occ, novf * n_tiles);
+                    kern<<<grid, k3_threads, smem, st>>>(p);
+                    YG_CUDA(ctx, cudaGetLastError());
+                    ctx->tm.n_kernel_launches++;
+                }
+            } else {
+                const unsigned long long units = (unsigned long long)(row_end - row_begin) * n_tiles;
+                const int grid = (int)std::min<unsigned long long>((unsigned long long)ctx->num_sms * occ, units);
+                kern<<<grid, k3_threads, smem, st>>>(p);
+                YG_CUDA(ctx, cudaGetLastError());
+                ctx->tm.n_kernel_launches++;
+            }
             YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-            unsigned long long cnt = 0;
             YG_CUDA(ctx, cudaMemcpyAsync(&cnt, &ctx->d_scalars[SC_OUT], sizeof cnt, cudaMemcpyDeviceToHost, st));
             YG_CUDA(ctx, cudaStreamSynchronize(st));
             ctx->tm.ms_count += elapsed(ctx, 0, 1);
             ctx->tm.n_count_launches++;
-            ctx->tm.n_kernel_launches++;
+            ctx->last_count_kernel = use_warp ? 2 : 1;
+            ctx->last_count_overflow_rows = novf;
             npairs = cnt;
             if (npairs <= ctx->out_cap) break;
             if (attempt == 1) return ygpu_fail(ctx, YGPU_ERR_CUDA, "pair buffer overflow after resize");
@@ -820,6 +1014,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return YGPU_ERR_ARG;
     if (!strcmp(name, "force_tile_w")) { ctx->force_tile_w = (uint32_t)value; return 0; }
     if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
+    if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

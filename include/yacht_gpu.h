@@ -150,6 +150,10 @@ void ygpu_sketch_set_free(ygpu_sketch_set* s);
 /* hashes[offsets[g] .. offsets[g+1]) is sketch g (any order, duplicates allowed).  HOST pointers;
  * copied to the device (pinned staging is the caller's choice).                                 */
 int ygpu_load_sketches(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* offsets, uint32_t n_genomes);
+/* Same sketches given as `nblocks` separate HOST pieces that concatenate to the flat hash array
+ * (what a multi-threaded parser leaves behind): copied piece by piece, no host-side assembly.   */
+int ygpu_load_sketch_blocks(ygpu_ctx* ctx, const uint64_t* const* blocks, const uint64_t* block_lens, uint32_t nblocks,
+                            const uint64_t* offsets, uint32_t n_genomes);
 /* Same, but DEVICE pointers on ctx's device; the arrays are copied device-to-device.            */
 int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n_genomes);
 int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats /* may be NULL */);

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libyachtgpu.so")
 # every symbol include/yacht_gpu.h declares (tests check the library exports each of them)
 ABI_SYMBOLS = [
     "ygpu_device_count", "ygpu_ctx_create", "ygpu_ctx_destroy", "ygpu_last_error", "ygpu_free",
-    "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketches_device",
+    "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketch_blocks", "ygpu_load_sketches_device",
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test",
@@ -98,6 +98,7 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.ygpu_load_sketches.argtypes = [vp, vp, vp, u32]
     lib.ygpu_load_sketches_device.argtypes = [vp, vp, vp, u32]
+    lib.ygpu_load_sketch_blocks.argtypes = [vp, vp, vp, u32, vp, u32]
     lib.ygpu_build_index.argtypes = [vp, ctypes.POINTER(IndexStats)]
     lib.ygpu_pairwise_flag.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.ygpu_row_partition.argtypes = [vp, u32, vp]

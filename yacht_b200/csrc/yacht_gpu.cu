@@ -224,6 +224,35 @@ static int load_common(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* of
 extern "C" int ygpu_load_sketches(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* offsets, uint32_t n) {
     return load_common(ctx, hashes, offsets, n, false);
 }
+extern "C" int ygpu_load_sketch_blocks(ygpu_ctx* ctx, const uint64_t* const* blocks, const uint64_t* block_lens, uint32_t nblocks,
+                                       const uint64_t* offsets, uint32_t n) {
+    if (!ctx || !offsets || (nblocks && (!blocks || !block_lens))) return YGPU_ERR_ARG;
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    release_sketches(ctx);
+    uint64_t T = 0;
+    for (uint32_t b = 0; b < nblocks; b++) T += block_lens[b];
+    if (T != offsets[n] || offsets[0] != 0) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketch_blocks: pieces hold %llu hashes, offsets say %llu",
+                                                             (unsigned long long)T, (unsigned long long)offsets[n]);
+    for (uint32_t g = 0; g < n; g++)
+        if (offsets[g + 1] < offsets[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+    if (T >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)T);
+    ctx->n = n;
+    ctx->T = T;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_hashes, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    uint64_t pos = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        if (block_lens[b]) YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_hashes + pos, blocks[b], block_lens[b] * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        pos += block_lens[b];
+    }
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    YG_CHECK(finish_load(ctx));
+    ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
+    return 0;
+}
+
 extern "C" int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n) {
     return load_common(ctx, d_hashes, d_offsets, n, true);
 }

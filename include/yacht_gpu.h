@@ -133,7 +133,8 @@ int ygpu_get_timings(ygpu_ctx* ctx, ygpu_timings* out);
 /* CUDA-event stopwatch on the context's stream (slots 0..3): time a whole step from outside.    */
 int ygpu_mark(ygpu_ctx* ctx, int slot);
 int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
-/* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel;
+/* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel and
+ * "force_u16" = 1 selects its packed 16-bit counters (both are otherwise chosen from N);
  * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default);
  * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic).   */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);

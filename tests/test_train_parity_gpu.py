@@ -122,3 +122,63 @@ def test_msd_two_level_partition(gpu_ctx):
     db2 = synth.from_sketches(parts)
     st, _ = _check(gpu_ctx, db2, THR, expect_path=1)
     assert st["has_duplicates"] == 1
+
+
+def test_count_kernel_tiled_and_u16_variants(gpu_ctx):
+    # the accumulator geometries that large N selects (column tiles, packed 16-bit counters), forced at small N
+    db = synth.make_reference_db(1500, 14, mean_size=500, sd_size=150)
+    ref = to.oracle_train(db.hashes, db.offsets, 0.1)
+    gpu_ctx.load_sketches(db.hashes, db.offsets)
+    gpu_ctx.build_index()
+    try:
+        for tile_w, u16 in [(0, 1), (401, 0), (400, 1), (64, 1), (3, 0)]:
+            gpu_ctx.set_option("force_tile_w", tile_w)
+            gpu_ctx.set_option("force_u16", u16)
+            got = gpu_ctx.pairwise_flag(0.1)
+            assert _pairs_tuple(got) == _pairs_tuple(ref.pairs), (tile_w, u16)
+    finally:
+        gpu_ctx.set_option("force_tile_w", 0)
+        gpu_ctx.set_option("force_u16", 0)
+
+
+def test_full_size_properties_85k(gpu_ctx):
+    """BASELINE.json's full size (85 205 genomes): properties that do not need the oracle --
+    the two independent count kernels agree, flagged pairs are consistent with the sketch sizes,
+    every planted twin pair above the threshold is found, and row-range shards union to the whole."""
+    db = synth.make_reference_db(85205, 3)
+    gpu_ctx.load_sketches(db.hashes, db.offsets)
+    st = gpu_ctx.build_index()
+    assert st["index_path"] == 1 and st["n_hashes"] == int(db.offsets[-1])
+    assert st["n_distinct"] - st["n_singleton"] == st["n_index"]
+    gpu_ctx.set_option("count_kernel", 1)
+    dense = gpu_ctx.pairwise_flag(THR)
+    gpu_ctx.set_option("count_kernel", 2)
+    warp = gpu_ctx.pairwise_flag(THR)
+    gpu_ctx.set_option("count_kernel", 0)
+    assert dense.tobytes() == warp.tobytes()
+    sizes = db.sizes
+    i, j, c = dense["i"].astype(np.int64), dense["j"].astype(np.int64), dense["count"].astype(np.int64)
+    assert np.all(i != j) and np.all(c >= 1) and np.all(c <= np.minimum(sizes[i], sizes[j]))
+    assert np.all(c / sizes[i] >= THR)                                   # every emitted pair passes the reference's test
+    key = i * db.n + j
+    assert np.all(np.diff(key) > 0)                                      # sorted by (i, j), no duplicates
+    same_cluster = db.cluster[i] == db.cluster[j]
+    assert np.all(same_cluster & (db.cluster[i] >= 0))                   # random 64-bit hashes never collide across clusters
+    # exact counts for a sample of flagged pairs, recomputed on the host
+    rng = np.random.default_rng(0)
+    for k in rng.choice(len(dense), size=200, replace=False):
+        a, b = db.sketch(int(i[k])), db.sketch(int(j[k]))
+        assert int(c[k]) == int(np.intersect1d(a, b, assume_unique=True).size)
+    # shards
+    b4 = gpu_ctx.row_partition(4)
+    parts = [gpu_ctx.pairwise_flag(THR, int(b4[k]), int(b4[k + 1])) for k in range(4)]
+    merged = np.sort(np.concatenate(parts), order=["i", "j"])
+    assert merged.tobytes() == dense.tobytes()
+    # the general (sort) index path gives the same answer at full size
+    gpu_ctx.set_option("index_path", 0)
+    st0 = gpu_ctx.build_index()
+    alt = gpu_ctx.pairwise_flag(THR)
+    gpu_ctx.set_option("index_path", 1)
+    assert st0["index_path"] == 0 and alt.tobytes() == dense.tobytes()
+    for f in ("n_distinct", "n_singleton", "n_index", "n_postings", "n_increments"):
+        assert st0[f] == st[f], f

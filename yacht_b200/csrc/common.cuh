@@ -67,6 +67,7 @@ struct ygpu_ctx {
     uint64_t pairs_cap = 0;
     uint64_t n_pairs = 0;
     uint32_t force_tile_w = 0;      // test hook: cap the accumulator tile width (0 = automatic)
+    int force_u16 = 0;              // test hook: packed 16-bit counters even when 32-bit ones fit
 
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
 

@@ -884,7 +884,10 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
             else if (u16_ok) { use_u16 = true; tile_w = (budget / 2) & ~1u; }
             else tile_w = budget / 4;
         }
+        if (ctx->force_u16 && u16_ok) use_u16 = true;                                       // test hook
         if (ctx->force_tile_w && ctx->force_tile_w < tile_w) tile_w = ctx->force_tile_w;   // test hook
+        if (use_u16) tile_w &= ~1u;
+        if (tile_w < 2) tile_w = 2;
         const uint32_t n_tiles = (n + tile_w - 1) / tile_w;
         const uint32_t acc_words = use_u16 ? (tile_w + 1) / 2 : tile_w;
         const size_t smem = (size_t)(acc_words + (acc_words & 1u)) * 4 + fixed;
@@ -1042,6 +1045,7 @@ extern "C" int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms
 extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return YGPU_ERR_ARG;
     if (!strcmp(name, "force_tile_w")) { ctx->force_tile_w = (uint32_t)value; return 0; }
+    if (!strcmp(name, "force_u16")) { ctx->force_u16 = (int)value; return 0; }
     if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
     if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);

@@ -38,7 +38,8 @@ struct ygpu_ctx {
     uint64_t* d_row_ptr = nullptr;  // [n+1] CSR over row_items (general path)
     const uint64_t* d_row_begin = nullptr;  // [n] start of row g's work list in d_row_items (d_row_ptr or d_offsets)
     uint64_t* d_row_items = nullptr;// [n_items] (first posting slot << 32) | count  -- per query genome
-    uint64_t* d_row_work = nullptr; // [n]   increments row i performs (sum of counts)
+    uint64_t* d_row_work = nullptr; // [n]   increments row i performs (sum of counts); filled on demand
+    bool row_work_valid = false;
     unsigned long long* d_row_cnt = nullptr;  // [n+1] build scratch
     // MSD-partition build (index_msd.cu)
     uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets

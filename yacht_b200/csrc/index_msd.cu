@@ -243,7 +243,7 @@ struct BucketArgs {
     uint32_t nb;
     int gb;
     uint32_t* post;              // [T] postings (genome ids): a bucket writes its groups at the start of its own slice
-    const uint64_t* row_off;     // [n] sketch offsets: row g's work list lives at row_items[row_off[g] ..]
+    const uint64_t* __restrict__ row_off;     // [n] sketch offsets: row g's work list lives at row_items[row_off[g] ..]
     uint64_t* row_items;         // [T] (first following posting << 32) | how many follow, per query genome
     unsigned long long* row_cnt; // [n] items written per row
     unsigned long long* row_work;// [n] increments per row
@@ -255,10 +255,9 @@ struct BucketArgs {
 __device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem) {
     const unsigned long long k = atomicAdd(&a.row_cnt[g], 1ull);
     a.row_items[a.row_off[g] + k] = (next_pos << 32) | ((uint64_t)rem << 2);      // item format v2, indirect
-    atomicAdd(&a.row_work[g], (unsigned long long)rem);
 }
 
-__global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
+__global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* E = (uint64_t*)smem_raw;                               // [BK_CAP] the bucket's packed words
     uint32_t* H = (uint32_t*)(E + BK_CAP);                           // [BK_HS]  slot -> most recent entry of that key's chain
@@ -267,6 +266,7 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
     unsigned short* queue = slot_of + BK_CAP;                        // [BK_CAP / 2] chain heads of groups with >= 2 members
     unsigned short* longq = queue + BK_CAP / 2;                      // [BK_LONGQ] heads of groups larger than BK_KMAX
     uint32_t* scratch = H;                                           // [BK_CAP] reused by the large-group path
+    uint32_t* scratch2 = H;                                          // [BK_CAP] dense pass: per-group id arrays (H is dead after the heads pass)
     __shared__ uint32_t s_nq, s_nlong, s_cnt, s_pcur;
     const unsigned short NONE = 0xFFFFu;
     const uint32_t EMPTY = 0xFFFFFFFFu;
@@ -317,53 +317,80 @@ __global__ void __launch_bounds__(BK_THREADS) k2_bucket(const BucketArgs a) {
         // ---- dense pass over the queued groups: order by genome id, claim a slice of the bucket's
         //      posting region (shared-memory cursor: no grid-wide reservation), write postings + items
         const uint32_t nq = s_nq;
+        const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
         for (uint32_t t = threadIdx.x; t < nq; t += BK_THREADS) {
-            uint32_t g[BK_KMAX];
-            uint32_t L = 0;
             const unsigned short head = queue[t];
-            for (unsigned short j = head; j != NONE; j = nxt[j]) {
-                if (L < BK_KMAX) g[L] = (uint32_t)(E[j] & gmask);
-                L++;
+            // ---- fast path: groups of 2..4 members (the bulk), entirely in scalar registers --------
+            const unsigned short j1 = nxt[head];                       // != NONE: queued groups have >= 2 members
+            const unsigned short j2 = nxt[j1];
+            const unsigned short j3 = j2 != NONE ? nxt[j2] : NONE;
+            const bool small = j3 == NONE || nxt[j3] == NONE;
+            if (small && can_inline) {
+                uint32_t g0 = (uint32_t)(E[head] & gmask), g1 = (uint32_t)(E[j1] & gmask);
+                uint32_t g2 = j2 != NONE ? (uint32_t)(E[j2] & gmask) : 0xFFFFFFFFu;
+                uint32_t g3 = j3 != NONE ? (uint32_t)(E[j3] & gmask) : 0xFFFFFFFFu;
+                const uint32_t L = 2u + (j2 != NONE) + (j3 != NONE);
+                // 5-comparator sorting network (absent members are +inf and sink to the end)
+#define YG_CSWAP(x, y) { const uint32_t lo_ = min(x, y), hi_ = max(x, y); x = lo_; y = hi_; }
+                YG_CSWAP(g0, g1) YG_CSWAP(g2, g3) YG_CSWAP(g0, g2) YG_CSWAP(g1, g3) YG_CSWAP(g1, g2)
+#undef YG_CSWAP
+                st_w += (unsigned long long)L * L;
+                st_p += L; st_i += L - 1;
+                st_dups += (g0 == g1) + (L > 2 && g1 == g2) + (L > 3 && g2 == g3);
+                // members 0 .. L-2 each get one inline item; loads and returning atomics first, stores after
+                const uint64_t ro0 = __ldg(&a.row_off[g0]);
+                const uint64_t ro1 = L > 2 ? __ldg(&a.row_off[g1]) : 0ull;
+                const uint64_t ro2 = L > 3 ? __ldg(&a.row_off[g2]) : 0ull;
+                const unsigned long long k0 = atomicAdd(&a.row_cnt[g0], 1ull);
+                const unsigned long long k1 = L > 2 ? atomicAdd(&a.row_cnt[g1], 1ull) : 0ull;
+                const unsigned long long k2 = L > 3 ? atomicAdd(&a.row_cnt[g2], 1ull) : 0ull;
+                uint64_t it0 = (uint64_t)(L - 1) | ((uint64_t)g1 << 2);
+                if (L > 2) it0 |= (uint64_t)g2 << 22;
+                if (L > 3) it0 |= (uint64_t)g3 << 42;
+                a.row_items[ro0 + k0] = it0;
+                if (L > 2) a.row_items[ro1 + k1] = (uint64_t)(L - 2) | ((uint64_t)g2 << 2) | (L > 3 ? (uint64_t)g3 << 22 : 0ull);
+                if (L > 3) a.row_items[ro2 + k2] = 1ull | ((uint64_t)g3 << 2);
+                continue;
             }
+            // ---- general path: 5 .. BK_KMAX members.  The group's ids are ordered in SHARED memory (a slice of
+            //      the dead hash table): with 4 CTAs x 57 KB of shared memory per SM almost no L1 is left, so a
+            //      thread-local array (local memory) would turn every access into an L2 round trip.
+            uint32_t L = 0;
+            for (unsigned short j = head; j != NONE; j = nxt[j]) L++;
             st_w += (unsigned long long)L * L;
             if (L > BK_KMAX) { longq[atomicAdd(&s_nlong, 1u)] = head; continue; }
-            for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
-                const uint32_t v = g[x];
-                uint32_t y = x;
-                while (y > 0 && g[y - 1] > v) { g[y] = g[y - 1]; y--; }
-                g[y] = v;
+            const uint32_t off = atomicAdd(&s_pcur, L);
+            uint32_t* gs = scratch2 + off;                 // off + L <= m <= BK_CAP
+            {
+                uint32_t x = 0;
+                for (unsigned short j = head; j != NONE; j = nxt[j]) gs[x++] = (uint32_t)(E[j] & gmask);
             }
-            // Items whose remaining list has <= 3 genomes carry those ids INLINE (item format v2, see
-            // common.cuh): the count kernel then never dereferences d_post for them -- that indirection
-            // was a 32-byte sector per 4-byte posting.  Groups of <= 4 members need no postings at all.
-            const bool can_inline = a.gb <= 20;
-            const bool need_post = !can_inline || L > 4;
-            const uint64_t pp = need_post ? (uint64_t)bb + atomicAdd(&s_pcur, L) : 0ull;
+            for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
+                const uint32_t v = gs[x];
+                uint32_t y = x;
+                while (y > 0 && gs[y - 1] > v) { gs[y] = gs[y - 1]; y--; }
+                gs[y] = v;
+            }
+            const uint64_t pp = (uint64_t)bb + off;
             st_p += L; st_i += L - 1;
-            // all returning atomics first (independent, so their latencies overlap), then the stores
-            uint32_t k[BK_KMAX];
-#pragma unroll
-            for (uint32_t x = 0; x < BK_KMAX - 1; x++)
-                if (x + 1 < L) k[x] = (uint32_t)atomicAdd(&a.row_cnt[g[x]], 1ull);
-#pragma unroll
-            for (uint32_t x = 0; x < BK_KMAX; x++)
-                if (x < L) {
-                    if (need_post) a.post[pp + x] = g[x];
-                    if (x + 1 < L) {
-                        if (g[x] == g[x + 1]) st_dups++;
-                        const uint32_t rem = L - x - 1;
-                        uint64_t item;
-                        if (can_inline && rem <= 3) {
-                            item = (uint64_t)rem | ((uint64_t)g[x + 1] << 2);
-                            if (rem >= 2) item |= (uint64_t)g[(x + 2) < BK_KMAX ? (x + 2) : 0] << 22;
-                            if (rem >= 3) item |= (uint64_t)g[(x + 3) < BK_KMAX ? (x + 3) : 0] << 42;
-                        } else {
-                            item = ((pp + x + 1) << 32) | ((uint64_t)rem << 2);
-                        }
-                        a.row_items[a.row_off[g[x]] + k[x]] = item;
-                        atomicAdd(&a.row_work[g[x]], (unsigned long long)rem);
+            for (uint32_t x = 0; x < L; x++) {
+                const uint32_t gx = gs[x];
+                a.post[pp + x] = gx;
+                if (x + 1 < L) {
+                    const uint32_t rem = L - x - 1;
+                    if (gx == gs[x + 1]) st_dups++;
+                    uint64_t item;
+                    if (can_inline && rem <= 3) {
+                        item = (uint64_t)rem | ((uint64_t)gs[x + 1] << 2);
+                        if (rem >= 2) item |= (uint64_t)gs[x + 2] << 22;
+                        if (rem >= 3) item |= (uint64_t)gs[x + 3] << 42;
+                    } else {
+                        item = ((pp + x + 1) << 32) | ((uint64_t)rem << 2);
                     }
+                    const unsigned long long k = atomicAdd(&a.row_cnt[gx], 1ull);
+                    a.row_items[__ldg(&a.row_off[gx]) + k] = item;
                 }
+            }
         }
         __syncthreads();
 

@@ -92,7 +92,7 @@ extern "C" int ygpu_ctx_create(ygpu_ctx** out, int device) {
         return ygpu_fail(nullptr, YGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    if (cudaMalloc(&ctx->d_scalars, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(unsigned long long)) != cudaSuccess) {
         ygpu_ctx_destroy(ctx);
         return ygpu_fail(nullptr, YGPU_ERR_NOMEM, "cudaMalloc(scalars) failed");
     }
@@ -101,6 +101,7 @@ extern "C" int ygpu_ctx_create(ygpu_ctx** out, int device) {
 }
 
 static void release_index(ygpu_ctx* ctx) {   // invalidate only: the buffers are kept for reuse
+    ctx->row_work_valid = false;
     ctx->sorted = false;
     ctx->indexed = false;
     ctx->P = 0; ctx->n_items = 0;
@@ -499,6 +500,7 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->d_row_begin = ctx->d_row_ptr;   // d_row_cnt (the scatter's fill cursors) now holds each row's item count
+    ctx->row_work_valid = true;          // k_post_compact accumulated it
     ctx->tm.n_kernel_launches += 1;  // k_flag_runs
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
 
@@ -886,7 +888,6 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
         }
         if (ctx->force_u16 && u16_ok) use_u16 = true;                                       // test hook
         if (ctx->force_tile_w && ctx->force_tile_w < tile_w) tile_w = ctx->force_tile_w;   // test hook
-        if (use_u16) tile_w &= ~1u;
         if (tile_w < 2) tile_w = 2;
         const uint32_t n_tiles = (n + tile_w - 1) / tile_w;
         const uint32_t acc_words = use_u16 ? (tile_w + 1) / 2 : tile_w;
@@ -1051,10 +1052,37 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 
+// increments each row performs = sum over its work items of how many postings follow (one warp per row)
+__global__ void __launch_bounds__(256) k_row_work(const uint64_t* __restrict__ list_begin, const unsigned long long* __restrict__ row_n,
+                                                   const uint64_t* __restrict__ row_items, uint32_t n, uint64_t* __restrict__ row_work) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += (gridDim.x * blockDim.x) >> 5) {
+        const uint64_t ib = list_begin[row];
+        const uint64_t cnt = row_n[row];
+        unsigned long long s = 0;
+        for (uint64_t k = lane; k < cnt; k += 32) {
+            const uint64_t item = row_items[ib + k];
+            const uint32_t c = (uint32_t)item & 3u;
+            s += c ? c : ((uint32_t)(item >> 2) & 0x3FFFFFFFu);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) row_work[row] = s;
+    }
+}
+
 extern "C" int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds) {
     if (!ctx || !bounds || nparts == 0) return YGPU_ERR_ARG;
     if (!ctx->indexed) return ygpu_fail(ctx, YGPU_ERR_STATE, "row_partition: build_index first");
     const uint32_t n = ctx->n;
+    if (nparts == 1) { bounds[0] = 0; bounds[1] = n; return 0; }
+    if (!ctx->row_work_valid && n && ctx->n_items) {
+        YG_CUDA(ctx, cudaSetDevice(ctx->device));
+        k_row_work<<<grid_for(ctx, (uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->d_row_begin, ctx->d_row_cnt, ctx->d_row_items, n, ctx->d_row_work);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+        YG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->row_work_valid = true;
+    }
     std::vector<uint64_t> work(n);
     if (n) YG_CUDA(ctx, cudaMemcpy(work.data(), ctx->d_row_work, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     // cost model: increments + a per-row constant (launching / scanning a row is not free)

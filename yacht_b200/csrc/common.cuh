@@ -45,6 +45,8 @@ struct ygpu_ctx {
     uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets
     uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
     uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
+    uint32_t* d_rec_gid = nullptr;  // [T] work records (query genome) before they are grouped by genome
+    uint32_t* d_nrec = nullptr;     // [buckets] records per final bucket
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
     int msd_fallbacks = 0;
     int last_index_path = 0;        // which path built the current index

@@ -36,8 +36,8 @@ constexpr int NB_MAX = 2048;        // digits per partition level
 constexpr int BK_CAP = 3072;        // max elements of a final bucket (shared-memory resident)
 constexpr int BK_HS = 4096;         // hash-table slots per bucket (> BK_CAP: never full)
 constexpr int BK_THREADS = 256;
-constexpr int BK_KMAX = 12;         // groups up to this size are ordered by one thread in registers
-constexpr int BK_LONGQ = 240;       // > BK_CAP / (BK_KMAX + 1) = 236: queue of larger groups
+constexpr int BK_KMAX = 8;          // groups up to this size are ordered by one thread in registers
+constexpr int BK_LONGQ = 352;       // > BK_CAP / (BK_KMAX + 1) = 236: queue of larger groups
 constexpr uint32_t A_TARGET = 1200; // average elements per used final bucket
 
 enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10 };   // extra slots of ctx->d_scalars
@@ -243,18 +243,17 @@ struct BucketArgs {
     uint32_t nb;
     int gb;
     uint32_t* post;              // [T] postings (genome ids): a bucket writes its groups at the start of its own slice
-    const uint64_t* __restrict__ row_off;     // [n] sketch offsets: row g's work list lives at row_items[row_off[g] ..]
-    uint64_t* row_items;         // [T] (first following posting << 32) | how many follow, per query genome
-    unsigned long long* row_cnt; // [n] items written per row
-    unsigned long long* row_work;// [n] increments per row
+    uint32_t* rec_gid;           // [T] work records (query genome, item), written into the bucket's own slice:
+    uint64_t* rec_item;          //     no atomics on hot per-genome counters inside this barrier-heavy kernel
+    uint32_t* nrec;              // [nb] records written per bucket
     unsigned long long* scal;
 };
 
-// one work item for query genome g: "the `rem` postings starting at `next_pos` share a hash with you".
-// A row can receive at most one item per hash it holds, so its slice of row_items never overflows.
-__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem) {
-    const unsigned long long k = atomicAdd(&a.row_cnt[g], 1ull);
-    a.row_items[a.row_off[g] + k] = (next_pos << 32) | ((uint64_t)rem << 2);      // item format v2, indirect
+// one work record for query genome g: "the `rem` postings starting at `next_pos` share a hash with you"
+// (item format v2, indirect).  k2_rec_scatter later moves the records into the per-genome lists.
+__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem, uint64_t q) {
+    a.rec_gid[q] = g;
+    a.rec_item[q] = (next_pos << 32) | ((uint64_t)rem << 2);
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
@@ -267,12 +266,18 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
     unsigned short* longq = queue + BK_CAP / 2;                      // [BK_LONGQ] heads of groups larger than BK_KMAX
     uint32_t* scratch = H;                                           // [BK_CAP] reused by the large-group path
     uint32_t* scratch2 = H;                                          // [BK_CAP] dense pass: per-group id arrays (H is dead after the heads pass)
-    __shared__ uint32_t s_nq, s_nlong, s_cnt, s_pcur;
+    __shared__ uint32_t s_nq, s_nlong, s_cnt, s_pcur, s_rcur;
     const unsigned short NONE = 0xFFFFu;
     const uint32_t EMPTY = 0xFFFFFFFFu;
     const uint64_t gmask = a.gb ? ((1ull << a.gb) - 1ull) : 0ull;
 
     unsigned long long st_heads = 0, st_single = 0, st_w = 0, st_dups = 0, st_p = 0, st_i = 0;
+#ifdef YG_PHASE_TIMING   // developer aid: per-phase clock64 totals of thread 0 and thread 255 -> d_scalars[20..31]
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define YG_PH(k) { const long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
+#else
+#define YG_PH(k)
+#endif
 
     for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
         const uint32_t bb = a.base[b];
@@ -280,8 +285,10 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
         if (m == 0) continue;      // uniform per CTA
         for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) { E[i] = a.ent[(uint64_t)bb + i]; nxt[i] = NONE; }
         for (uint32_t i = threadIdx.x; i < BK_HS; i += BK_THREADS) H[i] = EMPTY;
-        if (threadIdx.x == 0) { s_nq = 0; s_nlong = 0; s_pcur = 0; }
+        if (threadIdx.x == 0) { s_nq = 0; s_nlong = 0; s_pcur = 0; s_rcur = 0; }
+        YG_PH(0)
         __syncthreads();
+        YG_PH(1)
 
         // ---- insert: one CAS for a new key, one more to push onto an existing key's chain ------------
         for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
             }
             slot_of[i] = (unsigned short)slot;
         }
+        YG_PH(2)
         __syncthreads();
 
         // ---- heads: count distinct hashes / singletons, queue the groups that have >= 2 members -------
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
             queue[atomicAdd(&s_nq, 1u)] = (unsigned short)i;
         }
         __syncthreads();
+        YG_PH(3)
 
         // ---- dense pass over the queued groups: order by genome id, claim a slice of the bucket's
         //      posting region (shared-memory cursor: no grid-wide reservation), write postings + items
@@ -337,19 +346,14 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
                 st_w += (unsigned long long)L * L;
                 st_p += L; st_i += L - 1;
                 st_dups += (g0 == g1) + (L > 2 && g1 == g2) + (L > 3 && g2 == g3);
-                // members 0 .. L-2 each get one inline item; loads and returning atomics first, stores after
-                const uint64_t ro0 = __ldg(&a.row_off[g0]);
-                const uint64_t ro1 = L > 2 ? __ldg(&a.row_off[g1]) : 0ull;
-                const uint64_t ro2 = L > 3 ? __ldg(&a.row_off[g2]) : 0ull;
-                const unsigned long long k0 = atomicAdd(&a.row_cnt[g0], 1ull);
-                const unsigned long long k1 = L > 2 ? atomicAdd(&a.row_cnt[g1], 1ull) : 0ull;
-                const unsigned long long k2 = L > 3 ? atomicAdd(&a.row_cnt[g2], 1ull) : 0ull;
+                // members 0 .. L-2 each get one inline item, recorded in the bucket's own slice
+                const uint64_t q = (uint64_t)bb + atomicAdd(&s_rcur, L - 1);
                 uint64_t it0 = (uint64_t)(L - 1) | ((uint64_t)g1 << 2);
                 if (L > 2) it0 |= (uint64_t)g2 << 22;
                 if (L > 3) it0 |= (uint64_t)g3 << 42;
-                a.row_items[ro0 + k0] = it0;
-                if (L > 2) a.row_items[ro1 + k1] = (uint64_t)(L - 2) | ((uint64_t)g2 << 2) | (L > 3 ? (uint64_t)g3 << 22 : 0ull);
-                if (L > 3) a.row_items[ro2 + k2] = 1ull | ((uint64_t)g3 << 2);
+                a.rec_gid[q] = g0; a.rec_item[q] = it0;
+                if (L > 2) { a.rec_gid[q + 1] = g1; a.rec_item[q + 1] = (uint64_t)(L - 2) | ((uint64_t)g2 << 2) | (L > 3 ? (uint64_t)g3 << 22 : 0ull); }
+                if (L > 3) { a.rec_gid[q + 2] = g2; a.rec_item[q + 2] = 1ull | ((uint64_t)g3 << 2); }
                 continue;
             }
             // ---- general path: 5 .. BK_KMAX members.  The group's ids are ordered in SHARED memory (a slice of
@@ -373,6 +377,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
             }
             const uint64_t pp = (uint64_t)bb + off;
             st_p += L; st_i += L - 1;
+            const uint64_t q = (uint64_t)bb + atomicAdd(&s_rcur, L - 1);
             for (uint32_t x = 0; x < L; x++) {
                 const uint32_t gx = gs[x];
                 a.post[pp + x] = gx;
@@ -387,12 +392,14 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
                     } else {
                         item = ((pp + x + 1) << 32) | ((uint64_t)rem << 2);
                     }
-                    const unsigned long long k = atomicAdd(&a.row_cnt[gx], 1ull);
-                    a.row_items[__ldg(&a.row_off[gx]) + k] = item;
+                    a.rec_gid[q + x] = gx;
+                    a.rec_item[q + x] = item;
                 }
             }
         }
+        YG_PH(4)
         __syncthreads();
+        YG_PH(5)
 
         // ---- large groups: the whole CTA gathers, bitonic-sorts and writes one group at a time -------
         const uint32_t nlong = s_nlong;
@@ -421,19 +428,25 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
                     __syncthreads();
                 }
             const uint64_t pp = (uint64_t)bb + s_pcur;
+            const uint64_t qq = (uint64_t)bb + s_rcur;
             __syncthreads();
-            if (threadIdx.x == 0) { s_pcur += L; st_p += L; st_i += L - 1; }
+            if (threadIdx.x == 0) { s_pcur += L; s_rcur += L - 1; st_p += L; st_i += L - 1; }
             for (uint32_t x = threadIdx.x; x < L; x += BK_THREADS) {
                 const uint32_t gx = scratch[x];
                 a.post[pp + x] = gx;
                 if (x + 1 < L) {
                     if (gx == scratch[x + 1]) st_dups++;
-                    emit_member(a, gx, pp + x + 1, L - x - 1);
+                    emit_member(a, gx, pp + x + 1, L - x - 1, qq + x);
                 }
             }
             __syncthreads();
         }
+        if (threadIdx.x == 0) a.nrec[b] = s_rcur;      // every thread is past the last barrier that follows a write of s_rcur
+        __syncthreads();
     }
+#ifdef YG_PHASE_TIMING
+    if (threadIdx.x == 0 || threadIdx.x == 255) for (int k = 0; k < 6; k++) atomicAdd(&a.scal[(threadIdx.x ? 26 : 20) + k], (unsigned long long)ph[k]);
+#endif
     st_heads = block_sum<BK_THREADS>(st_heads);
     st_single = block_sum<BK_THREADS>(st_single);
     st_w = block_sum<BK_THREADS>(st_w);
@@ -447,6 +460,26 @@ __global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
         if (st_dups) atomicAdd(&a.scal[SC_DUPS], st_dups);
         if (st_p) atomicAdd(&a.scal[SCM_PCUR], st_p);
         if (st_i) atomicAdd(&a.scal[SCM_ICUR], st_i);
+    }
+}
+
+// records -> per-genome work lists.  One warp per bucket: the returning atomics on the (hot) per-genome
+// counters are issued with full thread-level parallelism here, instead of sitting on the critical path of
+// a CTA that synchronises after every phase.
+__global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict__ base, const uint32_t* __restrict__ nrec, uint32_t nb,
+                                                       const uint32_t* __restrict__ rec_gid, const uint64_t* __restrict__ rec_item,
+                                                       const uint64_t* __restrict__ row_off, unsigned long long* __restrict__ row_cnt,
+                                                       uint64_t* __restrict__ row_items) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += warps) {
+        const uint32_t n = nrec[b];
+        const uint64_t bb = base[b];
+        for (uint32_t k = lane; k < n; k += 32) {
+            const uint32_t g = rec_gid[bb + k];
+            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            row_items[row_off[g] + slot] = rec_item[bb + k];
+        }
     }
 }
 
@@ -510,6 +543,9 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     uint32_t* cursor = base2 + ((uint64_t)p.nfb + 2);      // level-1 cursors first, then reused for level 2
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
     YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_PCUR], 0, 4 * sizeof(unsigned long long), st));
+#ifdef YG_PHASE_TIMING
+    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[20], 0, 12 * sizeof(unsigned long long), st));
+#endif
 
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     // ---- level 1 ----------------------------------------------------------------------------------
@@ -578,10 +614,16 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_rec_gid, T));
+    uint64_t* rec_item = nullptr;
+    if (d2) rec_item = ctx->d_ent1;                 // level-1 words are dead once level 2 has run
+    else { YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T)); rec_item = ctx->d_ent2; }
+    const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_nrec, (uint64_t)nbuckets + 1));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_nrec, 0, ((uint64_t)nbuckets + 1) * sizeof(uint32_t), st));
     BucketArgs b{};
-    b.ent = final_ent; b.base = final_base; b.nb = d2 ? p.nfb : p.nb1; b.gb = p.gb;
-    b.post = ctx->d_post; b.row_off = ctx->d_offsets; b.row_items = ctx->d_row_items;
-    b.row_cnt = ctx->d_row_cnt; b.row_work = (unsigned long long*)ctx->d_row_work; b.scal = ctx->d_scalars;
+    b.ent = final_ent; b.base = final_base; b.nb = nbuckets; b.gb = p.gb;
+    b.post = ctx->d_post; b.rec_gid = ctx->d_rec_gid; b.rec_item = rec_item; b.nrec = ctx->d_nrec; b.scal = ctx->d_scalars;
     {
         const size_t smem = (size_t)BK_CAP * 8 + (size_t)BK_HS * 4 + (size_t)BK_CAP * 2 * 2 + (size_t)BK_CAP + (size_t)BK_LONGQ * 2;
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -590,12 +632,23 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
         const int grid = (int)std::min<uint64_t>(b.nb, (uint64_t)ctx->num_sms * std::max(occ, 1));
         k2_bucket<<<grid, BK_THREADS, smem, st>>>(b);
         YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches++;
+        k2_rec_scatter<<<grid_for(ctx, (uint64_t)nbuckets * 32, 256, 16), 256, 0, st>>>(final_base, ctx->d_nrec, nbuckets, ctx->d_rec_gid, rec_item,
+                                                                                       ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 2;
     }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
+#ifdef YG_PHASE_TIMING
+    {
+        unsigned long long ph[12];
+        cudaMemcpy(ph, &ctx->d_scalars[20], sizeof ph, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[k2_bucket phases, cycles summed over CTAs; thread 0 | thread 255] load+init %llu | %llu, bar %llu | %llu, insert %llu | %llu, bar+heads+bar %llu | %llu, dense %llu | %llu, bar %llu | %llu\n",
+                ph[0], ph[6], ph[1], ph[7], ph[2], ph[8], ph[3], ph[9], ph[4], ph[10], ph[5], ph[11]);
+    }
+#endif
     const uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
     ctx->P = P;
     ctx->n_items = I;

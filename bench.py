@@ -344,10 +344,10 @@ def run_b200_arm(args):
                                   else "CUB DeviceRadixSort of (hash, genome) pairs (general path)",
                                   52 * Tn if msd else 12 * Tn * 2 * 7, part_ms,
                                   "8T + (12T+8T) + 8T + (8T+8T) = 52*T" if msd else "12*T*2*7 (SURVEY.md 8d)"),
-            "index_grouping": rl("k2_bucket + k2_rec_scatter (K2: shared-memory hash grouping -> postings + work records -> per-genome lists)" if msd
+            "index_grouping": rl("k2_group (K2: in-shared-memory counting sort + neighbour scan -> postings + per-genome work lists)" if msd
                                  else "k_flag_runs + scan + k_post_compact + k_items_scatter (general path)",
-                                 8 * Tn + 4 * Pn + 32 * In if msd else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
-                                 "8*T (words) + 4*P (postings) + 12*I + 12*I (records out/in) + 8*I (items)" if msd else "12*T + 4*P + 16*I"),
+                                 8 * Tn + 4 * Pn + 8 * In if msd else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
+                                 "8*T (words) + 4*P (postings) + 8*I (items)" if msd else "12*T + 4*P + 16*I"),
         }
         # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), when they were taken
         # on this very workload

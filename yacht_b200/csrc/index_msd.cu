@@ -483,6 +483,236 @@ __global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict
     }
 }
 
+// ---- grouping kernel (k2_group): sub-bucket counting filter + dense candidate scan ------------------------
+// k2_bucket (above) chains equal hashes through a CAS hash table; its chain walks are divergent (15 of 32
+// lanes active on average) and barrier-bound.  k2_group does the same job with uniform work per thread and
+// spends almost nothing on the ~80 % of hashes nobody shares:
+//   A  words -> registers; sub-bucket = next GK_SUBBITS hash bits; rank inside the sub-bucket from one
+//      shared-memory atomicAdd.  A word alone in its sub-bucket is a singleton: it is only counted.
+//   B  exclusive scan over the sizes of the sub-buckets holding >= 2 words (8 counters per thread, warp shuffles)
+//   C  the words of those sub-buckets ("candidates", ~30 %) are scattered to a dense array, sub-bucket by
+//      sub-bucket: 32 low bits of the remaining hash, genome id (+ remaining high hash bits), sub-bucket id
+//   D  one thread per candidate scans its sub-bucket (2-3 words): group size L, own rank among the members by
+//      genome id, first member's position; that first member claims L posting slots (shared-memory cursor)
+//   E  members write (genome id, members that follow) at claimed offset + rank: the groups are now dense and
+//      ordered by genome id in shared memory (aliasing the candidate arrays, which are dead)
+//   F  one thread per staged posting: coalesced posting writes (only for groups some item points into) and
+//      the member's work item, appended to the member's per-genome list.  The returning atomicAdd on the
+//      per-genome counter is consumed one bucket later (software pipelining), so its latency never sits
+//      between two barriers -- this replaces the separate record pass (k2_rec_scatter).
+constexpr int GK_THREADS = 256;
+constexpr int GK_SUBBITS = 11;
+constexpr int GK_NSUB = 1 << GK_SUBBITS;            // 2048 = 8 counters per thread
+constexpr int GK_FAST = 4;                          // words per thread for buckets of <= 1024 words (all but skewed ones)
+constexpr int GK_SLOW = BK_CAP / GK_THREADS;        // 12
+
+struct GroupArgs {
+    const uint64_t* ent;
+    const uint32_t* base;        // [nb + 1]
+    uint32_t nb;
+    int gb;
+    int sub_shift;               // sub-bucket digit = (word >> sub_shift) & sub_mask
+    uint32_t sub_mask;
+    uint64_t rest_mask;          // (word >> gb) & rest_mask = hash bits below the sub-bucket digit
+    uint32_t* post;              // [T]
+    const uint64_t* row_off;     // [n] start of genome g's work list (= sketch offsets)
+    unsigned long long* row_cnt; // [n] items appended so far
+    uint64_t* row_items;         // [T]
+    unsigned long long* scal;
+};
+
+struct GroupStats { uint32_t heads, single, dups; unsigned long long w; };   // postings = T - singles, items = postings - shared groups
+struct GroupPending { uint64_t item; uint32_t dst, slot; bool has; };         // T < 2^32: list positions fit 32 bits
+
+struct GroupSmem {
+    uint32_t* cnt;               // [GK_NSUB]      sub-bucket sizes (zero between buckets)
+    unsigned short* start2;      // [GK_NSUB + 8]  candidate-array start of every sub-bucket
+    uint32_t* K2;                // [BK_CAP]       candidates: low 32 bits of the remaining hash
+    uint32_t* G2;                // [BK_CAP]       candidates: genome id | remaining high hash bits << gb
+    unsigned short* SUB2;        // [BK_CAP]       candidates: sub-bucket id
+    unsigned short* gbase;       // [BK_CAP]       posting offset claimed by the group whose first member sits here
+    uint32_t* s_wsum;            // [8]
+};
+
+template <int ITEMS>
+__device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t bb, const uint32_t m, const GroupSmem& sm,
+                                             uint32_t* s_pcur, GroupStats& st, GroupPending& pd) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gmask = a.gb ? (uint32_t)((1ull << a.gb) - 1ull) : 0u;
+    // ---- A: load, sub-bucket rank ------------------------------------------------------------------
+    uint64_t e[ITEMS];
+    uint32_t rk[ITEMS];
+    const uint64_t* src = a.ent + bb + tid;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        if (k * GK_THREADS + tid < m) e[k] = src[k * GK_THREADS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        if (k * GK_THREADS + tid < m) rk[k] = atomicAdd(&sm.cnt[(uint32_t)(e[k] >> a.sub_shift) & a.sub_mask], 1u);
+    if (tid == 0) *s_pcur = 0;
+    __syncthreads();
+    // ---- B: scan the sizes of sub-buckets with >= 2 words (and reset the counters for the next bucket) ----
+    {
+        uint4* c4 = reinterpret_cast<uint4*>(&sm.cnt[8 * tid]);
+        uint4 c0 = c4[0], c1 = c4[1];
+        c4[0] = make_uint4(0u, 0u, 0u, 0u);
+        c4[1] = make_uint4(0u, 0u, 0u, 0u);
+        c0.x = c0.x >= 2 ? c0.x : 0u; c0.y = c0.y >= 2 ? c0.y : 0u; c0.z = c0.z >= 2 ? c0.z : 0u; c0.w = c0.w >= 2 ? c0.w : 0u;
+        c1.x = c1.x >= 2 ? c1.x : 0u; c1.y = c1.y >= 2 ? c1.y : 0u; c1.z = c1.z >= 2 ? c1.z : 0u; c1.w = c1.w >= 2 ? c1.w : 0u;
+        const uint32_t sum = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += v;
+        }
+        if (lane == 31) sm.s_wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wp = 0;
+#pragma unroll
+        for (int w = 0; w < GK_THREADS / 32 - 1; w++) wp += (w < (int)warp) ? sm.s_wsum[w] : 0u;
+        const uint32_t p0 = wp + inc - sum;
+        const uint32_t p1 = p0 + c0.x, p2 = p1 + c0.y, p3 = p2 + c0.z, p4 = p3 + c0.w, p5 = p4 + c1.x, p6 = p5 + c1.y, p7 = p6 + c1.z;
+        *reinterpret_cast<uint4*>(&sm.start2[8 * tid]) = make_uint4(p0 | (p1 << 16), p2 | (p3 << 16), p4 | (p5 << 16), p6 | (p7 << 16));
+        if (tid == GK_THREADS - 1) sm.start2[GK_NSUB] = (unsigned short)(p7 + c1.w);
+    }
+    __syncthreads();
+    // ---- C: candidates -> dense array, sub-bucket by sub-bucket; everything else is a singleton ---------------
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        if (k * GK_THREADS + tid < m) {
+            const uint32_t s = (uint32_t)(e[k] >> a.sub_shift) & a.sub_mask;
+            const uint32_t lo = sm.start2[s], hi = sm.start2[s + 1];
+            if (hi > lo) {
+                const uint64_t rest = (e[k] >> a.gb) & a.rest_mask;
+                const uint32_t pos = lo + rk[k];
+                sm.K2[pos] = (uint32_t)rest;
+                sm.G2[pos] = ((uint32_t)e[k] & gmask) | ((uint32_t)(rest >> 32) << a.gb);
+                sm.SUB2[pos] = (unsigned short)s;
+            } else {
+                st.heads++;
+                st.single++;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- D: dense scan over the candidates -----------------------------------------------------------------------
+    const uint32_t ncand = sm.start2[GK_NSUB];
+    uint32_t lr[ITEMS];            // group size | rank << 16   (0 = not a member of a shared group)
+    uint32_t gq[ITEMS];            // genome id of this thread's candidate
+    unsigned short qf[ITEMS];      // candidate position of the group's first member
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t q = k * GK_THREADS + tid;
+        lr[k] = 0; qf[k] = 0; gq[k] = 0;
+        if (q < ncand) {
+            const uint32_t kq = sm.K2[q], xq = sm.G2[q], s = sm.SUB2[q];
+            const uint32_t lo = sm.start2[s], hi = sm.start2[s + 1];
+            const uint32_t g = xq & gmask;
+            uint32_t L = 1, rank = 0, first = q, dup = 0;
+            for (uint32_t x = lo; x < hi; x++) {
+                if (sm.K2[x] == kq && x != q) {
+                    const uint32_t x2 = sm.G2[x];
+                    if (((x2 ^ xq) & ~gmask) == 0) {           // remaining high hash bits agree too
+                        L++;
+                        first = min(first, x);
+                        const uint32_t g2 = x2 & gmask;
+                        const bool tie = (g2 == g) && (x < q);
+                        rank += ((g2 < g) || tie) ? 1u : 0u;
+                        dup |= tie ? 1u : 0u;
+                    }
+                }
+            }
+            st.heads += rank == 0;
+            st.single += L == 1;
+            if (L >= 2) {
+                lr[k] = L | (rank << 16);
+                qf[k] = (unsigned short)first;
+                gq[k] = g;
+                st.dups += dup;
+                if (rank == 0) st.w += (unsigned long long)L * L;
+                if (first == q) sm.gbase[q] = (unsigned short)atomicAdd(s_pcur, L);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- E: dense, ordered groups in shared memory (the candidate arrays are dead: alias them) ---------------
+    uint32_t* stg_g = sm.K2;                                                     // [BK_CAP]
+    unsigned short* stg_rem = reinterpret_cast<unsigned short*>(sm.G2);          // [BK_CAP]
+    const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        if (lr[k]) {
+            const uint32_t L = lr[k] & 0xffffu, rank = lr[k] >> 16;
+            const uint32_t x = (uint32_t)sm.gbase[qf[k]] + rank;
+            stg_g[x] = gq[k];
+            stg_rem[x] = (unsigned short)((L - 1 - rank) | ((!can_inline || L > 4) ? 0x8000u : 0u));
+        }
+    }
+    __syncthreads();
+    // ---- F: postings + work items -------------------------------------------------------------------------------
+    const uint32_t np = *s_pcur;
+    for (uint32_t x = tid; x < np; x += GK_THREADS) {
+        const uint32_t g = stg_g[x];
+        const uint32_t rr = stg_rem[x];
+        const uint32_t rem = rr & 0x7fffu;
+        if (rr & 0x8000u) a.post[(uint64_t)bb + x] = g;
+        if (rem) {
+            uint64_t item;
+            if (can_inline && rem <= 3) {
+                item = (uint64_t)rem | ((uint64_t)stg_g[x + 1] << 2);
+                if (rem >= 2) item |= (uint64_t)stg_g[x + 2] << 22;
+                if (rem >= 3) item |= (uint64_t)stg_g[x + 3] << 42;
+            } else {
+                item = (((uint64_t)bb + x + 1) << 32) | ((uint64_t)rem << 2);
+            }
+            const uint32_t slot = (uint32_t)atomicAdd(&a.row_cnt[g], 1ull);
+            const uint32_t dst = (uint32_t)a.row_off[g];
+            if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued one bucket ago
+            pd.item = item; pd.dst = dst; pd.slot = slot; pd.has = true;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GroupSmem sm;
+    sm.cnt = (uint32_t*)smem_raw;                                    // 8 KB
+    sm.K2 = sm.cnt + GK_NSUB;                                        // 12 KB
+    sm.G2 = sm.K2 + BK_CAP;                                          // 12 KB
+    sm.start2 = (unsigned short*)(sm.G2 + BK_CAP);                   // 4 KB + 16
+    sm.SUB2 = sm.start2 + GK_NSUB + 8;                               // 6 KB
+    sm.gbase = sm.SUB2 + BK_CAP;                                     // 6 KB
+    __shared__ uint32_t s_wsum[GK_THREADS / 32];
+    __shared__ uint32_t s_pcur[2];
+    sm.s_wsum = s_wsum;
+
+    for (uint32_t i = threadIdx.x; i < GK_NSUB; i += GK_THREADS) sm.cnt[i] = 0;
+    __syncthreads();
+    GroupStats st{0, 0, 0, 0ull};
+    GroupPending pd{0ull, 0u, 0u, false};
+    uint32_t par = 0;
+    for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
+        const uint32_t bb = a.base[b];
+        const uint32_t m = a.base[b + 1] - bb;
+        if (m == 0) continue;      // uniform per CTA
+        if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST>(a, bb, m, sm, &s_pcur[par], st, pd);
+        else group_bucket<GK_SLOW>(a, bb, m, sm, &s_pcur[par], st, pd);
+        par ^= 1;
+    }
+    if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;
+    const unsigned long long heads = block_sum<GK_THREADS>(st.heads);
+    const unsigned long long single = block_sum<GK_THREADS>(st.single);
+    const unsigned long long w = block_sum<GK_THREADS>(st.w);
+    const unsigned long long dups = block_sum<GK_THREADS>(st.dups);
+    if (threadIdx.x == 0) {
+        if (heads) atomicAdd(&a.scal[SC_HEADS], heads);
+        if (single) atomicAdd(&a.scal[SC_SINGLE], single);
+        if (w) atomicAdd(&a.scal[SC_W], w);
+        if (dups) atomicAdd(&a.scal[SC_DUPS], dups);
+    }
+}
+
 int bitlen(uint64_t v) {
     int b = 0;
     while (b < 64 && (v >> b) != 0) b++;
@@ -614,11 +844,33 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
+    if (ctx->group_kernel != 0) {
+        // v2: counting sort + neighbour scan, items appended to the per-genome lists in the same kernel
+        GroupArgs g{};
+        g.ent = final_ent; g.base = final_base; g.nb = nbuckets; g.gb = p.gb;
+        const int key_bits = p.kb1 - d2;                       // hash bits that still vary inside a final bucket
+        const int sbits = std::max(0, std::min(GK_SUBBITS, key_bits));
+        const int rest_bits = key_bits - sbits;                // compared inside a sub-bucket (32 low + the rest beside the genome id)
+        g.sub_shift = p.gb + rest_bits;
+        g.sub_mask = (1u << sbits) - 1u;
+        g.rest_mask = rest_bits >= 64 ? ~0ull : ((1ull << rest_bits) - 1ull);
+        if (g.sub_shift > 63) { g.sub_shift = 0; g.sub_mask = 0; }
+        if (rest_bits > 32 && rest_bits - 32 + p.gb > 32) return 0;     // does not fit the candidate arrays: general path
+        g.post = ctx->d_post; g.row_off = ctx->d_offsets; g.row_cnt = ctx->d_row_cnt; g.row_items = ctx->d_row_items; g.scal = ctx->d_scalars;
+        const size_t smem = (size_t)GK_NSUB * 4 + (size_t)BK_CAP * 8 + (size_t)(GK_NSUB + 8) * 2 + (size_t)BK_CAP * 4;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_group, GK_THREADS, smem));
+        const int grid = (int)std::min<uint64_t>(nbuckets, (uint64_t)ctx->num_sms * std::max(occ, 1));
+        k2_group<<<grid, GK_THREADS, smem, st>>>(g);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 1;
+    } else {
     YG_CHECK(dev_alloc(ctx, &ctx->d_rec_gid, T));
     uint64_t* rec_item = nullptr;
     if (d2) rec_item = ctx->d_ent1;                 // level-1 words are dead once level 2 has run
     else { YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T)); rec_item = ctx->d_ent2; }
-    const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
     YG_CHECK(dev_alloc(ctx, &ctx->d_nrec, (uint64_t)nbuckets + 1));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_nrec, 0, ((uint64_t)nbuckets + 1) * sizeof(uint32_t), st));
     BucketArgs b{};
@@ -637,6 +889,7 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
         YG_CUDA(ctx, cudaGetLastError());
         ctx->tm.n_kernel_launches += 2;
     }
+    }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -649,7 +902,11 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
                 ph[0], ph[6], ph[1], ph[7], ph[2], ph[8], ph[3], ph[9], ph[4], ph[10], ph[5], ph[11]);
     }
 #endif
-    const uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
+    uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
+    if (ctx->group_kernel != 0) {           // every word is a singleton or a member of a shared group
+        P = T - sc[SC_SINGLE];
+        I = P - (sc[SC_HEADS] - sc[SC_SINGLE]);
+    }
     ctx->P = P;
     ctx->n_items = I;
     ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])

@@ -608,6 +608,11 @@ __device__ __forceinline__ uint32_t acc_take(uint32_t* acc, uint32_t col) {
     }
 }
 
+// Work units (row, column tile) come from a global ticket.  A row's critical path would otherwise be a chain of
+// dependent global round trips (ticket -> row metadata -> first items), and with a 170 KB accumulator only one
+// row is in flight per SM, so the chain is software-pipelined three deep: while unit k is accumulated, every
+// thread already holds its first item of unit k+1 in a register, and thread 0 resolves the metadata of unit
+// k+2 from a ticket drawn one iteration earlier.
 template <bool U16>
 __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
     const uint32_t NT = blockDim.x;   // 256 when several accumulators share an SM, up to 1024 when one CTA owns it
@@ -616,30 +621,70 @@ __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
     uint32_t* acc = smem;                               // [acc_words] dense row accumulator
     uint32_t* touched = acc + acc_words;                // [K3_TOUCH_CAP]
     uint64_t* longq = (uint64_t*)(touched + K3_TOUCH_CAP + (acc_words & 1u));  // 8-byte aligned
-    __shared__ uint32_t s_nt, s_nlong;
-    __shared__ unsigned long long s_unit;
-
-    for (uint32_t c = threadIdx.x; c < acc_words; c += NT) acc[c] = 0;
-    if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
-    __syncthreads();
+    __shared__ uint32_t s_ntv[2], s_nlongv[2];          // double-buffered by iteration parity: no reset barrier
+    __shared__ unsigned long long s_unit[3];            // pipeline slots: unit id, its row, work-list start, length
+    __shared__ uint64_t s_ib[3];
+    __shared__ uint32_t s_row[3], s_n[3];
 
     const unsigned long long n_units = (unsigned long long)(p.row_list ? p.n_list : (p.row_end - p.row_begin)) * p.n_tiles;
+    // the first two units of a CTA are static; tickets continue from 2 * gridDim.x
+    if (threadIdx.x < 2) {
+        const unsigned long long u = (unsigned long long)blockIdx.x + (unsigned long long)threadIdx.x * gridDim.x;
+        uint32_t row = 0, n = 0;
+        uint64_t ib = 0;
+        if (u < n_units) {
+            const uint32_t ridx = p.n_tiles == 1 ? (uint32_t)u : (uint32_t)(u / p.n_tiles);
+            row = p.row_list ? p.row_list[ridx] : p.row_begin + ridx;
+            ib = p.list_begin[row];
+            n = (uint32_t)p.row_n[row];
+        }
+        s_unit[threadIdx.x] = u; s_row[threadIdx.x] = row; s_ib[threadIdx.x] = ib; s_n[threadIdx.x] = n;
+    }
+    unsigned long long tick = 0;
+    if (threadIdx.x == 0) {
+        s_ntv[0] = 0; s_ntv[1] = 0; s_nlongv[0] = 0; s_nlongv[1] = 0;
+        tick = 2ull * gridDim.x + atomicAdd(&p.scal[SC_UNIT], 1ull);
+    }
+    for (uint32_t c = threadIdx.x; c < acc_words; c += NT) acc[c] = 0;
+    __syncthreads();
+    uint64_t item_cur = 0;
+    if (s_unit[0] < n_units && threadIdx.x < s_n[0]) item_cur = p.row_items[s_ib[0] + threadIdx.x];
+
+    uint32_t cur = 0, par = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_unit = atomicAdd(&p.scal[SC_UNIT], 1ull);
-        __syncthreads();
-        const unsigned long long unit = s_unit;
+        const unsigned long long unit = s_unit[cur];
         if (unit >= n_units) break;
-        const uint32_t ridx = (uint32_t)(unit / p.n_tiles);
-        const uint32_t row = p.row_list ? p.row_list[ridx] : p.row_begin + ridx;
-        const uint32_t tile = (uint32_t)(unit % p.n_tiles);
+        uint32_t& s_nt = s_ntv[par];
+        uint32_t& s_nlong = s_nlongv[par];
+        const uint32_t nxt = cur == 2 ? 0 : cur + 1, nx2 = nxt == 2 ? 0 : nxt + 1;
+        const uint32_t row = s_row[cur];
+        const uint64_t ib = s_ib[cur], ie = ib + s_n[cur];
+        // this thread's first item of the next unit
+        uint64_t item_next = 0;
+        if (s_unit[nxt] < n_units && threadIdx.x < s_n[nxt]) item_next = p.row_items[s_ib[nxt] + threadIdx.x];
+        // thread 0: metadata of the unit after next (loads issued here, consumed at the bottom of the iteration)
+        unsigned long long u2 = 0;
+        uint32_t r2 = 0, n2 = 0;
+        uint64_t ib2 = 0;
+        if (threadIdx.x == 0) {
+            u2 = tick;
+            s_ntv[par ^ 1] = 0; s_nlongv[par ^ 1] = 0;      // last read before the previous iteration's final barrier
+            if (u2 < n_units) {
+                const uint32_t ridx = p.n_tiles == 1 ? (uint32_t)u2 : (uint32_t)(u2 / p.n_tiles);
+                r2 = p.row_list ? p.row_list[ridx] : p.row_begin + ridx;
+                ib2 = p.list_begin[r2];
+                n2 = (uint32_t)p.row_n[r2];
+                tick = 2ull * gridDim.x + atomicAdd(&p.scal[SC_UNIT], 1ull);
+            }
+        }
+        const uint32_t tile = p.n_tiles == 1 ? 0u : (uint32_t)(unit % p.n_tiles);
         const uint32_t c0 = tile * p.tile_w;
         const uint32_t c1 = min(p.n, c0 + p.tile_w);
-        const uint64_t ib = p.list_begin[row], ie = ib + p.row_n[row];
         // upper triangle: only columns > row matter
         if (c1 > row + 1 && ie > ib) {
             // ---- accumulate -----------------------------------------------------------------
-            for (uint64_t it = ib + threadIdx.x; it < ie; it += NT) {
-                const uint64_t item = p.row_items[it];
+            uint64_t item = item_cur;
+            for (uint64_t it = ib + threadIdx.x; it < ie;) {
                 const uint32_t inl = (uint32_t)item & 3u;
                 if (inl) {                                         // the following genome ids are inside the item
                     for (uint32_t e = 0; e < inl; e++) {
@@ -650,27 +695,31 @@ __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
                             if (k < K3_TOUCH_CAP) touched[k] = g;
                         }
                     }
-                    continue;
-                }
-                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
-                if (len > K3_LONG_LEN) {
-                    const uint32_t q = atomicAdd(&s_nlong, 1u);
-                    if (q < K3_LONG_CAP) { longq[q] = item; continue; }
-                }
-                for (uint32_t e = 0; e < len; e++) {
-                    const uint32_t g = p.post[start + e];
-                    if (g <= row || g < c0 || g >= c1) continue;   // g == row: duplicate hash inside the sketch
-                    if (acc_add<U16>(acc, g - c0) == 0) {
-                        const uint32_t k = atomicAdd(&s_nt, 1u);
-                        if (k < K3_TOUCH_CAP) touched[k] = g;
+                } else {
+                    const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
+                    bool queued = false;
+                    if (len > K3_LONG_LEN) {
+                        const uint32_t q = atomicAdd(&s_nlong, 1u);
+                        if (q < K3_LONG_CAP) { longq[q] = item; queued = true; }
                     }
+                    if (!queued)
+                        for (uint32_t e = 0; e < len; e++) {
+                            const uint32_t g = p.post[start + e];
+                            if (g <= row || g < c0 || g >= c1) continue;   // g == row: duplicate hash inside the sketch
+                            if (acc_add<U16>(acc, g - c0) == 0) {
+                                const uint32_t k = atomicAdd(&s_nt, 1u);
+                                if (k < K3_TOUCH_CAP) touched[k] = g;
+                            }
+                        }
                 }
+                it += NT;
+                if (it < ie) item = p.row_items[it];
             }
             __syncthreads();
             const uint32_t nlong = min(s_nlong, (uint32_t)K3_LONG_CAP);
             for (uint32_t q = 0; q < nlong; q++) {
-                const uint64_t item = longq[q];
-                const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
+                const uint64_t litem = longq[q];
+                const uint32_t start = (uint32_t)(litem >> 32), len = (uint32_t)(litem >> 2) & 0x3FFFFFFFu;
                 for (uint32_t e = threadIdx.x; e < len; e += NT) {
                     const uint32_t g = p.post[start + e];
                     if (g <= row || g < c0 || g >= c1) continue;
@@ -680,7 +729,7 @@ __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
                     }
                 }
             }
-            __syncthreads();
+            if (nlong) __syncthreads();
             // ---- threshold + compaction (K4), and reset of the accumulator ---------------------
             const uint32_t nt = s_nt;
             if (nt <= K3_TOUCH_CAP) {
@@ -696,10 +745,13 @@ __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
                     if (cnt) test_pair(p, row, c0 + c, cnt);
                 }
             }
-            __syncthreads();
-            if (threadIdx.x == 0) { s_nt = 0; s_nlong = 0; }
         }
+        // slot nx2 was last read one iteration ago (a barrier lies in between); it is read again after the barrier below
+        if (threadIdx.x == 0) { s_unit[nx2] = u2; s_row[nx2] = r2; s_ib[nx2] = ib2; s_n[nx2] = n2; }
         __syncthreads();
+        item_cur = item_next;
+        cur = nxt;
+        par ^= 1;
     }
 }
 
@@ -1049,6 +1101,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "force_u16")) { ctx->force_u16 = (int)value; return 0; }
     if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
     if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
+    if (!strcmp(name, "group_kernel")) { ctx->group_kernel = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

@@ -74,7 +74,38 @@ def all_gather_pairs(local, n_local: int, world: int, device=None, group=None) -
     allp = torch.empty(world * 3 * m, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(allp, mine, group=group)
     parts = [allp[r * 3 * m: r * 3 * m + 3 * sizes[r]] for r in range(world)]
-    merged = torch.cat(parts).cpu().numpy().view(PAIR_DTYPE)
+    cat = torch.cat(parts).view(-1, 3)
     # rank-ordered concatenation is deterministic; ranges interleave (the owner of row a also
-    # reports (b, a)), so one final ordering by (i, j)
-    return np.sort(merged, order=["i", "j"])
+    # reports (b, a)), so one final ordering by (i, j) -- on the device that holds the lists
+    if cat.shape[0]:
+        key = (cat[:, 0].to(torch.int64) << 32) | cat[:, 1].to(torch.int64)
+        cat = cat[torch.argsort(key)]
+    return cat.contiguous().cpu().numpy().reshape(-1).view(PAIR_DTYPE)
+
+
+def slice_bounds(total: int, world: int) -> np.ndarray:
+    """Equal contiguous slices of the flat hash array (the last one may be short): slice r = [b[r], b[r+1])."""
+    per = (int(total) + world - 1) // world if world else 0
+    return np.minimum(np.arange(world + 1, dtype=np.int64) * per, int(total))
+
+
+def load_sketches_sharded(ctx, pinned_slice, offsets: np.ndarray, total: int, rank: int, world: int, device, group=None):
+    """Sharded ingest: every rank copies only ITS slice of the flat hash array from (pinned) host
+    memory over its own PCIe link, the slices are all-gathered over NVLink (NCCL), and the assembled array is
+    handed to the library device-to-device.  `pinned_slice` is a pinned int64 torch tensor holding
+    hashes[b[rank]:b[rank+1]] with b = slice_bounds(total, world).  Returns the assembled device tensor."""
+    import torch
+    import torch.distributed as dist
+
+    per = (int(total) + world - 1) // world
+    full = torch.empty(max(per, 1) * world, dtype=torch.int64, device=device)
+    mine = full[rank * per: (rank + 1) * per]
+    n_mine = int(pinned_slice.numel())
+    if n_mine:
+        mine[:n_mine].copy_(pinned_slice, non_blocking=True)
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.uint64).view(np.int64)).to(device, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()      # the library works on its own stream
+    ctx.load_sketches_device(full.data_ptr(), d_off.data_ptr(), int(offsets.shape[0]) - 1)
+    return full

@@ -194,7 +194,9 @@ def workload_config(args, db):
                         f"{T} hashes (mean {T / max(db.n, 1):.0f}/genome), planted ANI clusters, seed {args.seed}; "
                         f"all-vs-all train hot path, k={KSIZE}, ani_thresh={ANI}",
             "genomes": db.n, "hashes": T, "seed": args.seed, "containment_threshold": THR,
-            "parallelism": f"rows sharded over {args.gpus} GPU(s) by work, index replicated",
+            "parallelism": "1 GPU" if args.gpus == 1 else
+                           f"{args.gpus} GPUs: index build sharded by hash range (group streams all-gathered over NCCL), "
+                           f"pairwise count sharded by query rows, pair lists all-gathered",
             "l2": f"inputs {8 * T / 1e9:.2f} GB > L2 {L2_BYTES / 1e6:.0f} MB: no flush needed" if 8 * T > L2_BYTES
                   else "inputs fit L2: an L2 flush (write of 256 MB) runs before every timed step"}
 
@@ -267,18 +269,43 @@ def run_b200_arm(args):
         return sum(sizes)
 
     index_stats = {}
+    mode = {"index": "single GPU"}
+    # N > 1, e2e: every rank copies only its slice of the hash array over its own PCIe link (pinned, torch-owned)
+    pinned_slice = None
+    if world > 1:
+        sb = sharding.slice_bounds(T, world)
+        pinned_slice = torch.empty(int(sb[rank + 1] - sb[rank]), dtype=torch.int64, pin_memory=True)
+        pinned_slice.numpy()[:] = db.hashes[int(sb[rank]):int(sb[rank + 1])].view(np.int64)
 
-    def step_resident():
+    row_bounds = sharding.split_rows_by_size(offsets, world)     # depends on the sketch sizes only: once per database
+
+    def index_and_rows():
+        """index build + this rank's row range: hash-range sharded across the ranks when the database qualifies
+        (group streams all-gathered over NCCL), else replicated with rows split by measured work."""
+        if world > 1:
+            res = sharding.build_index_sharded(ctx, offsets, rank, world, dev, bounds=row_bounds)
+            if res is not None:
+                rb, re, total = res
+                index_stats.update(total, index_path=1)
+                mode["index"] = "hash-range sharded build, group streams all-gathered (NCCL)"
+                return rb, re
+            mode["index"] = "replicated build (database does not qualify for the partition path)"
         index_stats.update(ctx.build_index())
         b = ctx.row_partition(world)
-        n_r = ctx.pairwise_flag_device(THR, int(b[rank]), int(b[rank + 1]))
+        return int(b[rank]), int(b[rank + 1])
+
+    def step_resident():
+        rb, re = index_and_rows()
+        n_r = ctx.pairwise_flag_device(THR, rb, re)
         return gather_pairs(n_r, False)
 
     def step_e2e():
-        ctx.load_sketches(pinned, offsets)
-        ctx.build_index()
-        b = ctx.row_partition(world)
-        n_r = ctx.pairwise_flag_device(THR, int(b[rank]), int(b[rank + 1]))
+        if world > 1:
+            sharding.load_sketches_sharded(ctx, pinned_slice, offsets, T, rank, world, dev)
+        else:
+            ctx.load_sketches(pinned, offsets)
+        rb, re = index_and_rows()
+        n_r = ctx.pairwise_flag_device(THR, rb, re)
         return gather_pairs(n_r, True)
 
     def timed(fn, reload_first: bool):
@@ -342,12 +369,17 @@ def run_b200_arm(args):
                                  (8 * Tn + 4 * Wn + 12 * F) * share, k3_ms, "8*T + 4*W + 12*F (SURVEY.md 8d), x rank share"),
             "index_partition": rl("k2_hist1 + k2_scatter<1> + k2_hist2 + k2_scatter<2> (K2: MSD radix partition)" if msd
                                   else "CUB DeviceRadixSort of (hash, genome) pairs (general path)",
-                                  52 * Tn if msd else 12 * Tn * 2 * 7, part_ms,
-                                  "8T + (12T+8T) + 8T + (8T+8T) = 52*T" if msd else "12*T*2*7 (SURVEY.md 8d)"),
-            "index_grouping": rl("k2_group (K2: in-shared-memory counting sort + neighbour scan -> postings + per-genome work lists)" if msd
+                                  (52 * Tn if world == 1 else 20 * Tn + 32 * Tn / world) if msd else 12 * Tn * 2 * 7, part_ms,
+                                  ("8T + (12T+8T) + 8T + (8T+8T) = 52*T" if world == 1 else
+                                   "this rank: 8T + 12T read by every rank, 8T/N written, level 2 (8+16)T/N = 20*T + 32*T/N") if msd
+                                  else "12*T*2*7 (SURVEY.md 8d)"),
+            "index_grouping": rl("k2_group (K2: sub-bucket counting filter + dense candidate scan -> postings + per-genome work lists)" if msd
                                  else "k_flag_runs + scan + k_post_compact + k_items_scatter (general path)",
-                                 8 * Tn + 4 * Pn + 8 * In if msd else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
-                                 "8*T (words) + 4*P (postings) + 8*I (items)" if msd else "12*T + 4*P + 16*I"),
+                                 (8 * Tn + 4 * Pn + 8 * In if world == 1 else (8 * Tn + 6 * Pn + 8 * In) / world + 6 * Pn) if msd
+                                 else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
+                                 ("8*T (words) + 4*P (postings) + 8*I (items)" if world == 1 else
+                                  "this rank: (8*T words + 6*P stream out + 8*I items)/N + 6*P gathered stream in (k2_group<stream> + k2_items)") if msd
+                                 else "12*T + 4*P + 16*I"),
         }
         # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), when they were taken
         # on this very workload
@@ -368,12 +400,15 @@ def run_b200_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 (+f64 threshold)",
             "data": "synthetic", "config": workload_config(args, db),
             "e2e": {"value": pairs_total / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 8 * T + 8 * (n + 1), "d2h_bytes_per_step": 12 * F,
+                    "h2d_bytes_per_step": 8 * T + world * 8 * (n + 1), "d2h_bytes_per_step": 12 * F * world,
+                    "ingest": "whole array from pinned host memory" if world == 1 else
+                              f"each rank copies 1/{world} of the hash array over its own PCIe link, slices all-gathered over NVLink (NCCL)",
                     "phases_ms": {k: tm_e2e[k] / steps for k in ("ms_h2d", "ms_sort", "ms_index", "ms_count", "ms_pairsort", "ms_d2h")}},
             "gpu_launches": int(tm_res["n_kernel_launches"]),
             "library_launches": int(tm_res["n_library_launches"]),
             "clocks": clocks,
             "roofline": dominant, "rooflines": rooflines, "index_path": "msd-partition" if msd else "general-sort",
+            "index_mode": mode["index"],
             "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},
             "workload_counts": dict(counts, F=F, genomes=n), "wall_ms_per_step": wall_res * 1e3, "gen_seconds": gen_s,
         }

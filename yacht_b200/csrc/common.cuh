@@ -45,10 +45,9 @@ struct ygpu_ctx {
     uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets
     uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
     uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
-    uint32_t* d_rec_gid = nullptr;  // [T] work records (query genome) before they are grouped by genome
-    uint32_t* d_nrec = nullptr;     // [buckets] records per final bucket
+    uint16_t* d_st_rem = nullptr;   // [T] group stream of a hash-range sharded build: members of the same group that follow
+    uint64_t stream_entries = 0;    //     entries of the stream of the last ygpu_index_partial (genome ids are in d_post)
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
-    int group_kernel = 1;           // MSD path grouping: 1 = k2_group (counting sort + neighbour scan), 0 = k2_bucket + k2_rec_scatter
     int msd_fallbacks = 0;
     int last_index_path = 0;        // which path built the current index
     int count_kernel = 0;           // 0: automatic, 1: dense row accumulator per CTA, 2: one warp per row (hash table)

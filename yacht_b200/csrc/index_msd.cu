@@ -33,20 +33,17 @@ constexpr int SC_TILE = 4096;       // elements per scatter tile (512 threads x 
 constexpr int SC_THREADS = 512;
 constexpr int SC_ITEMS = SC_TILE / SC_THREADS;
 constexpr int NB_MAX = 2048;        // digits per partition level
-constexpr int BK_CAP = 3072;        // max elements of a final bucket (shared-memory resident)
-constexpr int BK_HS = 4096;         // hash-table slots per bucket (> BK_CAP: never full)
-constexpr int BK_THREADS = 256;
-constexpr int BK_KMAX = 8;          // groups up to this size are ordered by one thread in registers
-constexpr int BK_LONGQ = 352;       // > BK_CAP / (BK_KMAX + 1) = 236: queue of larger groups
 constexpr uint32_t A_TARGET = 1200; // average elements per used final bucket
 
-enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10 };   // extra slots of ctx->d_scalars
+enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10, SCM_STREAM = 12 };   // extra slots of ctx->d_scalars (SCM_MAXB uses two)
 
 struct MsdPlan {
     int hb, gb, d1, d2, kb1;
     uint32_t nb1;     // used level-1 buckets
     uint32_t nfb;     // final buckets (nb1 << d2)
     uint64_t T;
+    // hash-range sharding (multi-GPU): this rank keeps level-1 digits [dlo, dhi) only, i.e. level-2 tiles [unit_lo, unit_hi)
+    uint32_t dlo, dhi, unit_lo, unit_hi;
 };
 
 __device__ __forceinline__ uint32_t digit1_of(uint64_t key, const MsdPlan& p) {
@@ -120,8 +117,7 @@ __device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& 
         b1 = 0;
         return true;
     }
-    const uint32_t units = a.tile_start[p.nb1];
-    if (unit >= units) return false;
+    if (unit >= p.unit_hi || unit >= a.tile_start[p.nb1]) return false;
     // level-1 bucket holding this tile: last b with tile_start[b] <= unit
     uint32_t lo = 0, hi = p.nb1;
     while (hi - lo > 1) {
@@ -139,7 +135,7 @@ __device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& 
 __global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPlan p) {
     extern __shared__ uint32_t sh[];
     const uint32_t nd = 1u << p.d2;
-    for (uint32_t unit = blockIdx.x;; unit += gridDim.x) {
+    for (uint32_t unit = p.unit_lo + blockIdx.x;; unit += gridDim.x) {
         uint64_t begin; uint32_t m, b1;
         if (!unit_range<2>(a, p, unit, begin, m, b1)) break;
         for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sh[i] = 0;
@@ -153,7 +149,7 @@ __global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPl
 }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t n_units_l1) {
+__global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t n_units_l1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* stage = (uint64_t*)smem_raw;                         // [SC_TILE]
     uint32_t* cnt = (uint32_t*)(stage + SC_TILE);                  // [nd]
@@ -164,7 +160,8 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
     typedef cub::BlockScan<uint32_t, SC_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_ts;
 
-    for (uint32_t unit = blockIdx.x;; unit += gridDim.x) {
+    constexpr uint16_t SKIP = 0xFFFFu;     // not in the tile, or (level 1, sharded) a digit another rank owns
+    for (uint32_t unit = (LEVEL == 1 ? 0u : p.unit_lo) + blockIdx.x;; unit += gridDim.x) {
         uint64_t begin; uint32_t m, b1;
         if (LEVEL == 1 && unit >= n_units_l1) break;
         if (!unit_range<LEVEL>(a, p, unit, begin, m, b1)) break;
@@ -172,26 +169,36 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
         __syncthreads();
         uint64_t e[SC_ITEMS];
         uint16_t dg[SC_ITEMS], rk[SC_ITEMS];
+        uint32_t gi[SC_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SC_ITEMS; k++) {
+        for (int k = 0; k < SC_ITEMS; k++) {      // all loads of the tile in flight before any is consumed
             const uint32_t idx = k * SC_THREADS + threadIdx.x;
             if (idx < m) {
-                if (LEVEL == 1) {
-                    const uint64_t key = a.hashes[begin + idx];
-                    dg[k] = (uint16_t)digit1_of(key, p);
-                    e[k] = pack_entry(key, a.gid[begin + idx], p);
-                } else {
-                    e[k] = a.in_ent[begin + idx];
-                    dg[k] = (uint16_t)digit2_of(e[k], p);
-                }
+                if (LEVEL == 1) { e[k] = a.hashes[begin + idx]; gi[k] = a.gid[begin + idx]; }
+                else e[k] = a.in_ent[begin + idx];
             }
         }
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
             const uint32_t idx = k * SC_THREADS + threadIdx.x;
-            if (idx < m) rk[k] = (uint16_t)atomicAdd(&cnt[dg[k]], 1u);
+            dg[k] = SKIP;
+            if (idx < m) {
+                if (LEVEL == 1) {
+                    const uint32_t d = digit1_of(e[k], p);
+                    if (d >= p.dlo && d < p.dhi) {
+                        dg[k] = (uint16_t)d;
+                        e[k] = pack_entry(e[k], gi[k], p);
+                    }
+                } else {
+                    dg[k] = (uint16_t)digit2_of(e[k], p);
+                }
+            }
         }
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; k++)
+            if (dg[k] != SKIP) rk[k] = (uint16_t)atomicAdd(&cnt[dg[k]], 1u);
         __syncthreads();
+        uint32_t mv = 0;     // words of this tile that are kept
         // exclusive scan of cnt -> lbase; reserve global space per digit -> gbase
         {
             const uint32_t per = (nd + SC_THREADS - 1) / SC_THREADS;
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
             uint32_t s = 0;
             for (uint32_t k = 0; k < per; k++) if (d0 + k < nd) s += cnt[d0 + k];
             uint32_t off;
-            Scan(scan_ts).ExclusiveSum(s, off);
+            Scan(scan_ts).ExclusiveSum(s, off, mv);
             for (uint32_t k = 0; k < per; k++) {
                 const uint32_t d = d0 + k;
                 if (d < nd) {
@@ -216,8 +223,7 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
-            const uint32_t idx = k * SC_THREADS + threadIdx.x;
-            if (idx < m) {
+            if (dg[k] != SKIP) {
                 const uint32_t q = lbase[dg[k]] + rk[k];
                 stage[q] = e[k];
                 sdig[q] = dg[k];
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
             const uint32_t q = k * SC_THREADS + threadIdx.x;
-            if (q < m) {
+            if (q < mv) {
                 const uint32_t d = sdig[q];
                 a.out_ent[(uint64_t)gbase[d] + (q - lbase[d])] = stage[q];
             }
@@ -236,256 +242,11 @@ __global__ void __launch_bounds__(SC_THREADS) k2_scatter(const ScatterArgs a, co
     }
 }
 
-// ---- bucket kernel: group equal hashes in shared memory, emit postings + work records ------------
-struct BucketArgs {
-    const uint64_t* ent;
-    const uint32_t* base;        // [nb + 1]
-    uint32_t nb;
-    int gb;
-    uint32_t* post;              // [T] postings (genome ids): a bucket writes its groups at the start of its own slice
-    uint32_t* rec_gid;           // [T] work records (query genome, item), written into the bucket's own slice:
-    uint64_t* rec_item;          //     no atomics on hot per-genome counters inside this barrier-heavy kernel
-    uint32_t* nrec;              // [nb] records written per bucket
-    unsigned long long* scal;
-};
-
-// one work record for query genome g: "the `rem` postings starting at `next_pos` share a hash with you"
-// (item format v2, indirect).  k2_rec_scatter later moves the records into the per-genome lists.
-__device__ __forceinline__ void emit_member(const BucketArgs& a, uint32_t g, uint64_t next_pos, uint32_t rem, uint64_t q) {
-    a.rec_gid[q] = g;
-    a.rec_item[q] = (next_pos << 32) | ((uint64_t)rem << 2);
-}
-
-__global__ void __launch_bounds__(BK_THREADS, 4) k2_bucket(const BucketArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* E = (uint64_t*)smem_raw;                               // [BK_CAP] the bucket's packed words
-    uint32_t* H = (uint32_t*)(E + BK_CAP);                           // [BK_HS]  slot -> most recent entry of that key's chain
-    unsigned short* nxt = (unsigned short*)(H + BK_HS);              // [BK_CAP] chain links (towards older entries)
-    unsigned short* slot_of = nxt + BK_CAP;                          // [BK_CAP] slot each entry landed in
-    unsigned short* queue = slot_of + BK_CAP;                        // [BK_CAP / 2] chain heads of groups with >= 2 members
-    unsigned short* longq = queue + BK_CAP / 2;                      // [BK_LONGQ] heads of groups larger than BK_KMAX
-    uint32_t* scratch = H;                                           // [BK_CAP] reused by the large-group path
-    uint32_t* scratch2 = H;                                          // [BK_CAP] dense pass: per-group id arrays (H is dead after the heads pass)
-    __shared__ uint32_t s_nq, s_nlong, s_cnt, s_pcur, s_rcur;
-    const unsigned short NONE = 0xFFFFu;
-    const uint32_t EMPTY = 0xFFFFFFFFu;
-    const uint64_t gmask = a.gb ? ((1ull << a.gb) - 1ull) : 0ull;
-
-    unsigned long long st_heads = 0, st_single = 0, st_w = 0, st_dups = 0, st_p = 0, st_i = 0;
-#ifdef YG_PHASE_TIMING   // developer aid: per-phase clock64 totals of thread 0 and thread 255 -> d_scalars[20..31]
-    long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define YG_PH(k) { const long long tn = clock64(); ph[k] += tn - tprev; tprev = tn; }
-#else
-#define YG_PH(k)
-#endif
-
-    for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
-        const uint32_t bb = a.base[b];
-        const uint32_t m = a.base[b + 1] - bb;
-        if (m == 0) continue;      // uniform per CTA
-        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) { E[i] = a.ent[(uint64_t)bb + i]; nxt[i] = NONE; }
-        for (uint32_t i = threadIdx.x; i < BK_HS; i += BK_THREADS) H[i] = EMPTY;
-        if (threadIdx.x == 0) { s_nq = 0; s_nlong = 0; s_pcur = 0; s_rcur = 0; }
-        YG_PH(0)
-        __syncthreads();
-        YG_PH(1)
-
-        // ---- insert: one CAS for a new key, one more to push onto an existing key's chain ------------
-        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
-            const uint64_t key = E[i] >> a.gb;
-            uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (BK_HS - 1);
-            for (;;) {
-                uint32_t cur = *((volatile uint32_t*)&H[slot]);
-                if (cur == EMPTY) {
-                    const uint32_t old = atomicCAS(&H[slot], EMPTY, i);
-                    if (old == EMPTY) break;
-                    cur = old;
-                }
-                if ((E[cur] >> a.gb) == key) {
-                    const uint32_t old = atomicCAS(&H[slot], cur, i);
-                    if (old == cur) { nxt[i] = (unsigned short)cur; break; }
-                    continue;    // the chain head moved: retry this slot
-                }
-                slot = (slot + 1) & (BK_HS - 1);
-            }
-            slot_of[i] = (unsigned short)slot;
-        }
-        YG_PH(2)
-        __syncthreads();
-
-        // ---- heads: count distinct hashes / singletons, queue the groups that have >= 2 members -------
-        for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS) {
-            if (H[slot_of[i]] != i) continue;          // not the head of its chain
-            st_heads++;
-            if (nxt[i] == NONE) { st_single++; continue; }
-            queue[atomicAdd(&s_nq, 1u)] = (unsigned short)i;
-        }
-        __syncthreads();
-        YG_PH(3)
-
-        // ---- dense pass over the queued groups: order by genome id, claim a slice of the bucket's
-        //      posting region (shared-memory cursor: no grid-wide reservation), write postings + items
-        const uint32_t nq = s_nq;
-        const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
-        for (uint32_t t = threadIdx.x; t < nq; t += BK_THREADS) {
-            const unsigned short head = queue[t];
-            // ---- fast path: groups of 2..4 members (the bulk), entirely in scalar registers --------
-            const unsigned short j1 = nxt[head];                       // != NONE: queued groups have >= 2 members
-            const unsigned short j2 = nxt[j1];
-            const unsigned short j3 = j2 != NONE ? nxt[j2] : NONE;
-            const bool small = j3 == NONE || nxt[j3] == NONE;
-            if (small && can_inline) {
-                uint32_t g0 = (uint32_t)(E[head] & gmask), g1 = (uint32_t)(E[j1] & gmask);
-                uint32_t g2 = j2 != NONE ? (uint32_t)(E[j2] & gmask) : 0xFFFFFFFFu;
-                uint32_t g3 = j3 != NONE ? (uint32_t)(E[j3] & gmask) : 0xFFFFFFFFu;
-                const uint32_t L = 2u + (j2 != NONE) + (j3 != NONE);
-                // 5-comparator sorting network (absent members are +inf and sink to the end)
-#define YG_CSWAP(x, y) { const uint32_t lo_ = min(x, y), hi_ = max(x, y); x = lo_; y = hi_; }
-                YG_CSWAP(g0, g1) YG_CSWAP(g2, g3) YG_CSWAP(g0, g2) YG_CSWAP(g1, g3) YG_CSWAP(g1, g2)
-#undef YG_CSWAP
-                st_w += (unsigned long long)L * L;
-                st_p += L; st_i += L - 1;
-                st_dups += (g0 == g1) + (L > 2 && g1 == g2) + (L > 3 && g2 == g3);
-                // members 0 .. L-2 each get one inline item, recorded in the bucket's own slice
-                const uint64_t q = (uint64_t)bb + atomicAdd(&s_rcur, L - 1);
-                uint64_t it0 = (uint64_t)(L - 1) | ((uint64_t)g1 << 2);
-                if (L > 2) it0 |= (uint64_t)g2 << 22;
-                if (L > 3) it0 |= (uint64_t)g3 << 42;
-                a.rec_gid[q] = g0; a.rec_item[q] = it0;
-                if (L > 2) { a.rec_gid[q + 1] = g1; a.rec_item[q + 1] = (uint64_t)(L - 2) | ((uint64_t)g2 << 2) | (L > 3 ? (uint64_t)g3 << 22 : 0ull); }
-                if (L > 3) { a.rec_gid[q + 2] = g2; a.rec_item[q + 2] = 1ull | ((uint64_t)g3 << 2); }
-                continue;
-            }
-            // ---- general path: 5 .. BK_KMAX members.  The group's ids are ordered in SHARED memory (a slice of
-            //      the dead hash table): with 4 CTAs x 57 KB of shared memory per SM almost no L1 is left, so a
-            //      thread-local array (local memory) would turn every access into an L2 round trip.
-            uint32_t L = 0;
-            for (unsigned short j = head; j != NONE; j = nxt[j]) L++;
-            st_w += (unsigned long long)L * L;
-            if (L > BK_KMAX) { longq[atomicAdd(&s_nlong, 1u)] = head; continue; }
-            const uint32_t off = atomicAdd(&s_pcur, L);
-            uint32_t* gs = scratch2 + off;                 // off + L <= m <= BK_CAP
-            {
-                uint32_t x = 0;
-                for (unsigned short j = head; j != NONE; j = nxt[j]) gs[x++] = (uint32_t)(E[j] & gmask);
-            }
-            for (uint32_t x = 1; x < L; x++) {          // insertion sort, L <= BK_KMAX
-                const uint32_t v = gs[x];
-                uint32_t y = x;
-                while (y > 0 && gs[y - 1] > v) { gs[y] = gs[y - 1]; y--; }
-                gs[y] = v;
-            }
-            const uint64_t pp = (uint64_t)bb + off;
-            st_p += L; st_i += L - 1;
-            const uint64_t q = (uint64_t)bb + atomicAdd(&s_rcur, L - 1);
-            for (uint32_t x = 0; x < L; x++) {
-                const uint32_t gx = gs[x];
-                a.post[pp + x] = gx;
-                if (x + 1 < L) {
-                    const uint32_t rem = L - x - 1;
-                    if (gx == gs[x + 1]) st_dups++;
-                    uint64_t item;
-                    if (can_inline && rem <= 3) {
-                        item = (uint64_t)rem | ((uint64_t)gs[x + 1] << 2);
-                        if (rem >= 2) item |= (uint64_t)gs[x + 2] << 22;
-                        if (rem >= 3) item |= (uint64_t)gs[x + 3] << 42;
-                    } else {
-                        item = ((pp + x + 1) << 32) | ((uint64_t)rem << 2);
-                    }
-                    a.rec_gid[q + x] = gx;
-                    a.rec_item[q + x] = item;
-                }
-            }
-        }
-        YG_PH(4)
-        __syncthreads();
-        YG_PH(5)
-
-        // ---- large groups: the whole CTA gathers, bitonic-sorts and writes one group at a time -------
-        const uint32_t nlong = s_nlong;
-        for (uint32_t lg = 0; lg < nlong; lg++) {
-            const uint64_t key = E[longq[lg]] >> a.gb;
-            if (threadIdx.x == 0) s_cnt = 0;
-            __syncthreads();                                  // H is dead from here on: it becomes `scratch`
-            for (uint32_t i = threadIdx.x; i < m; i += BK_THREADS)
-                if ((E[i] >> a.gb) == key) scratch[atomicAdd(&s_cnt, 1u)] = (uint32_t)(E[i] & gmask);
-            __syncthreads();
-            const uint32_t L = s_cnt;
-            uint32_t n2 = 1;
-            while (n2 < L) n2 <<= 1;
-            for (uint32_t i = L + threadIdx.x; i < n2; i += BK_THREADS) scratch[i] = 0xFFFFFFFFu;
-            __syncthreads();
-            for (uint32_t k = 2; k <= n2; k <<= 1)
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = threadIdx.x; i < n2; i += BK_THREADS) {
-                        const uint32_t ixj = i ^ j;
-                        if (ixj > i) {
-                            const uint32_t x = scratch[i], y = scratch[ixj];
-                            const bool up = (i & k) == 0;
-                            if ((x > y) == up) { scratch[i] = y; scratch[ixj] = x; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            const uint64_t pp = (uint64_t)bb + s_pcur;
-            const uint64_t qq = (uint64_t)bb + s_rcur;
-            __syncthreads();
-            if (threadIdx.x == 0) { s_pcur += L; s_rcur += L - 1; st_p += L; st_i += L - 1; }
-            for (uint32_t x = threadIdx.x; x < L; x += BK_THREADS) {
-                const uint32_t gx = scratch[x];
-                a.post[pp + x] = gx;
-                if (x + 1 < L) {
-                    if (gx == scratch[x + 1]) st_dups++;
-                    emit_member(a, gx, pp + x + 1, L - x - 1, qq + x);
-                }
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) a.nrec[b] = s_rcur;      // every thread is past the last barrier that follows a write of s_rcur
-        __syncthreads();
-    }
-#ifdef YG_PHASE_TIMING
-    if (threadIdx.x == 0 || threadIdx.x == 255) for (int k = 0; k < 6; k++) atomicAdd(&a.scal[(threadIdx.x ? 26 : 20) + k], (unsigned long long)ph[k]);
-#endif
-    st_heads = block_sum<BK_THREADS>(st_heads);
-    st_single = block_sum<BK_THREADS>(st_single);
-    st_w = block_sum<BK_THREADS>(st_w);
-    st_dups = block_sum<BK_THREADS>(st_dups);
-    st_p = block_sum<BK_THREADS>(st_p);
-    st_i = block_sum<BK_THREADS>(st_i);
-    if (threadIdx.x == 0) {
-        if (st_heads) atomicAdd(&a.scal[SC_HEADS], st_heads);
-        if (st_single) atomicAdd(&a.scal[SC_SINGLE], st_single);
-        if (st_w) atomicAdd(&a.scal[SC_W], st_w);
-        if (st_dups) atomicAdd(&a.scal[SC_DUPS], st_dups);
-        if (st_p) atomicAdd(&a.scal[SCM_PCUR], st_p);
-        if (st_i) atomicAdd(&a.scal[SCM_ICUR], st_i);
-    }
-}
-
-// records -> per-genome work lists.  One warp per bucket: the returning atomics on the (hot) per-genome
-// counters are issued with full thread-level parallelism here, instead of sitting on the critical path of
-// a CTA that synchronises after every phase.
-__global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict__ base, const uint32_t* __restrict__ nrec, uint32_t nb,
-                                                       const uint32_t* __restrict__ rec_gid, const uint64_t* __restrict__ rec_item,
-                                                       const uint64_t* __restrict__ row_off, unsigned long long* __restrict__ row_cnt,
-                                                       uint64_t* __restrict__ row_items) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += warps) {
-        const uint32_t n = nrec[b];
-        const uint64_t bb = base[b];
-        for (uint32_t k = lane; k < n; k += 32) {
-            const uint32_t g = rec_gid[bb + k];
-            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            row_items[row_off[g] + slot] = rec_item[bb + k];
-        }
-    }
-}
+constexpr int BK_CAP = 3072;        // max words of a final bucket (shared-memory resident)
 
 // ---- grouping kernel (k2_group): sub-bucket counting filter + dense candidate scan ------------------------
-// k2_bucket (above) chains equal hashes through a CAS hash table; its chain walks are divergent (15 of 32
-// lanes active on average) and barrier-bound.  k2_group does the same job with uniform work per thread and
+// (The first version of this kernel chained equal hashes through a CAS hash table; its chain walks were
+// divergent -- 15 of 32 lanes active on average -- and barrier-bound.)  k2_group has uniform work per thread and
 // spends almost nothing on the ~80 % of hashes nobody shares:
 //   A  words -> registers; sub-bucket = next GK_SUBBITS hash bits; rank inside the sub-bucket from one
 //      shared-memory atomicAdd.  A word alone in its sub-bucket is a singleton: it is only counted.
@@ -499,7 +260,9 @@ __global__ void __launch_bounds__(256) k2_rec_scatter(const uint32_t* __restrict
 //   F  one thread per staged posting: coalesced posting writes (only for groups some item points into) and
 //      the member's work item, appended to the member's per-genome list.  The returning atomicAdd on the
 //      per-genome counter is consumed one bucket later (software pipelining), so its latency never sits
-//      between two barriers -- this replaces the separate record pass (k2_rec_scatter).
+//      between two barriers.
+//   F' (stream mode, hash-range sharded build across GPUs) instead writes the staged groups to a compact stream
+//      (genome id, members that follow); ranks all-gather their streams and k2_items builds the work lists.
 constexpr int GK_THREADS = 256;
 constexpr int GK_SUBBITS = 11;
 constexpr int GK_NSUB = 1 << GK_SUBBITS;            // 2048 = 8 counters per thread
@@ -510,6 +273,7 @@ struct GroupArgs {
     const uint64_t* ent;
     const uint32_t* base;        // [nb + 1]
     uint32_t nb;
+    uint32_t b_lo, b_hi;         // final buckets this launch covers (all, or one rank's hash range)
     int gb;
     int sub_shift;               // sub-bucket digit = (word >> sub_shift) & sub_mask
     uint32_t sub_mask;
@@ -518,6 +282,9 @@ struct GroupArgs {
     const uint64_t* row_off;     // [n] start of genome g's work list (= sketch offsets)
     unsigned long long* row_cnt; // [n] items appended so far
     uint64_t* row_items;         // [T]
+    // stream mode (hash-range sharded build): the groups leave as a compact stream instead of work items
+    uint32_t* st_gid;            // genome ids, group by group, ascending inside a group
+    unsigned short* st_rem;      // members of the same group that follow
     unsigned long long* scal;
 };
 
@@ -534,9 +301,9 @@ struct GroupSmem {
     uint32_t* s_wsum;            // [8]
 };
 
-template <int ITEMS>
+template <int ITEMS, bool STREAM>
 __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t bb, const uint32_t m, const GroupSmem& sm,
-                                             uint32_t* s_pcur, GroupStats& st, GroupPending& pd) {
+                                             uint32_t* s_pcur, uint32_t* s_gpos, GroupStats& st, GroupPending& pd) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gmask = a.gb ? (uint32_t)((1ull << a.gb) - 1ull) : 0u;
     // ---- A: load, sub-bucket rank ------------------------------------------------------------------
@@ -609,19 +376,18 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
             const uint32_t kq = sm.K2[q], xq = sm.G2[q], s = sm.SUB2[q];
             const uint32_t lo = sm.start2[s], hi = sm.start2[s + 1];
             const uint32_t g = xq & gmask;
-            uint32_t L = 1, rank = 0, first = q, dup = 0;
+            // branch-free: most candidates do have partners, found at different iterations by different lanes, so a
+            // divergent match body would be executed by nearly every warp on nearly every iteration
+            uint32_t L = 0, rank = 0, first = 0xFFFFFFFFu, dup = 0;
+            const uint32_t hmask = ~gmask;
             for (uint32_t x = lo; x < hi; x++) {
-                if (sm.K2[x] == kq && x != q) {
-                    const uint32_t x2 = sm.G2[x];
-                    if (((x2 ^ xq) & ~gmask) == 0) {           // remaining high hash bits agree too
-                        L++;
-                        first = min(first, x);
-                        const uint32_t g2 = x2 & gmask;
-                        const bool tie = (g2 == g) && (x < q);
-                        rank += ((g2 < g) || tie) ? 1u : 0u;
-                        dup |= tie ? 1u : 0u;
-                    }
-                }
+                const uint32_t k2 = sm.K2[x], x2 = sm.G2[x];
+                const bool same = (k2 == kq) & (((x2 ^ xq) & hmask) == 0u);      // same hash (this candidate included)
+                const bool tie = same & (x2 == xq) & (x < q);                    // same genome too: in-sketch duplicate
+                L += same ? 1u : 0u;
+                rank += (same & ((x2 < xq) | tie)) ? 1u : 0u;                    // high bits agree: order of G2 = order of genome ids
+                first = min(first, same ? x : 0xFFFFFFFFu);
+                dup |= tie ? 1u : 0u;
             }
             st.heads += rank == 0;
             st.single += L == 1;
@@ -640,6 +406,10 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     uint32_t* stg_g = sm.K2;                                                     // [BK_CAP]
     unsigned short* stg_rem = reinterpret_cast<unsigned short*>(sm.G2);          // [BK_CAP]
     const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
+    if (STREAM && tid == 0) {        // claim this bucket's slice of the stream (the cursor is final: barrier above)
+        const uint32_t np0 = *s_pcur;
+        *s_gpos = np0 ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np0) : 0u;
+    }
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         if (lr[k]) {
@@ -652,6 +422,14 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     __syncthreads();
     // ---- F: postings + work items -------------------------------------------------------------------------------
     const uint32_t np = *s_pcur;
+    if (STREAM) {
+        const uint32_t gpos = *s_gpos;
+        for (uint32_t x = tid; x < np; x += GK_THREADS) {
+            a.st_gid[(uint64_t)gpos + x] = stg_g[x];
+            a.st_rem[(uint64_t)gpos + x] = (unsigned short)(stg_rem[x] & 0x7fffu);
+        }
+        return;
+    }
     for (uint32_t x = tid; x < np; x += GK_THREADS) {
         const uint32_t g = stg_g[x];
         const uint32_t rr = stg_rem[x];
@@ -674,6 +452,7 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     }
 }
 
+template <bool STREAM>
 __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GroupSmem sm;
@@ -684,7 +463,7 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     sm.SUB2 = sm.start2 + GK_NSUB + 8;                               // 6 KB
     sm.gbase = sm.SUB2 + BK_CAP;                                     // 6 KB
     __shared__ uint32_t s_wsum[GK_THREADS / 32];
-    __shared__ uint32_t s_pcur[2];
+    __shared__ uint32_t s_pcur[2], s_gpos[2];
     sm.s_wsum = s_wsum;
 
     for (uint32_t i = threadIdx.x; i < GK_NSUB; i += GK_THREADS) sm.cnt[i] = 0;
@@ -692,12 +471,12 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     GroupStats st{0, 0, 0, 0ull};
     GroupPending pd{0ull, 0u, 0u, false};
     uint32_t par = 0;
-    for (uint32_t b = blockIdx.x; b < a.nb; b += gridDim.x) {
+    for (uint32_t b = a.b_lo + blockIdx.x; b < a.b_hi; b += gridDim.x) {
         const uint32_t bb = a.base[b];
         const uint32_t m = a.base[b + 1] - bb;
         if (m == 0) continue;      // uniform per CTA
-        if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST>(a, bb, m, sm, &s_pcur[par], st, pd);
-        else group_bucket<GK_SLOW>(a, bb, m, sm, &s_pcur[par], st, pd);
+        if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd);
+        else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd);
         par ^= 1;
     }
     if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;
@@ -713,15 +492,39 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     }
 }
 
+// group stream -> work items of the rows [row_begin, row_end): one thread per stream entry (the fused phase F of
+// k2_group does this per bucket when the build is not sharded)
+__global__ void __launch_bounds__(256) k2_items(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem, uint64_t n_entries,
+                                                uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_off,
+                                                unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_entries; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = rem[x];
+        if (!r) continue;
+        const uint32_t g = gid[x];
+        if (g < row_begin || g >= row_end) continue;
+        uint64_t item;
+        if (can_inline && r <= 3) {
+            item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
+            if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
+            if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
+        } else {
+            item = ((x + 1) << 32) | ((uint64_t)r << 2);
+        }
+        const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+        row_items[row_off[g] + slot] = item;
+    }
+}
+
 int bitlen(uint64_t v) {
     int b = 0;
     while (b < 64 && (v >> b) != 0) b++;
     return b;
 }
 
-}  // namespace
-
-int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
+// part / nparts: this call covers the `part`-th share of the hash space (level-1 digits split by hash count);
+// stream: leave the groups as a compact stream (d_post = genome ids, d_st_rem = members that follow) instead of
+// building work lists.  *used = 0 when the input does not qualify for this path.
+int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint32_t nparts, bool stream) {
     *used = 0;
     const uint64_t T = ctx->T;
     const uint32_t n = ctx->n;
@@ -759,6 +562,12 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     p.nb1 = d1 ? (uint32_t)(maxkey >> (p.hb - d1)) + 1 : 1u;
     if (p.nb1 > NB_MAX) return 0;
     p.nfb = p.nb1 << d2;
+    p.dlo = 0; p.dhi = p.nb1; p.unit_lo = 0; p.unit_hi = 0xFFFFFFFFu;
+    // sub-bucket digit of the grouping kernel
+    const int key_bits = p.kb1 - d2;                       // hash bits that still vary inside a final bucket
+    const int sbits = std::max(0, std::min(GK_SUBBITS, key_bits));
+    const int rest_bits = key_bits - sbits;                // compared inside a sub-bucket (32 low bits + the rest beside the genome id)
+    if (rest_bits > 32 && rest_bits - 32 + p.gb > 32) return 0;     // does not fit the candidate arrays: general path
 
     // ---- buffers ----------------------------------------------------------------------------------
     YG_CHECK(dev_alloc(ctx, &ctx->d_ent1, T));
@@ -772,10 +581,7 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     uint32_t* base2 = hist2 + ((uint64_t)p.nfb + 2);
     uint32_t* cursor = base2 + ((uint64_t)p.nfb + 2);      // level-1 cursors first, then reused for level 2
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
-    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_PCUR], 0, 4 * sizeof(unsigned long long), st));
-#ifdef YG_PHASE_TIMING
-    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[20], 0, 12 * sizeof(unsigned long long), st));
-#endif
+    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_PCUR], 0, 5 * sizeof(unsigned long long), st));
 
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     // ---- level 1 ----------------------------------------------------------------------------------
@@ -783,6 +589,32 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     YG_CUDA(ctx, cudaGetLastError());
     k2_prep1<<<1, 1024, 0, st>>>(hist1, p.nb1, base1, tile_start, cursor, ctx->d_scalars);
     YG_CUDA(ctx, cudaGetLastError());
+    uint64_t T_mine = T;
+    if (nparts > 1) {
+        // this rank's share of the hash space: level-1 digits [dlo, dhi), split by hash count
+        std::vector<uint32_t> h(p.nb1);
+        YG_CUDA(ctx, cudaMemcpyAsync(h.data(), hist1, (size_t)p.nb1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<uint32_t> cut(nparts + 1, p.nb1);
+        cut[0] = 0;
+        uint64_t acc = 0;
+        uint32_t k = 1;
+        for (uint32_t d = 0; d < p.nb1 && k < nparts; d++) {
+            acc += h[d];
+            while (k < nparts && acc * nparts >= (uint64_t)k * T) cut[k++] = d + 1;
+        }
+        p.dlo = cut[part]; p.dhi = cut[part + 1];
+        uint64_t tiles = 0;
+        T_mine = 0;
+        p.unit_lo = 0; p.unit_hi = 0;
+        for (uint32_t d = 0; d < p.nb1; d++) {
+            if (d == p.dlo) p.unit_lo = (uint32_t)tiles;
+            tiles += ((uint64_t)h[d] + SC_TILE - 1) / SC_TILE;
+            if (d >= p.dlo && d < p.dhi) T_mine += h[d];
+            if (d + 1 == p.dhi) p.unit_hi = (uint32_t)tiles;
+        }
+        if (p.dlo >= p.dhi) { p.unit_lo = 0; p.unit_hi = 0; }
+    }
     ScatterArgs a{};
     a.hashes = ctx->d_hashes; a.gid = ctx->d_gid; a.out_ent = ctx->d_ent1; a.cursor = cursor;
     a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2;
@@ -805,6 +637,7 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
         const int grid_h = ctx->num_sms * 8;
         k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p);
         YG_CUDA(ctx, cudaGetLastError());
+        // final-bucket bases: a rank's own buckets are contiguous, foreign ones are empty -> positions are local
         size_t tb = 0;
         YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist2, base2, (int64_t)p.nfb + 1, st));
         size_t tb2 = 0;
@@ -833,86 +666,64 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     YG_CUDA(ctx, cudaMemcpyAsync(maxb, &ctx->d_scalars[SCM_MAXB], sizeof maxb, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];
+    const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];   // (level-1 maximum: over all digits, a safe bound)
     if (largest > BK_CAP) {
         ctx->msd_fallbacks++;
         return 0;                                   // skewed: the general (sort) path handles it
     }
 
-    // ---- buckets -> postings + per-genome work lists ------------------------------------------------
+    // ---- buckets -> postings + per-genome work lists (or the group stream) ------------------------------
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, T));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-    const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
-    if (ctx->group_kernel != 0) {
-        // v2: counting sort + neighbour scan, items appended to the per-genome lists in the same kernel
+    if (stream) {
+        YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, T));
+    } else {
+        YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
+        YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    }
+    {
         GroupArgs g{};
-        g.ent = final_ent; g.base = final_base; g.nb = nbuckets; g.gb = p.gb;
-        const int key_bits = p.kb1 - d2;                       // hash bits that still vary inside a final bucket
-        const int sbits = std::max(0, std::min(GK_SUBBITS, key_bits));
-        const int rest_bits = key_bits - sbits;                // compared inside a sub-bucket (32 low + the rest beside the genome id)
+        g.ent = final_ent; g.base = final_base; g.gb = p.gb;
+        g.nb = d2 ? p.nfb : p.nb1;
+        g.b_lo = d2 ? (p.dlo << d2) : p.dlo;
+        g.b_hi = d2 ? (p.dhi << d2) : p.dhi;
         g.sub_shift = p.gb + rest_bits;
         g.sub_mask = (1u << sbits) - 1u;
         g.rest_mask = rest_bits >= 64 ? ~0ull : ((1ull << rest_bits) - 1ull);
         if (g.sub_shift > 63) { g.sub_shift = 0; g.sub_mask = 0; }
-        if (rest_bits > 32 && rest_bits - 32 + p.gb > 32) return 0;     // does not fit the candidate arrays: general path
-        g.post = ctx->d_post; g.row_off = ctx->d_offsets; g.row_cnt = ctx->d_row_cnt; g.row_items = ctx->d_row_items; g.scal = ctx->d_scalars;
+        g.post = ctx->d_post; g.row_off = ctx->d_offsets; g.row_cnt = ctx->d_row_cnt; g.row_items = ctx->d_row_items;
+        g.st_gid = ctx->d_post; g.st_rem = ctx->d_st_rem; g.scal = ctx->d_scalars;
         const size_t smem = (size_t)GK_NSUB * 4 + (size_t)BK_CAP * 8 + (size_t)(GK_NSUB + 8) * 2 + (size_t)BK_CAP * 4;
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = stream ? k2_group<true> : k2_group<false>;
+        YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_group, GK_THREADS, smem));
-        const int grid = (int)std::min<uint64_t>(nbuckets, (uint64_t)ctx->num_sms * std::max(occ, 1));
-        k2_group<<<grid, GK_THREADS, smem, st>>>(g);
-        YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches += 1;
-    } else {
-    YG_CHECK(dev_alloc(ctx, &ctx->d_rec_gid, T));
-    uint64_t* rec_item = nullptr;
-    if (d2) rec_item = ctx->d_ent1;                 // level-1 words are dead once level 2 has run
-    else { YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, T)); rec_item = ctx->d_ent2; }
-    YG_CHECK(dev_alloc(ctx, &ctx->d_nrec, (uint64_t)nbuckets + 1));
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_nrec, 0, ((uint64_t)nbuckets + 1) * sizeof(uint32_t), st));
-    BucketArgs b{};
-    b.ent = final_ent; b.base = final_base; b.nb = nbuckets; b.gb = p.gb;
-    b.post = ctx->d_post; b.rec_gid = ctx->d_rec_gid; b.rec_item = rec_item; b.nrec = ctx->d_nrec; b.scal = ctx->d_scalars;
-    {
-        const size_t smem = (size_t)BK_CAP * 8 + (size_t)BK_HS * 4 + (size_t)BK_CAP * 2 * 2 + (size_t)BK_CAP + (size_t)BK_LONGQ * 2;
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_bucket, BK_THREADS, smem));
-        const int grid = (int)std::min<uint64_t>(b.nb, (uint64_t)ctx->num_sms * std::max(occ, 1));
-        k2_bucket<<<grid, BK_THREADS, smem, st>>>(b);
-        YG_CUDA(ctx, cudaGetLastError());
-        k2_rec_scatter<<<grid_for(ctx, (uint64_t)nbuckets * 32, 256, 16), 256, 0, st>>>(final_base, ctx->d_nrec, nbuckets, ctx->d_rec_gid, rec_item,
-                                                                                       ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items);
-        YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches += 2;
-    }
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GK_THREADS, smem));
+        const uint64_t nbk = g.b_hi > g.b_lo ? g.b_hi - g.b_lo : 0;
+        if (nbk) {
+            const int grid = (int)std::min<uint64_t>(nbk, (uint64_t)ctx->num_sms * std::max(occ, 1));
+            kern<<<grid, GK_THREADS, smem, st>>>(g);
+            YG_CUDA(ctx, cudaGetLastError());
+            ctx->tm.n_kernel_launches += 1;
+        }
     }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
-#ifdef YG_PHASE_TIMING
-    {
-        unsigned long long ph[12];
-        cudaMemcpy(ph, &ctx->d_scalars[20], sizeof ph, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[k2_bucket phases, cycles summed over CTAs; thread 0 | thread 255] load+init %llu | %llu, bar %llu | %llu, insert %llu | %llu, bar+heads+bar %llu | %llu, dense %llu | %llu, bar %llu | %llu\n",
-                ph[0], ph[6], ph[1], ph[7], ph[2], ph[8], ph[3], ph[9], ph[4], ph[10], ph[5], ph[11]);
-    }
-#endif
-    uint64_t P = sc[SCM_PCUR], I = sc[SCM_ICUR];
-    if (ctx->group_kernel != 0) {           // every word is a singleton or a member of a shared group
-        P = T - sc[SC_SINGLE];
-        I = P - (sc[SC_HEADS] - sc[SC_SINGLE]);
-    }
-    ctx->P = P;
-    ctx->n_items = I;
-    ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])
+    // every word is a singleton or a member of a shared group
+    const uint64_t P = T_mine - sc[SC_SINGLE];
+    const uint64_t I = P - (sc[SC_HEADS] - sc[SC_SINGLE]);
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
-
+    if (stream) {
+        if (sc[SCM_STREAM] != P) return ygpu_fail(ctx, YGPU_ERR_CUDA, "group stream holds %llu entries, expected %llu", sc[SCM_STREAM], (unsigned long long)P);
+        ctx->stream_entries = P;
+    } else {
+        ctx->P = P;
+        ctx->n_items = I;
+        ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])
+    }
+    S->n_hashes = T_mine;
     S->n_distinct = sc[SC_HEADS];
     S->n_singleton = sc[SC_SINGLE];
     S->n_index = S->n_distinct - S->n_singleton;
@@ -921,5 +732,91 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     S->n_row_items = I;
     S->has_duplicates = sc[SC_DUPS] ? 1u : 0u;
     *used = 1;
+    return 0;
+}
+
+}  // namespace
+
+int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
+    const uint64_t T = ctx->T;
+    const int rc = msd_build(ctx, S, used, 0, 1, false);
+    S->n_hashes = T;
+    return rc;
+}
+
+static uint32_t max_sketch_of(ygpu_ctx* ctx) {
+    std::vector<uint32_t> sz(ctx->n);
+    if (ctx->n) cudaMemcpy(sz.data(), ctx->d_sizes, (size_t)ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    uint32_t mx = 0;
+    for (uint32_t v : sz) mx = std::max(mx, v);
+    return mx;
+}
+
+// ---- hash-range sharded build (one rank per GPU; the exchange itself is the caller's: NCCL all-gather) -------
+extern "C" int ygpu_index_partial(ygpu_ctx* ctx, uint32_t part, uint32_t nparts, ygpu_index_stats* stats, uint64_t* n_entries) {
+    if (!ctx || !stats || !n_entries || nparts == 0 || part >= nparts) return YGPU_ERR_ARG;
+    if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_partial: no sketches loaded");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->indexed = false; ctx->row_work_valid = false; ctx->P = 0; ctx->n_items = 0; ctx->stream_entries = 0;
+    *n_entries = 0;
+    ygpu_index_stats S{};
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    int used = 0;
+    YG_CHECK(msd_build(ctx, &S, &used, part, nparts, true));
+    if (!used) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_partial: this database does not qualify for the partition path (use ygpu_build_index)");
+    S.index_path = 1;
+    *stats = S;
+    *n_entries = ctx->stream_entries;
+    return 0;
+}
+
+extern "C" int ygpu_index_stream_copy(ygpu_ctx* ctx, uint32_t* d_gid_dst, uint16_t* d_rem_dst) {
+    if (!ctx || ((!d_gid_dst || !d_rem_dst) && ctx->stream_entries)) return YGPU_ERR_ARG;
+    if (!ctx->stream_entries) return 0;
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    YG_CUDA(ctx, cudaMemcpyAsync(d_gid_dst, ctx->d_post, ctx->stream_entries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    YG_CUDA(ctx, cudaMemcpyAsync(d_rem_dst, ctx->d_st_rem, ctx->stream_entries * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    YG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ygpu_index_finish(ygpu_ctx* ctx, const uint32_t* d_gid, const uint16_t* d_rem, uint64_t n_entries, uint32_t row_begin,
+                                 uint32_t row_end, const ygpu_index_stats* total) {
+    if (!ctx || !total || (n_entries && (!d_gid || !d_rem))) return YGPU_ERR_ARG;
+    if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_finish: no sketches loaded");
+    if (row_begin > row_end || row_end > ctx->n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad row range [%u,%u) of %u", row_begin, row_end, ctx->n);
+    if (n_entries >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "group stream of %llu entries >= 2^32 not supported", (unsigned long long)n_entries);
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t T = ctx->T;
+    const uint32_t n = ctx->n;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_post, std::max<uint64_t>(T, n_entries + 4)));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    if (n_entries) {
+        if (d_gid != ctx->d_post)
+            YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_post, d_gid, n_entries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        const int gb = bitlen(n > 0 ? (uint64_t)n - 1 : 0);
+        k2_items<<<grid_for(ctx, n_entries, 256, 16), 256, 0, st>>>(ctx->d_post, d_rem, n_entries, row_begin, row_end,
+                                                                     gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 1;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_index += elapsed(ctx, 0, 1);
+    ygpu_index_stats S = *total;
+    S.n_hashes = T;
+    S.max_sketch = max_sketch_of(ctx);
+    S.index_path = 1;
+    ctx->stats = S;
+    ctx->P = n_entries;
+    ctx->n_items = S.n_row_items;
+    ctx->d_row_begin = ctx->d_offsets;
+    ctx->row_work_valid = false;
+    ctx->last_index_path = 1;
+    ctx->indexed = true;
     return 0;
 }

@@ -117,7 +117,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
-    dev_free(ctx, &ctx->d_ovf_rows); dev_free(ctx, &ctx->d_rec_gid); dev_free(ctx, &ctx->d_nrec);
+    dev_free(ctx, &ctx->d_ovf_rows); dev_free(ctx, &ctx->d_st_rem);
     dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
@@ -1101,7 +1101,6 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "force_u16")) { ctx->force_u16 = (int)value; return 0; }
     if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
     if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
-    if (!strcmp(name, "group_kernel")) { ctx->group_kernel = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

@@ -21,22 +21,13 @@ ROW_CONSTANT = 64.0   # per-row fixed cost in "increment" units (same constant a
 def split_rows_by_work(work: np.ndarray, nparts: int) -> np.ndarray:
     """Contiguous row ranges of nearly equal (work + constant) -- the host mirror of ygpu_row_partition."""
     n = int(work.shape[0])
-    bounds = np.zeros(nparts + 1, dtype=np.uint32)
-    cost = work.astype(np.float64) + ROW_CONSTANT
-    total = float(cost.sum())
-    acc = 0.0
-    part = 1
-    for g in range(n):
-        if part >= nparts:
-            break
-        acc += float(cost[g])
-        while part < nparts and acc >= total * part / nparts:
-            bounds[part] = g + 1
-            part += 1
-    while part < nparts:
-        bounds[part] = n
-        part += 1
-    bounds[nparts] = n
+    bounds = np.full(nparts + 1, n, dtype=np.uint32)
+    bounds[0] = 0
+    if n and nparts > 1:
+        cs = np.cumsum(work.astype(np.float64) + ROW_CONSTANT)
+        targets = cs[-1] * np.arange(1, nparts, dtype=np.float64) / nparts
+        # part k ends after the first row at which the running cost reaches k/nparts of the total
+        bounds[1:nparts] = np.minimum(np.searchsorted(cs, targets, side="left") + 1, n)
     return bounds
 
 
@@ -109,3 +100,72 @@ def load_sketches_sharded(ctx, pinned_slice, offsets: np.ndarray, total: int, ra
     torch.cuda.current_stream(device).synchronize()      # the library works on its own stream
     ctx.load_sketches_device(full.data_ptr(), d_off.data_ptr(), int(offsets.shape[0]) - 1)
     return full
+
+
+SUMMED_STATS = ("n_hashes", "n_distinct", "n_singleton", "n_index", "n_postings", "n_increments", "n_row_items", "has_duplicates")
+
+
+def split_rows_by_size(offsets: np.ndarray, nparts: int) -> np.ndarray:
+    """Contiguous row ranges holding nearly equal numbers of sketch hashes (known before any index exists)."""
+    sizes = np.diff(np.asarray(offsets).astype(np.int64)).astype(np.float64)
+    return split_rows_by_work(sizes, nparts)
+
+
+_stream_buffers = {}     # (device index, world) -> (gid, rem) device tensors reused across builds
+
+
+def _stream_buffer(device, world: int, m: int):
+    import torch
+    key = (str(device), world)
+    buf = _stream_buffers.get(key)
+    if buf is None or buf[0].numel() < world * m:
+        cap = world * (m + m // 16 + 1024)
+        buf = (torch.zeros(cap, dtype=torch.int32, device=device), torch.zeros(cap, dtype=torch.int16, device=device))
+        _stream_buffers[key] = buf
+    return buf[0][: world * m], buf[1][: world * m]
+
+
+def build_index_sharded(ctx, offsets: np.ndarray, rank: int, world: int, device, group=None, bounds: Optional[np.ndarray] = None):
+    """Index build split by hash range across the ranks (include/yacht_gpu.h: ygpu_index_partial / _finish).
+
+    Every rank holds all sketches.  Rank r partitions and groups only its share of the hash space, the ranks
+    all-gather their group streams over NCCL (padded to the longest; padding entries carry follow-count 0 and
+    are ignored), and each rank builds the work lists of its own query rows (`bounds`: row ranges per rank,
+    default split_rows_by_size(offsets, world)).  Returns (row_begin, row_end, total statistics), or None when
+    the database does not qualify (the caller then runs ctx.build_index())."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import YgpuError
+
+    try:
+        st, n_r = ctx.index_partial(rank, world)
+        ok = 1
+    except YgpuError:
+        st, n_r, ok = {k: 0 for k in SUMMED_STATS}, 0, 0
+    head = torch.tensor([ok, n_r] + [int(st[k]) for k in SUMMED_STATS], dtype=torch.int64, device=device)
+    if world > 1:
+        allh = torch.empty(world * head.numel(), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allh, head, group=group)
+        allh = allh.view(world, -1).cpu()
+    else:
+        allh = head.view(1, -1).cpu()
+    if int(allh[:, 0].min()) == 0:
+        return None
+    m = max(int(allh[:, 1].max()), 1)
+    total = {k: int(allh[:, 2 + i].sum()) for i, k in enumerate(SUMMED_STATS)}
+    total["has_duplicates"] = 1 if total["has_duplicates"] else 0
+    gid, rem = _stream_buffer(device, world, m)
+    mine_g, mine_r = gid[rank * m: (rank + 1) * m], rem[rank * m: (rank + 1) * m]
+    if n_r < m:                                            # padding of this rank's slice: follow-count 0 = ignored
+        mine_r[n_r:].zero_()
+    torch.cuda.current_stream(device).synchronize()        # the library writes on its own stream
+    ctx.index_stream_copy(mine_g.data_ptr(), mine_r.data_ptr())
+    if world > 1:
+        dist.all_gather_into_tensor(gid, mine_g, group=group)
+        dist.all_gather_into_tensor(rem.view(torch.uint8), mine_r.view(torch.uint8), group=group)   # NCCL has no int16
+        torch.cuda.current_stream(device).synchronize()
+    if bounds is None:
+        bounds = split_rows_by_size(offsets, world)
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
+    ctx.index_finish(gid.data_ptr(), rem.data_ptr(), world * m, rb, re, total)
+    return rb, re, total

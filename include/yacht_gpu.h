@@ -8,6 +8,7 @@
  *
  *   ygpu_read_signatures    read_min_hashes() / read_sketches()                main.cpp:62-124
  *   ygpu_load_sketches      the in-memory result of read_sketches()            main.cpp:89-124
+ *   ygpu_upload_begin / _block / _finish   the same, streamed while parsing        main.cpp:89-124
  *                           (vector<vector<hash_t>> sketches, :51) as one flat
  *                           uint64 array + CSR offsets; genome id = file-list
  *                           line index (:127-139)
@@ -156,6 +157,15 @@ int ygpu_load_sketches(ygpu_ctx* ctx, const uint64_t* hashes, const uint64_t* of
  * (what a multi-threaded parser leaves behind): copied piece by piece, no host-side assembly.   */
 int ygpu_load_sketch_blocks(ygpu_ctx* ctx, const uint64_t* const* blocks, const uint64_t* block_lens, uint32_t nblocks,
                             const uint64_t* offsets, uint32_t n_genomes);
+/* Streaming ingest for callers that parse files themselves (read_sketches(), main.cpp:89-124, parses while
+ * nothing else happens): blocks of consecutive sketches are uploaded WHILE later files are still being parsed.
+ * ygpu_upload_block is thread-safe (parser threads call it concurrently; the host block may be released when it
+ * returns) and stages through page-locked bounce buffers; block ids are the caller's.  ygpu_upload_finish takes
+ * the position of every block in the flat array (known once all sketch sizes are) and leaves the context in the
+ * same state as ygpu_load_sketches.                                                                          */
+int ygpu_upload_begin(ygpu_ctx* ctx);
+int ygpu_upload_block(ygpu_ctx* ctx, uint32_t block_id, const uint64_t* hashes, uint64_t len);
+int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n_genomes);
 /* Same, but DEVICE pointers on ctx's device; the arrays are copied device-to-device.            */
 int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n_genomes);
 int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats /* may be NULL */);

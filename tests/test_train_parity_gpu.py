@@ -182,3 +182,18 @@ def test_full_size_properties_85k(gpu_ctx):
     assert st0["index_path"] == 0 and alt.tobytes() == dense.tobytes()
     for f in ("n_distinct", "n_singleton", "n_index", "n_postings", "n_increments"):
         assert st0[f] == st[f], f
+
+
+@pytest.mark.parametrize("per_block", [7, 32, 2000])
+def test_streamed_ingest_matches_plain_load(gpu_ctx, per_block):
+    # ygpu_upload_begin / _block / _finish (blocks uploaded out of order, an empty sketch, a block larger than one
+    # bounce buffer when per_block = 2000) leaves the same resident sketches as ygpu_load_sketches
+    db = synth.make_reference_db(2400, 21, mean_size=700, sd_size=200)
+    parts = [db.sketch(g) for g in range(db.n)]
+    parts[5] = np.zeros(0, dtype=np.uint64)
+    db2 = synth.from_sketches(parts)
+    ref = to.oracle_train(db2.hashes, db2.offsets, THR)
+    gpu_ctx.load_sketches_streamed(db2.hashes, db2.offsets, per_block)
+    st = gpu_ctx.build_index()
+    assert (st["n_hashes"], st["n_distinct"], st["n_singleton"]) == (int(db2.offsets[-1]), ref.n_distinct, ref.n_singleton)
+    assert _pairs_tuple(gpu_ctx.pairwise_flag(THR)) == _pairs_tuple(ref.pairs)

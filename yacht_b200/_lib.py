@@ -21,6 +21,7 @@ ABI_SYMBOLS = [
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test", "ygpu_index_partial", "ygpu_index_stream_copy", "ygpu_index_finish",
+    "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish",
 ]
 
 
@@ -102,6 +103,9 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_build_index.argtypes = [vp, ctypes.POINTER(IndexStats)]
     lib.ygpu_pairwise_flag.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.ygpu_row_partition.argtypes = [vp, u32, vp]
+    lib.ygpu_upload_begin.argtypes = [vp]
+    lib.ygpu_upload_block.argtypes = [vp, u32, vp, u64]
+    lib.ygpu_upload_finish.argtypes = [vp, vp, u32, vp, u32]
     lib.ygpu_index_partial.argtypes = [vp, u32, u32, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     lib.ygpu_index_stream_copy.argtypes = [vp, vp, vp]
     lib.ygpu_index_finish.argtypes = [vp, vp, vp, u64, u32, u32, ctypes.POINTER(IndexStats)]
@@ -171,6 +175,23 @@ class GpuContext:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = offsets.shape[0] - 1
         self._check(self.lib.ygpu_load_sketches(self.h, hashes.ctypes.data, offsets.ctypes.data, n), "ygpu_load_sketches")
+        self.n = n
+
+    def load_sketches_streamed(self, hashes: np.ndarray, offsets: np.ndarray, genomes_per_block: int = 32) -> None:
+        """The streaming ingest ABI (ygpu_upload_begin / _block / _finish) driven from one thread: blocks of
+        `genomes_per_block` consecutive sketches, uploaded in REVERSE order (any order must work)."""
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = int(offsets.shape[0]) - 1
+        nblocks = (n + genomes_per_block - 1) // genomes_per_block
+        dst = np.array([int(offsets[min(b * genomes_per_block, n)]) for b in range(nblocks)] + [int(offsets[n])], dtype=np.uint64)
+        self._check(self.lib.ygpu_upload_begin(self.h), "ygpu_upload_begin")
+        for b in reversed(range(nblocks)):
+            lo, hi = int(dst[b]), int(dst[b + 1])
+            if hi > lo:
+                blk = hashes[lo:hi]
+                self._check(self.lib.ygpu_upload_block(self.h, b, blk.ctypes.data, hi - lo), "ygpu_upload_block")
+        self._check(self.lib.ygpu_upload_finish(self.h, dst.ctypes.data, nblocks, offsets.ctypes.data, n), "ygpu_upload_finish")
         self.n = n
 
     def load_sketches_device(self, d_hashes_ptr: int, d_offsets_ptr: int, n: int) -> None:

@@ -73,6 +73,7 @@ struct ygpu_ctx {
     int force_u16 = 0;              // test hook: packed 16-bit counters even when 32-bit ones fit
 
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
+    void* upload = nullptr;         // streaming ingest state (yacht_gpu.cu: ygpu_upload_*)
 
     ygpu_timings tm = {};
 };
@@ -166,3 +167,4 @@ int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used);
 
 // run path (run_kernels.cu)
 void ygpu_run_release(ygpu_ctx* ctx);
+void ygpu_upload_release(ygpu_ctx* ctx);

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <mutex>
 #include <string>
@@ -35,6 +36,9 @@ struct Ingest {
     std::vector<int> empty_ids;
     // when read_sketches(..., assemble_flat = false): the parsed blocks stay where the workers left them
     std::vector<std::vector<uint64_t>> blocks;     // block b = sketches of files [b * kFilesPerBlock, ...)
+    // called by a parser thread as soon as block b is complete (blocks[b] is final from then on): lets the caller
+    // ship blocks to the GPU while later files are still being parsed
+    std::function<void(uint32_t)> on_block;
     bool fatal = false;
     bool quiet = false;              // library use: do not print the per-file message
     std::atomic<uint32_t> n_unreadable{0};
@@ -65,7 +69,8 @@ inline void pin_worker(int t) {
 inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
     const uint32_t n = (uint32_t)in.names.size();
     const uint32_t nblocks = (n + kFilesPerBlock - 1) / kFilesPerBlock;
-    std::vector<std::vector<uint64_t>> block_hashes(nblocks);
+    in.blocks.assign(nblocks, std::vector<uint64_t>());
+    std::vector<std::vector<uint64_t>>& block_hashes = in.blocks;
     std::vector<uint32_t> sizes(n, 0);
     std::atomic<uint32_t> next{0};
     std::mutex mu;
@@ -98,6 +103,7 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
                 sizes[f] = (uint32_t)(out.size() - before);
             }
             block_hashes[b] = std::move(out);
+            if (in.on_block) in.on_block(b);
         }
     };
     const auto t_begin = std::chrono::high_resolution_clock::now();
@@ -114,7 +120,6 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
     }
     const uint64_t T = in.offsets[n];
     if (!assemble_flat) {
-        in.blocks = std::move(block_hashes);
         if (getenv("YACHT_INGEST_TIMING")) {
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             std::cerr << "[ingest] " << n << " files, " << T << " hashes, " << nt << " threads: parse " << ms(t_begin, t_parsed)
@@ -141,6 +146,7 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
     pool.clear();
     for (int t = 0; t < nt; t++) pool.emplace_back(copier, t);
     for (auto& t : pool) t.join();
+    in.blocks.clear();
     if (getenv("YACHT_INGEST_TIMING")) {
         const auto t_end = std::chrono::high_resolution_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

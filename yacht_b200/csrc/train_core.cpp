@@ -23,12 +23,15 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <iostream>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <utility>
 #include <vector>
 
@@ -156,6 +159,7 @@ int64_t ms_since(std::chrono::high_resolution_clock::time_point t0) {
 }  // namespace
 
 int main(int argc, char** argv) {
+    const auto t_main = std::chrono::high_resolution_clock::now();
     Arguments args;
     const int pa = parse_arguments(argc, argv, args);
     if (pa == 2) return 0;
@@ -188,14 +192,62 @@ int main(int argc, char** argv) {
     std::vector<ygpu_ctx*> ctxs(ndev, nullptr);
     std::vector<DeviceResult> res(ndev);
     std::vector<std::thread> ctx_threads;
+    // Parsed blocks are shipped to the GPU(s) while later files are still being parsed: parser threads queue the
+    // ids of finished blocks; uploader threads -- started as soon as the contexts exist -- feed ygpu_upload_block.
+    const bool stream_upload = !getenv("YACHT_NO_STREAM_UPLOAD");
+    std::mutex q_mu;
+    std::condition_variable q_cv;
+    std::deque<uint32_t> q_blocks;
+    bool q_done = false;
+    std::atomic<int> upload_rc{0};
     for (int d = 0; d < ndev; d++)
         ctx_threads.emplace_back([&, d]() {
             res[d].rc = ygpu_ctx_create(&ctxs[d], d);
             if (res[d].rc) res[d].err = ygpu_last_error(nullptr);
+            else if (stream_upload) {
+                res[d].rc = ygpu_upload_begin(ctxs[d]);
+                if (res[d].rc) res[d].err = ygpu_last_error(ctxs[d]);
+            }
         });
+    std::vector<std::thread> uploaders;
+    std::thread upload_master;
+    if (stream_upload) {
+        in.on_block = [&](uint32_t b) {
+            { std::lock_guard<std::mutex> lk(q_mu); q_blocks.push_back(b); }
+            q_cv.notify_one();
+        };
+        upload_master = std::thread([&]() {
+            for (auto& t : ctx_threads) t.join();              // contexts + bounce buffers ready
+            for (int d = 0; d < ndev; d++) if (res[d].rc) return;
+            const int nu = std::max(2, std::min(4, args.number_of_threads / 4));
+            for (int k = 0; k < nu; k++)
+                uploaders.emplace_back([&]() {
+                    for (;;) {
+                        uint32_t b;
+                        {
+                            std::unique_lock<std::mutex> lk(q_mu);
+                            q_cv.wait(lk, [&] { return !q_blocks.empty() || q_done; });
+                            if (q_blocks.empty()) return;
+                            b = q_blocks.front();
+                            q_blocks.pop_front();
+                        }
+                        for (int d = 0; d < ndev; d++) {
+                            const int rc = ygpu_upload_block(ctxs[d], b, in.blocks[b].data(), in.blocks[b].size());
+                            if (rc) upload_rc = rc;
+                        }
+                    }
+                });
+        });
+    }
     yingest::read_sketches(in, args.number_of_threads, /*assemble_flat=*/false);
+    if (stream_upload) {
+        { std::lock_guard<std::mutex> lk(q_mu); q_done = true; }
+        q_cv.notify_all();
+        upload_master.join();
+        for (auto& t : uploaders) t.join();
+    }
     if (in.fatal) {
-        for (auto& t : ctx_threads) t.join();
+        if (!stream_upload) for (auto& t : ctx_threads) t.join();
         std::cerr << "run_yacht_train_core: cannot parse signature " << in.fatal_msg << std::endl;
         return 4;
     }
@@ -211,7 +263,9 @@ int main(int argc, char** argv) {
     // ---- index + pairwise on the GPU(s) ----------------------------------------------------------
     auto t_index = std::chrono::high_resolution_clock::now();
     std::cout << "Building index from sketches..." << std::endl;
-    for (auto& t : ctx_threads) t.join();
+    if (!stream_upload) for (auto& t : ctx_threads) t.join();
+    std::vector<uint64_t> block_dst(in.blocks.size());
+    for (size_t b = 0; b < in.blocks.size(); b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)];
     std::vector<const uint64_t*> block_ptrs(in.blocks.size());
     std::vector<uint64_t> block_lens(in.blocks.size());
     for (size_t b = 0; b < in.blocks.size(); b++) { block_ptrs[b] = in.blocks[b].data(); block_lens[b] = in.blocks[b].size(); }
@@ -221,8 +275,11 @@ int main(int argc, char** argv) {
             th.emplace_back([&, d]() {
                 DeviceResult& r = res[d];
                 if (r.rc) return;
-                r.rc = ygpu_load_sketch_blocks(ctxs[d], block_ptrs.data(), block_lens.data(), (uint32_t)block_ptrs.size(),
-                                               in.offsets.data(), n);
+                if (stream_upload)
+                    r.rc = upload_rc ? (int)upload_rc : ygpu_upload_finish(ctxs[d], block_dst.data(), (uint32_t)block_dst.size(), in.offsets.data(), n);
+                else
+                    r.rc = ygpu_load_sketch_blocks(ctxs[d], block_ptrs.data(), block_lens.data(), (uint32_t)block_ptrs.size(),
+                                                   in.offsets.data(), n);
                 if (!r.rc) r.rc = ygpu_build_index(ctxs[d], &r.stats);
                 if (r.rc) r.err = ygpu_last_error(ctxs[d]);
             });
@@ -351,6 +408,16 @@ int main(int argc, char** argv) {
         std::cout << "[gpu " << d << "] rows [" << bounds[d] << "," << bounds[d + 1] << ") h2d " << t.ms_h2d << " ms, sort "
                   << t.ms_sort << " ms, index " << t.ms_index << " ms, count+flag " << t.ms_count << " ms, d2h " << t.ms_d2h
                   << " ms, pairs " << res[d].n_pairs << std::endl;
+    }
+    std::cout << "[wall] " << ms_since(t_main) << " ms from process start to results on disk" << std::endl;
+    // Every output is on disk.  Tearing down ~20 GB of device buffers, the CUDA context and the parsed blocks costs
+    // more than the whole GPU computation; a command-line process leaves that to the OS (YACHT_TRAIN_TEARDOWN=1 keeps
+    // the orderly path, e.g. under compute-sanitizer).
+    if (!getenv("YACHT_TRAIN_TEARDOWN")) {
+        std::cout.flush();
+        std::cerr.flush();
+        fflush(nullptr);
+        _exit(0);
     }
     for (auto* c : ctxs) ygpu_ctx_destroy(c);
     if (in.hashes) { if (in.pinned) ygpu_host_free(in.hashes); else free(in.hashes); }

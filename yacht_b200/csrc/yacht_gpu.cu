@@ -130,6 +130,7 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     release_sketches(ctx);
     free_all(ctx);
     ygpu_run_release(ctx);
+    ygpu_upload_release(ctx);
     if (ctx->d_pairs) cudaFree(ctx->d_pairs);
     if (ctx->d_temp) cudaFree(ctx->d_temp);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -252,6 +253,170 @@ extern "C" int ygpu_load_sketch_blocks(ygpu_ctx* ctx, const uint64_t* const* blo
     YG_CHECK(finish_load(ctx));
     ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
     return 0;
+}
+
+// ---- streaming ingest: blocks of parsed sketches travel to the device while later files are still being
+// parsed.  Their final position in the flat array is only known once every sketch size is (CSR offsets are a
+// prefix sum), so a block is first uploaded to a staging chunk -- through a small pool of page-locked bounce
+// buffers, filled by the calling threads in parallel, DMA'd asynchronously -- and ygpu_upload_finish moves all
+// blocks to their places with one device-side copy kernel.
+#include <condition_variable>
+#include <mutex>
+
+namespace {
+struct UploadBlk { const uint64_t* src; uint64_t len; uint32_t id; };
+struct UploadState {
+    static constexpr int NB = 8;
+    static constexpr uint64_t BOUNCE = 1ull << 20;        // hashes per bounce buffer (8 MB)
+    static constexpr uint64_t CHUNK = 1ull << 25;         // hashes per device staging chunk (256 MB)
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t*> chunks;
+    uint64_t fill = CHUNK;                                // used part of the last chunk (CHUNK = none yet)
+    std::vector<UploadBlk> blocks;
+    uint64_t* bounce[NB] = {};
+    cudaEvent_t bev[NB] = {};
+    cudaStream_t bst[NB] = {};
+    bool busy[NB] = {};
+    uint64_t total = 0;
+    int failed = 0;
+};
+
+struct PlaceDesc { const uint64_t* src; uint64_t dst; uint64_t len; };
+
+__global__ void __launch_bounds__(256) k_place_blocks(const PlaceDesc* __restrict__ d, uint32_t nd, uint64_t* __restrict__ out) {
+    for (uint32_t b = blockIdx.x; b < nd; b += gridDim.x) {
+        const PlaceDesc p = d[b];
+        for (uint64_t i = threadIdx.x; i < p.len; i += blockDim.x) out[p.dst + i] = p.src[i];
+    }
+}
+}  // namespace
+
+void ygpu_upload_release(ygpu_ctx* ctx) {
+    UploadState* u = (UploadState*)ctx->upload;
+    if (!u) return;
+    for (int b = 0; b < UploadState::NB; b++) {
+        if (u->bst[b]) { cudaStreamSynchronize(u->bst[b]); cudaStreamDestroy(u->bst[b]); }
+        if (u->bev[b]) cudaEventDestroy(u->bev[b]);
+        if (u->bounce[b]) cudaFreeHost(u->bounce[b]);
+    }
+    for (uint64_t* c : u->chunks) cudaFree(c);
+    delete u;
+    ctx->upload = nullptr;
+}
+
+extern "C" int ygpu_upload_begin(ygpu_ctx* ctx) {
+    if (!ctx) return YGPU_ERR_ARG;
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    ygpu_upload_release(ctx);
+    release_sketches(ctx);
+    UploadState* u = new (std::nothrow) UploadState();
+    if (!u) return ygpu_fail(ctx, YGPU_ERR_NOMEM, "out of host memory");
+    ctx->upload = u;
+    for (int b = 0; b < UploadState::NB; b++) {
+        YG_CUDA(ctx, cudaHostAlloc((void**)&u->bounce[b], UploadState::BOUNCE * sizeof(uint64_t), cudaHostAllocDefault));
+        YG_CUDA(ctx, cudaStreamCreateWithFlags(&u->bst[b], cudaStreamNonBlocking));
+        YG_CUDA(ctx, cudaEventCreateWithFlags(&u->bev[b], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// Thread-safe: parser / uploader threads call it concurrently.  `hashes` may be released when it returns.
+extern "C" int ygpu_upload_block(ygpu_ctx* ctx, uint32_t block_id, const uint64_t* hashes, uint64_t len) {
+    if (!ctx || (len && !hashes)) return YGPU_ERR_ARG;
+    UploadState* u = (UploadState*)ctx->upload;
+    if (!u) return ygpu_fail(ctx, YGPU_ERR_STATE, "upload_block: ygpu_upload_begin first");
+    if (len == 0) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { u->failed = 1; return YGPU_ERR_CUDA; }
+    uint64_t done = 0;
+    uint64_t* base = nullptr;      // where this block lives in the staging chunks
+    while (done < len) {
+        const uint64_t piece = std::min<uint64_t>(len - done, UploadState::BOUNCE);
+        int b = -1;
+        {
+            std::unique_lock<std::mutex> lk(u->mu);
+            if (done == 0) {          // reserve device space for the whole block (contiguous inside one chunk when it fits)
+                if (len > UploadState::CHUNK) { u->failed = 1; return ygpu_fail(ctx, YGPU_ERR_ARG, "upload_block: block of %llu hashes exceeds the staging chunk", (unsigned long long)len); }
+                if (u->fill + len > UploadState::CHUNK) {
+                    uint64_t* c = nullptr;
+                    if (cudaMalloc((void**)&c, UploadState::CHUNK * sizeof(uint64_t)) != cudaSuccess) { u->failed = 1; return ygpu_fail(ctx, YGPU_ERR_NOMEM, "upload_block: staging chunk"); }
+                    u->chunks.push_back(c);
+                    u->fill = 0;
+                }
+                base = u->chunks.back() + u->fill;
+                u->blocks.push_back(UploadBlk{base, len, block_id});
+                u->fill += len;
+                u->total += len;
+            }
+            u->cv.wait(lk, [&] { for (int i = 0; i < UploadState::NB; i++) if (!u->busy[i]) return true; return false; });
+            for (int i = 0; i < UploadState::NB; i++) if (!u->busy[i]) { b = i; break; }
+            u->busy[b] = true;
+        }
+        cudaError_t e = cudaEventSynchronize(u->bev[b]);            // the previous DMA out of this bounce buffer
+        if (e == cudaSuccess) {
+            memcpy(u->bounce[b], hashes + done, piece * sizeof(uint64_t));
+            e = cudaMemcpyAsync(base + done, u->bounce[b], piece * sizeof(uint64_t), cudaMemcpyHostToDevice, u->bst[b]);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(u->bev[b], u->bst[b]);
+        {
+            std::lock_guard<std::mutex> lk(u->mu);
+            u->busy[b] = false;
+            if (e != cudaSuccess) u->failed = 1;
+        }
+        u->cv.notify_one();
+        if (e != cudaSuccess) return ygpu_fail(ctx, YGPU_ERR_CUDA, "upload_block: %s", cudaGetErrorString(e));
+        done += piece;
+    }
+    return 0;
+}
+
+// block_dst[id] = position of block `id` in the flat hash array; offsets / n as for ygpu_load_sketches.
+extern "C" int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n) {
+    if (!ctx || !offsets || (nblocks && !block_dst)) return YGPU_ERR_ARG;
+    UploadState* u = (UploadState*)ctx->upload;
+    if (!u) return ygpu_fail(ctx, YGPU_ERR_STATE, "upload_finish: ygpu_upload_begin first");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int b = 0; b < UploadState::NB; b++) YG_CUDA(ctx, cudaStreamSynchronize(u->bst[b]));
+    const uint64_t T = offsets[n];
+    int rc = 0;
+    if (u->failed) rc = ygpu_fail(ctx, YGPU_ERR_CUDA, "upload_finish: an upload failed");
+    else if (u->total != T || offsets[0] != 0) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "upload_finish: %llu hashes uploaded, offsets say %llu", (unsigned long long)u->total, (unsigned long long)T);
+    else if (T >= (1ull << 32)) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)T);
+    for (uint32_t g = 0; g < n && !rc; g++)
+        if (offsets[g + 1] < offsets[g]) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+    std::vector<PlaceDesc> desc;
+    for (const UploadBlk& k : u->blocks) {
+        if (rc) break;
+        if (k.id >= nblocks || block_dst[k.id] + k.len > T) { rc = ygpu_fail(ctx, YGPU_ERR_ARG, "upload_finish: block %u does not fit", k.id); break; }
+        desc.push_back(PlaceDesc{k.src, block_dst[k.id], k.len});
+    }
+    if (!rc) {
+        ctx->n = n;
+        ctx->T = T;
+        rc = dev_alloc(ctx, &ctx->d_hashes, T);
+        if (!rc) rc = dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1);
+        if (!rc) rc = ygpu_temp_reserve(ctx, std::max<size_t>(desc.size(), 1) * sizeof(PlaceDesc));
+    }
+    if (!rc) {
+        cudaStream_t st = ctx->stream;
+        cudaError_t e = cudaEventRecord(ctx->ev[0], st);
+        if (e == cudaSuccess && !desc.empty()) {
+            e = cudaMemcpyAsync(ctx->d_temp, desc.data(), desc.size() * sizeof(PlaceDesc), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                k_place_blocks<<<(unsigned)std::min<size_t>(desc.size(), (size_t)ctx->num_sms * 16), 256, 0, st>>>((const PlaceDesc*)ctx->d_temp, (uint32_t)desc.size(), ctx->d_hashes);
+                e = cudaGetLastError();
+                ctx->tm.n_kernel_launches++;
+            }
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[1], st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // desc is a host temporary
+        if (e != cudaSuccess) rc = ygpu_fail(ctx, YGPU_ERR_CUDA, "upload_finish: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = finish_load(ctx);
+    if (!rc) ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
+    ygpu_upload_release(ctx);
+    return rc;
 }
 
 extern "C" int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n) {

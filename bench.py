@@ -393,7 +393,23 @@ def run_b200_arm(args):
                         rooflines[k]["traffic_source"] = tr.get("source")
         except Exception:
             pass
-        dominant = max(rooflines.values(), key=lambda r: r["ms_per_launch"])
+        rooflines["index_partition"]["kernels"] = 4          # a phase of four kernels: not a candidate for `roofline`
+        if msd:
+            # the partition phase kernel by kernel (CUDA events around each launch, ygpu_timings.ms_hist1 ...)
+            wsh = 1.0 if world == 1 else 1.0 / world
+            for key, kern, nbytes, formula in (
+                    ("part_hist1", "k2_hist1 (level-1 digit histogram)", 8 * Tn, "8*T"),
+                    ("part_scatter1", "k2_scatter<1> (pack (hash, genome) words, scatter to level-1 buckets)", 12 * Tn + 8 * Tn * wsh,
+                     "12*T read + 8*T written" + ("" if world == 1 else "/N")),
+                    ("part_hist2", "k2_hist2 (level-2 digit histogram)", 8 * Tn * wsh, "8*T" + ("" if world == 1 else "/N")),
+                    ("part_scatter2", "k2_scatter<2> (scatter to final buckets)", 16 * Tn * wsh, "16*T" + ("" if world == 1 else "/N"))):
+                ms = tm_res["ms_" + key.split("_", 1)[1]] / steps
+                if ms > 0:
+                    rooflines[key] = rl(kern, nbytes, ms, formula)
+            if tm_res.get("ms_group", 0) > 0 and world > 1:
+                rooflines["index_grouping_k2_group"] = rl("k2_group<stream> alone", (8 * Tn + 6 * Pn) / world, tm_res["ms_group"] / steps,
+                                                          "(8*T words + 6*P stream)/N")
+        dominant = max((r for r in rooflines.values() if r.get("kernels", 1) == 1), key=lambda r: r["ms_per_launch"])
         line = {
             "metric": "ref-pair containments/s (yacht train hot path)", "value": pairs_total / (ms_res * 1e-3), "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,

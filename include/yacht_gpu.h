@@ -77,8 +77,8 @@ typedef struct {
 /* Device timings (CUDA events on the context's stream) accumulated since ygpu_reset_timers(). */
 typedef struct {
     double ms_h2d;          /* ygpu_load_sketches host->device copies                          */
-    double ms_sort;         /* K2a: (hash, genome) radix sort                                  */
-    double ms_index;        /* K2b: run detection, posting compaction, per-genome work lists   */
+    double ms_sort;         /* K2a: MSD partition (or the (hash, genome) radix sort of the general path) */
+    double ms_index;        /* K2b: grouping -> postings + per-genome work lists                */
     double ms_count;        /* K3+K4: pairwise shared-hash count fused with threshold/compact  */
     double ms_pairsort;     /* ordering of the flagged pairs by (i, j)                         */
     double ms_d2h;          /* pair-list device->host copy                                     */
@@ -87,6 +87,9 @@ typedef struct {
     uint64_t n_count_launches;   /* launches of the K3+K4 kernel                               */
     uint64_t n_kernel_launches;  /* launches of this library's own hand-written kernels         */
     uint64_t n_library_launches; /* launches it asked CUB for (radix sort / scan / reduce passes) */
+    /* partition path, per kernel (their sum + the small scans in between = ms_sort):              */
+    double ms_hist1, ms_scatter1, ms_hist2, ms_scatter2;
+    double ms_group;        /* k2_group alone (ms_index additionally holds k2_items when sharded)  */
 } ygpu_timings;
 
 /* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */

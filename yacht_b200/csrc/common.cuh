@@ -13,6 +13,7 @@ struct ygpu_ctx {
     int smem_optin = 0;          // max dynamic shared memory per CTA (opt-in), bytes
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evp[10] = {};     // per-kernel events of the partition path
     std::string err;
 
     // ---- sketches (flat, device resident) ---------------------------------------------------
@@ -23,6 +24,8 @@ struct ygpu_ctx {
     uint32_t* d_sizes = nullptr;    // [n]   sketch sizes
     uint32_t* d_gid = nullptr;      // [T]   genome id of every hash slot
     bool loaded = false;
+    bool maxkey_valid = false;      // largest resident hash: a property of the loaded sketches, computed once per load
+    uint64_t maxkey = 0;
 
     // ---- inverted index (K2 output) ---------------------------------------------------------
     bool indexed = false;
@@ -162,6 +165,7 @@ static inline int grid_for(ygpu_ctx* ctx, uint64_t work, int bs, int per_sm = 8)
 
 
 int ygpu_sort_sketches(ygpu_ctx* ctx);   // K2a (yacht_gpu.cu)
+int ygpu_max_hash(ygpu_ctx* ctx, uint64_t* maxkey);   // largest resident hash (cached per load)
 // MSD-partition index build (index_msd.cu): *used = 0 when the input does not qualify for it
 int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used);
 

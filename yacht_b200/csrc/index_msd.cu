@@ -301,18 +301,29 @@ struct GroupSmem {
     uint32_t* s_wsum;            // [8]
 };
 
+// `staged`: this bucket's words were prefetched into shared memory (cp.async issued during the previous bucket's
+// phase E, into the start2|SUB2 region, dead by then); bb_next / m_next: the bucket to prefetch during this one.
 template <int ITEMS, bool STREAM>
 __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t bb, const uint32_t m, const GroupSmem& sm,
-                                             uint32_t* s_pcur, uint32_t* s_gpos, GroupStats& st, GroupPending& pd) {
+                                             uint32_t* s_pcur, uint32_t* s_gpos, GroupStats& st, GroupPending& pd,
+                                             const bool staged, const uint32_t bb_next, const uint32_t m_next) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gmask = a.gb ? (uint32_t)((1ull << a.gb) - 1ull) : 0u;
     // ---- A: load, sub-bucket rank ------------------------------------------------------------------
     uint64_t e[ITEMS];
     uint32_t rk[ITEMS];
-    const uint64_t* src = a.ent + bb + tid;
+    uint64_t* stage = reinterpret_cast<uint64_t*>(sm.start2);      // [GK_FAST * GK_THREADS] words (start2 + SUB2: 10 KB)
+    if (ITEMS == GK_FAST && staged) {
+        asm volatile("cp.async.wait_all;" ::: "memory");           // each thread reads back exactly the words it copied
 #pragma unroll
-    for (int k = 0; k < ITEMS; k++)
-        if (k * GK_THREADS + tid < m) e[k] = src[k * GK_THREADS];
+        for (int k = 0; k < ITEMS; k++)
+            if (k * GK_THREADS + tid < m) e[k] = stage[k * GK_THREADS + tid];
+    } else {
+        const uint64_t* src = a.ent + bb + tid;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++)
+            if (k * GK_THREADS + tid < m) e[k] = src[k * GK_THREADS];
+    }
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
         if (k * GK_THREADS + tid < m) rk[k] = atomicAdd(&sm.cnt[(uint32_t)(e[k] >> a.sub_shift) & a.sub_mask], 1u);
@@ -406,6 +417,15 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     uint32_t* stg_g = sm.K2;                                                     // [BK_CAP]
     unsigned short* stg_rem = reinterpret_cast<unsigned short*>(sm.G2);          // [BK_CAP]
     const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
+    if (m_next && m_next <= GK_FAST * GK_THREADS) {      // start2 / SUB2 were last read in phase D: stage the next bucket there
+        const uint64_t* nsrc = a.ent + bb_next + tid;
+        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage + tid);
+#pragma unroll
+        for (int k = 0; k < GK_FAST; k++)
+            if (k * GK_THREADS + tid < m_next)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + k * GK_THREADS * 8), "l"(nsrc + k * GK_THREADS) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     if (STREAM && tid == 0) {        // claim this bucket's slice of the stream (the cursor is final: barrier above)
         const uint32_t np0 = *s_pcur;
         *s_gpos = np0 ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np0) : 0u;
@@ -471,13 +491,24 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     GroupStats st{0, 0, 0, 0ull};
     GroupPending pd{0ull, 0u, 0u, false};
     uint32_t par = 0;
-    for (uint32_t b = a.b_lo + blockIdx.x; b < a.b_hi; b += gridDim.x) {
-        const uint32_t bb = a.base[b];
-        const uint32_t m = a.base[b + 1] - bb;
-        if (m == 0) continue;      // uniform per CTA
-        if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd);
-        else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd);
-        par ^= 1;
+    uint32_t b = a.b_lo + blockIdx.x;
+    uint32_t bb = 0, m = 0;
+    if (b < a.b_hi) { bb = a.base[b]; m = a.base[b + 1] - bb; }
+    bool staged = false;
+    while (b < a.b_hi) {
+        // the next bucket's extent is fetched now and used in phase E, where its words are prefetched
+        const uint32_t bn = b + gridDim.x;
+        uint32_t bbn = 0, mn = 0;
+        if (bn < a.b_hi) { bbn = a.base[bn]; mn = a.base[bn + 1] - bbn; }
+        if (m) {                   // uniform per CTA
+            if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, staged, bbn, mn);
+            else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, false, bbn, mn);
+            par ^= 1;
+            staged = mn && mn <= GK_FAST * GK_THREADS;
+        } else {
+            staged = false;
+        }
+        b = bn; bb = bbn; m = mn;
     }
     if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;
     const unsigned long long heads = block_sum<GK_THREADS>(st.heads);
@@ -532,18 +563,8 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     cudaStream_t st = ctx->stream;
 
     // ---- plan -----------------------------------------------------------------------------------
-    uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
-    {
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-        ctx->tm.n_library_launches += 2;
-    }
     uint64_t maxkey = 0;
-    YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    YG_CHECK(ygpu_max_hash(ctx, &maxkey));
     MsdPlan p{};
     p.T = T;
     p.hb = std::max(1, bitlen(maxkey));
@@ -585,8 +606,10 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
 
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     // ---- level 1 ----------------------------------------------------------------------------------
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[0], st));
     k2_hist1<<<ctx->num_sms * 8, 256, p.nb1 * sizeof(uint32_t), st>>>(ctx->d_hashes, p, hist1);
     YG_CUDA(ctx, cudaGetLastError());
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[1], st));
     k2_prep1<<<1, 1024, 0, st>>>(hist1, p.nb1, base1, tile_start, cursor, ctx->d_scalars);
     YG_CUDA(ctx, cudaGetLastError());
     uint64_t T_mine = T;
@@ -625,8 +648,10 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1>, SC_THREADS, smem));
         const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[2], st));
         k2_scatter<1><<<grid, SC_THREADS, smem, st>>>(a, p, units1);
         YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[3], st));
     }
     ctx->tm.n_kernel_launches += 3;
     const uint64_t* final_ent = ctx->d_ent1;
@@ -637,6 +662,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         const int grid_h = ctx->num_sms * 8;
         k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p);
         YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[4], st));
         // final-bucket bases: a rank's own buckets are contiguous, foreign ones are empty -> positions are local
         size_t tb = 0;
         YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist2, base2, (int64_t)p.nfb + 1, st));
@@ -655,8 +681,10 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2>, SC_THREADS, smem));
         const int grid = ctx->num_sms * std::max(occ, 1);
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[5], st));
         k2_scatter<2><<<grid, SC_THREADS, smem, st>>>(a, p, 0);
         YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[6], st));
         ctx->tm.n_kernel_launches += 2;
         final_ent = ctx->d_ent2;
         final_base = base2;
@@ -699,12 +727,14 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GK_THREADS, smem));
         const uint64_t nbk = g.b_hi > g.b_lo ? g.b_hi - g.b_lo : 0;
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[7], st));
         if (nbk) {
             const int grid = (int)std::min<uint64_t>(nbk, (uint64_t)ctx->num_sms * std::max(occ, 1));
             kern<<<grid, GK_THREADS, smem, st>>>(g);
             YG_CUDA(ctx, cudaGetLastError());
             ctx->tm.n_kernel_launches += 1;
         }
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
     }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
@@ -715,6 +745,13 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     const uint64_t I = P - (sc[SC_HEADS] - sc[SC_SINGLE]);
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
     ctx->tm.ms_index += elapsed(ctx, 1, 2);
+    {
+        auto el = [&](int x, int y) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->evp[x], ctx->evp[y]); return (double)ms; };
+        ctx->tm.ms_hist1 += el(0, 1);
+        ctx->tm.ms_scatter1 += el(2, 3);
+        if (d2) { ctx->tm.ms_hist2 += el(3, 4); ctx->tm.ms_scatter2 += el(5, 6); }
+        ctx->tm.ms_group += el(7, 8);
+    }
     if (stream) {
         if (sc[SCM_STREAM] != P) return ygpu_fail(ctx, YGPU_ERR_CUDA, "group stream holds %llu entries, expected %llu", sc[SCM_STREAM], (unsigned long long)P);
         ctx->stream_entries = P;

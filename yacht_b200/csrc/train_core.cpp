@@ -169,14 +169,10 @@ int main(int argc, char** argv) {
     }
     show_arguments(args);
 
-    int ndev = ygpu_device_count();
-    if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) ndev = std::min(ndev, v); }
-    if (ndev < 1) {
-        std::cerr << "run_yacht_train_core: no CUDA device available; this build has no CPU path" << std::endl;
-        return 3;
-    }
-
-    // ---- read (the GPU contexts are created meanwhile: CUDA initialisation costs ~0.5 s per process) ----
+    // ---- read.  CUDA initialisation (~1 s per process on this class of host) and the creation of the GPU
+    //      contexts run in the background from the very start; parsed blocks are shipped to the GPU(s) while later
+    //      files are still being parsed: parser threads queue the ids of finished blocks, uploader threads --
+    //      started as soon as the contexts exist -- feed ygpu_upload_block.
     auto t_read = std::chrono::high_resolution_clock::now();
     std::cout << "Reading all sketches in filelist using all " << args.number_of_threads << " threads..." << std::endl;
     yingest::Ingest in;
@@ -188,66 +184,74 @@ int main(int argc, char** argv) {
     }
     const uint32_t n = (uint32_t)in.names.size();
     std::cout << "Total number of sketches to read: " << n << std::endl;
-    ndev = std::max(1, std::min<int>(ndev, (int)std::max<uint32_t>(n, 1)));
-    std::vector<ygpu_ctx*> ctxs(ndev, nullptr);
-    std::vector<DeviceResult> res(ndev);
-    std::vector<std::thread> ctx_threads;
-    // Parsed blocks are shipped to the GPU(s) while later files are still being parsed: parser threads queue the
-    // ids of finished blocks; uploader threads -- started as soon as the contexts exist -- feed ygpu_upload_block.
+    int ndev = 0;
+    std::vector<ygpu_ctx*> ctxs;
+    std::vector<DeviceResult> res;
     const bool stream_upload = !getenv("YACHT_NO_STREAM_UPLOAD");
     std::mutex q_mu;
     std::condition_variable q_cv;
     std::deque<uint32_t> q_blocks;
     bool q_done = false;
     std::atomic<int> upload_rc{0};
-    for (int d = 0; d < ndev; d++)
-        ctx_threads.emplace_back([&, d]() {
-            res[d].rc = ygpu_ctx_create(&ctxs[d], d);
-            if (res[d].rc) res[d].err = ygpu_last_error(nullptr);
-            else if (stream_upload) {
-                res[d].rc = ygpu_upload_begin(ctxs[d]);
-                if (res[d].rc) res[d].err = ygpu_last_error(ctxs[d]);
-            }
-        });
     std::vector<std::thread> uploaders;
-    std::thread upload_master;
-    if (stream_upload) {
+    if (stream_upload)
         in.on_block = [&](uint32_t b) {
             { std::lock_guard<std::mutex> lk(q_mu); q_blocks.push_back(b); }
             q_cv.notify_one();
         };
-        upload_master = std::thread([&]() {
-            for (auto& t : ctx_threads) t.join();              // contexts + bounce buffers ready
-            for (int d = 0; d < ndev; d++) if (res[d].rc) return;
-            const int nu = std::max(2, std::min(4, args.number_of_threads / 4));
-            for (int k = 0; k < nu; k++)
-                uploaders.emplace_back([&]() {
-                    for (;;) {
-                        uint32_t b;
-                        {
-                            std::unique_lock<std::mutex> lk(q_mu);
-                            q_cv.wait(lk, [&] { return !q_blocks.empty() || q_done; });
-                            if (q_blocks.empty()) return;
-                            b = q_blocks.front();
-                            q_blocks.pop_front();
-                        }
-                        for (int d = 0; d < ndev; d++) {
-                            const int rc = ygpu_upload_block(ctxs[d], b, in.blocks[b].data(), in.blocks[b].size());
-                            if (rc) upload_rc = rc;
-                        }
+    std::thread gpu_init([&]() {
+        int nd = ygpu_device_count();
+        if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) nd = std::min(nd, v); }
+        if (nd < 1) return;
+        nd = std::max(1, std::min<int>(nd, (int)std::max<uint32_t>(n, 1)));
+        ctxs.assign(nd, nullptr);
+        res.resize(nd);
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; d++)
+            th.emplace_back([&, d]() {
+                res[d].rc = ygpu_ctx_create(&ctxs[d], d);
+                if (res[d].rc) res[d].err = ygpu_last_error(nullptr);
+                else if (stream_upload) {
+                    res[d].rc = ygpu_upload_begin(ctxs[d]);
+                    if (res[d].rc) res[d].err = ygpu_last_error(ctxs[d]);
+                }
+            });
+        for (auto& t : th) t.join();
+        ndev = nd;
+        if (!stream_upload) return;
+        for (int d = 0; d < nd; d++) if (res[d].rc) return;
+        const int nu = std::max(2, std::min(4, args.number_of_threads / 4));
+        for (int k = 0; k < nu; k++)
+            uploaders.emplace_back([&, k, nu, nd]() {
+                yingest::pin_worker(k * std::max(1, args.number_of_threads / nu));   // unpinned helper threads starve here
+                for (;;) {
+                    uint32_t b;
+                    {
+                        std::unique_lock<std::mutex> lk(q_mu);
+                        q_cv.wait(lk, [&] { return !q_blocks.empty() || q_done; });
+                        if (q_blocks.empty()) return;
+                        b = q_blocks.front();
+                        q_blocks.pop_front();
                     }
-                });
-        });
-    }
+                    for (int d = 0; d < nd; d++) {
+                        const int rc = ygpu_upload_block(ctxs[d], b, in.blocks[b].data(), in.blocks[b].size());
+                        if (rc) upload_rc = rc;
+                    }
+                }
+            });
+    });
     yingest::read_sketches(in, args.number_of_threads, /*assemble_flat=*/false);
-    if (stream_upload) {
+    {
         { std::lock_guard<std::mutex> lk(q_mu); q_done = true; }
         q_cv.notify_all();
-        upload_master.join();
+        gpu_init.join();
         for (auto& t : uploaders) t.join();
     }
+    if (ndev < 1) {
+        std::cerr << "run_yacht_train_core: no CUDA device available; this build has no CPU path" << std::endl;
+        return 3;
+    }
     if (in.fatal) {
-        if (!stream_upload) for (auto& t : ctx_threads) t.join();
         std::cerr << "run_yacht_train_core: cannot parse signature " << in.fatal_msg << std::endl;
         return 4;
     }
@@ -263,7 +267,6 @@ int main(int argc, char** argv) {
     // ---- index + pairwise on the GPU(s) ----------------------------------------------------------
     auto t_index = std::chrono::high_resolution_clock::now();
     std::cout << "Building index from sketches..." << std::endl;
-    if (!stream_upload) for (auto& t : ctx_threads) t.join();
     std::vector<uint64_t> block_dst(in.blocks.size());
     for (size_t b = 0; b < in.blocks.size(); b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)];
     std::vector<const uint64_t*> block_ptrs(in.blocks.size());

@@ -92,6 +92,7 @@ extern "C" int ygpu_ctx_create(ygpu_ctx** out, int device) {
         return ygpu_fail(nullptr, YGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->evp) cudaEventCreate(&ev);
     if (cudaMalloc(&ctx->d_scalars, 64 * sizeof(unsigned long long)) != cudaSuccess) {
         ygpu_ctx_destroy(ctx);
         return ygpu_fail(nullptr, YGPU_ERR_NOMEM, "cudaMalloc(scalars) failed");
@@ -110,6 +111,7 @@ static void release_index(ygpu_ctx* ctx) {   // invalidate only: the buffers are
 static void release_sketches(ygpu_ctx* ctx) {
     release_index(ctx);
     ctx->loaded = false;
+    ctx->maxkey_valid = false;
     ctx->n = 0; ctx->T = 0;
 }
 
@@ -135,6 +137,7 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     if (ctx->d_temp) cudaFree(ctx->d_temp);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->evp) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -189,6 +192,10 @@ static int finish_load(ygpu_ctx* ctx) {
     }
     YG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->loaded = true;
+    if (ctx->T) {           // the largest hash decides the partition plan: a property of the resident sketches, taken at load
+        uint64_t mk = 0;
+        YG_CHECK(ygpu_max_hash(ctx, &mk));
+    }
     return 0;
 }
 
@@ -510,6 +517,24 @@ __global__ void __launch_bounds__(256) k_items_scatter(const uint32_t* __restric
     }
 }
 
+int ygpu_max_hash(ygpu_ctx* ctx, uint64_t* maxkey) {
+    if (!ctx->maxkey_valid) {
+        cudaStream_t st = ctx->stream;
+        uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)ctx->T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)ctx->T, st));
+        ctx->tm.n_library_launches += 2;
+        YG_CUDA(ctx, cudaMemcpyAsync(&ctx->maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->maxkey_valid = true;
+    }
+    *maxkey = ctx->maxkey;
+    return 0;
+}
+
 // K2a: stable radix sort of (hash, genome id); equal-hash runs become posting lists in ascending
 // genome order (slots are generated genome-major and the sort is stable).  Kept resident: the
 // run path (K5) walks the same sorted array.
@@ -521,18 +546,8 @@ int ygpu_sort_sketches(ygpu_ctx* ctx) {
     YG_CHECK(dev_alloc(ctx, &ctx->d_skey, T));
     YG_CHECK(dev_alloc(ctx, &ctx->d_sgid, T));
     if (T) {
-        uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
-        {
-            size_t tb = 0;
-            YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-            YG_CHECK(ygpu_temp_reserve(ctx, tb));
-            tb = ctx->temp_bytes;
-            YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
-            ctx->tm.n_library_launches += 2;
-        }
         uint64_t maxkey = 0;
-        YG_CUDA(ctx, cudaMemcpyAsync(&maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        YG_CHECK(ygpu_max_hash(ctx, &maxkey));
         int end_bit = 1;
         while (end_bit < 64 && (maxkey >> end_bit) != 0) end_bit++;
         size_t tb = 0;

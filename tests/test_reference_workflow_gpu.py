@@ -82,9 +82,14 @@ def test_full_workflow(fixture_files):
     txt = pd.read_csv(os.path.join(d, "results", "result_all.txt"), sep="\t")
     assert len(txt) == 1 and txt["organism_name"].iloc[0] == PRESENT
 
+    # the first run left the packed sketch cache next to the reference's intermediate files ...
+    assert os.path.exists(os.path.join(inter, "ygpu_cache", "meta.json"))
+    assert sorted(os.listdir(os.path.join(inter, "signatures"))) == sorted(m + ".sig" for m in manifest["md5sum"])   # ... and touched nothing else
+
     # --keep_raw adds the raw_result sheet with *_wo_coverage columns; default coverage list
     res = _yacht("run", "--json", expected[0], "--sample_file", sample_zip, "--outdir", d, "--keep_raw", "--show_all")
     assert res.returncode == 0, res.stderr[-3000:]
+    assert "Packed sketch cache found" in res.stdout + res.stderr          # second run: no signature file parsed
     sheets = xlsx.read_xlsx(abundance_file)
     # with the DEFAULT list the first element is the int 1 (argparse's type= is not applied to defaults), so the
     # reference names that sheet "min_coverage1" (run_YACHT.py:59,252) -- kept

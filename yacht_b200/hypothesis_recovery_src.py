@@ -25,7 +25,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import pandas as pd
 
-from . import _lib, sigio
+from . import _lib, dbcache, sigio
 from .utils import _log, decompress_all_sig_files, load_signature_with_ksize
 
 SIG_SUFFIX = ".sig"
@@ -49,9 +49,17 @@ def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str
     key = (path_to_genome_temp_dir, tuple(manifest["md5sum"]))
     if _loaded_key == key:
         return
-    hashes, offsets, n_bad = _lib.read_signatures(paths, max(1, int(num_threads)))
-    if n_bad:
-        _log("WARNING", f"{n_bad} reference signature file(s) could not be opened; they count as empty sketches")
+    md5sums = list(manifest["md5sum"])
+    cached = dbcache.load(path_to_genome_temp_dir, md5sums)
+    if cached is not None:
+        hashes, offsets = cached
+        _log("INFO", f"Packed sketch cache found ({len(md5sums)} genomes, {int(offsets[-1])} hashes): signature files are not parsed")
+    else:
+        hashes, offsets, n_bad = _lib.read_signatures(paths, max(1, int(num_threads)))
+        if n_bad:
+            _log("WARNING", f"{n_bad} reference signature file(s) could not be opened; they count as empty sketches")
+        else:
+            dbcache.store(path_to_genome_temp_dir, md5sums, hashes, offsets)
     _context().load_sketches(hashes, offsets)
     _loaded_key = key
 

@@ -48,6 +48,7 @@ struct ygpu_ctx {
     uint64_t* d_ent1 = nullptr;     // [T] packed (hash low bits | genome id) words, level-1 buckets
     uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
     uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
+    uint32_t* d_units = nullptr;    // level-2 tile descriptors (uint2 per tile)
     uint16_t* d_st_rem = nullptr;   // [T] group stream of a hash-range sharded build: members of the same group that follow
     uint64_t stream_entries = 0;    //     entries of the stream of the last ygpu_index_partial (genome ids are in d_post)
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path

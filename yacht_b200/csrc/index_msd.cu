@@ -105,6 +105,7 @@ struct ScatterArgs {
     const uint32_t* tile_start;  // level 2: prefix of tiles per level-1 bucket ([nb1] = number of units)
     uint32_t* cursor;            // per output bucket
     uint32_t* hist2;             // hist2 kernel only
+    const uint2* units;          // level 2: per tile {first word, words | level-1 bucket << 16} (k2_units)
 };
 
 template <int LEVEL>
@@ -118,18 +119,28 @@ __device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& 
         return true;
     }
     if (unit >= p.unit_hi || unit >= a.tile_start[p.nb1]) return false;
-    // level-1 bucket holding this tile: last b with tile_start[b] <= unit
-    uint32_t lo = 0, hi = p.nb1;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a.tile_start[mid] <= unit) lo = mid; else hi = mid;
-    }
-    b1 = lo;
-    const uint32_t k = unit - a.tile_start[lo];
-    const uint32_t bb = a.base1[lo], be = a.base1[lo + 1];
-    begin = (uint64_t)bb + (uint64_t)k * SC_TILE;
-    m = (uint32_t)min((uint64_t)SC_TILE, (uint64_t)be - begin);
+    const uint2 u = a.units[unit];      // resolved once by k2_units: a per-tile binary search here would put ~10 dependent
+    begin = u.x;                        // L2 round trips on the critical path of every tile
+    m = u.y & 0xffffu;
+    b1 = u.y >> 16;
     return true;
+}
+
+// one thread per level-2 tile: which level-1 bucket it belongs to and which words it covers
+__global__ void __launch_bounds__(256) k2_units(const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ base1, uint32_t nb1,
+                                                uint2* __restrict__ units) {
+    const uint32_t n_units = tile_start[nb1];
+    for (uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x; unit < n_units; unit += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = nb1;          // last bucket b with tile_start[b] <= unit
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (tile_start[mid] <= unit) lo = mid; else hi = mid;
+        }
+        const uint32_t k = unit - tile_start[lo];
+        const uint64_t begin = (uint64_t)base1[lo] + (uint64_t)k * SC_TILE;
+        const uint32_t m = (uint32_t)min((uint64_t)SC_TILE, (uint64_t)base1[lo + 1] - begin);
+        units[unit] = make_uint2((uint32_t)begin, m | (lo << 16));
+    }
 }
 
 __global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPlan p) {
@@ -659,6 +670,12 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     // ---- level 2 ----------------------------------------------------------------------------------
     if (d2) {
         a.in_ent = ctx->d_ent1; a.out_ent = ctx->d_ent2;
+        const uint64_t max_units = T / SC_TILE + p.nb1 + 1;
+        YG_CHECK(dev_alloc(ctx, &ctx->d_units, 2 * max_units));
+        k2_units<<<grid_for(ctx, max_units, 256, 8), 256, 0, st>>>(tile_start, base1, p.nb1, (uint2*)ctx->d_units);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 1;
+        a.units = (const uint2*)ctx->d_units;
         const int grid_h = ctx->num_sms * 8;
         k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p);
         YG_CUDA(ctx, cudaGetLastError());

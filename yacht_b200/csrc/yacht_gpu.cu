@@ -119,7 +119,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_skey); dev_free(ctx, &ctx->d_sgid); dev_free(ctx, &ctx->d_flag); dev_free(ctx, &ctx->d_cpos);
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
-    dev_free(ctx, &ctx->d_ovf_rows); dev_free(ctx, &ctx->d_st_rem);
+    dev_free(ctx, &ctx->d_ovf_rows); dev_free(ctx, &ctx->d_st_rem); dev_free(ctx, &ctx->d_units);
     dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);

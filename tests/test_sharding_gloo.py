@@ -68,3 +68,15 @@ def test_split_rows_by_work_properties():
         if n >= 100 * parts:
             loads = [float((w[b[k]:b[k + 1]] + sharding.ROW_CONSTANT).sum()) for k in range(parts)]
             assert max(loads) < 1.3 * (sum(loads) / parts)
+
+
+def test_slice_bounds_and_size_split():
+    b = sharding.slice_bounds(10, 4)
+    assert b.tolist() == [0, 3, 6, 9, 10]                      # equal slices, the last one short
+    assert sharding.slice_bounds(0, 3).tolist() == [0, 0, 0, 0]
+    assert sharding.slice_bounds(8, 1).tolist() == [0, 8]
+    off = np.array([0, 10, 10, 30, 60, 100], dtype=np.uint64)   # sizes 10, 0, 20, 30, 40
+    r = sharding.split_rows_by_size(off, 2)
+    assert r[0] == 0 and r[-1] == 5 and 0 < r[1] < 5
+    sizes = np.diff(off.astype(np.int64))
+    assert abs(int(sizes[:r[1]].sum()) - int(sizes[r[1]:].sum())) <= int(sizes.max()) + 2 * int(sharding.ROW_CONSTANT)

@@ -267,6 +267,7 @@ extern "C" int ygpu_load_sketch_blocks(ygpu_ctx* ctx, const uint64_t* const* blo
 // prefix sum), so a block is first uploaded to a staging chunk -- through a small pool of page-locked bounce
 // buffers, filled by the calling threads in parallel, DMA'd asynchronously -- and ygpu_upload_finish moves all
 // blocks to their places with one device-side copy kernel.
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 
@@ -286,7 +287,7 @@ struct UploadState {
     cudaStream_t bst[NB] = {};
     bool busy[NB] = {};
     uint64_t total = 0;
-    int failed = 0;
+    std::atomic<int> failed{0};
 };
 
 struct PlaceDesc { const uint64_t* src; uint64_t dst; uint64_t len; };

@@ -71,7 +71,7 @@ typedef struct {
     uint32_t max_sketch;    /* largest sketch size                                             */
     uint32_t has_duplicates;/* 1 if some sketch holds the same hash twice                      */
     uint32_t index_path;    /* 1 = MSD partition + shared-memory grouping, 0 = general sort path */
-    uint32_t _pad;
+    uint32_t big_buckets;   /* path 1: final buckets too large for shared memory, grouped by the sort-based side route */
 } ygpu_index_stats;
 
 /* Device timings (CUDA events on the context's stream) accumulated since ygpu_reset_timers(). */
@@ -141,7 +141,9 @@ int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* Tuning / test hooks: "force_tile_w" caps the accumulator tile width of the count kernel and
  * "force_u16" = 1 selects its packed 16-bit counters (both are otherwise chosen from N);
  * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default);
- * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic).   */
+ * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic);
+ * "big_buckets" = 0 sends a database with ANY oversized final bucket to the general path (default 1:
+ * only those buckets leave the partition path).                                                  */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

@@ -100,10 +100,29 @@ def test_row_ranges_union(gpu_ctx):
 
 
 def test_skewed_long_postings(gpu_ctx):
-    # conserved-core hashes present in many genomes: long posting lists, touched-list overflow; the
-    # buckets holding them overflow shared memory, so the build falls back to the general path
+    # conserved-core hashes present in many genomes: long posting lists, touched-list overflow.  The final buckets
+    # holding them overflow shared memory: only those buckets leave the partition path (sort-based side route) ...
     db = synth.make_reference_db(6000, 9, mean_size=60, sd_size=10, min_size=20, core_hashes=6, core_lo=0.7, core_hi=0.95)
-    _check(gpu_ctx, db, 0.05, expect_path=0)
+    st, _ = _check(gpu_ctx, db, 0.05, expect_path=1)
+    assert 1 <= st["big_buckets"] <= 6
+    # ... and with the side route switched off the whole database falls back to the general path
+    gpu_ctx.set_option("big_buckets", 0)
+    try:
+        _check(gpu_ctx, db, 0.05, expect_path=0)
+    finally:
+        gpu_ctx.set_option("big_buckets", 1)
+
+
+def test_oversized_buckets_with_duplicates_and_two_levels(gpu_ctx):
+    # two partition levels (d2 > 0), several core hashes in > 3 072 genomes each, one sketch holding a core hash twice
+    db = synth.make_reference_db(9000, 23, mean_size=300, sd_size=60, min_size=100, core_hashes=4, core_lo=0.5, core_hi=0.9)
+    parts = [db.sketch(g) for g in range(db.n)]
+    core = np.intersect1d(np.intersect1d(parts[0], parts[1]), parts[2])
+    if core.size:
+        parts[1] = np.concatenate([parts[1], core[:1]])
+    db2 = synth.from_sketches(parts)
+    st, _ = _check(gpu_ctx, db2, 0.02, expect_path=1)
+    assert st["big_buckets"] >= 1
 
 
 def test_long_groups_inside_msd_buckets(gpu_ctx):

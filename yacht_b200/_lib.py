@@ -33,7 +33,7 @@ class IndexStats(ctypes.Structure):
     _fields_ = [("n_hashes", ctypes.c_uint64), ("n_distinct", ctypes.c_uint64), ("n_singleton", ctypes.c_uint64),
                 ("n_index", ctypes.c_uint64), ("n_postings", ctypes.c_uint64), ("n_increments", ctypes.c_uint64),
                 ("n_row_items", ctypes.c_uint64), ("max_sketch", ctypes.c_uint32), ("has_duplicates", ctypes.c_uint32),
-                ("index_path", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
+                ("index_path", ctypes.c_uint32), ("big_buckets", ctypes.c_uint32)]
 
     def as_dict(self) -> dict:
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -49,6 +49,13 @@ struct ygpu_ctx {
     uint64_t* d_ent2 = nullptr;     // [T] same, final buckets
     uint32_t* d_msd_aux = nullptr;  // histograms / bases / cursors
     uint32_t* d_units = nullptr;    // level-2 tile descriptors (uint2 per tile)
+    // final buckets too large for shared memory (k2_big_*): their list, compact starts, gathered / sorted words
+    uint32_t* d_big_list = nullptr;
+    uint64_t* d_big_cstart = nullptr;
+    uint64_t* d_big_a = nullptr;
+    uint64_t* d_big_b = nullptr;
+    int big_buckets = 1;            // option: 0 = any oversized bucket sends the whole database to the general path
+    uint32_t msd_big_buckets = 0;   // oversized buckets of the last build
     uint16_t* d_st_rem = nullptr;   // [T] group stream of a hash-range sharded build: members of the same group that follow
     uint64_t stream_entries = 0;    //     entries of the stream of the last ygpu_index_partial (genome ids are in d_post)
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
         const uint32_t bn = b + gridDim.x;
         uint32_t bbn = 0, mn = 0;
         if (bn < a.b_hi) { bbn = a.base[bn]; mn = a.base[bn + 1] - bbn; }
-        if (m) {                   // uniform per CTA
+        if (m && m <= BK_CAP) {    // uniform per CTA (larger buckets: k2_big_*, below)
             if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, staged, bbn, mn);
             else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, false, bbn, mn);
             par ^= 1;
@@ -531,6 +531,92 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
         if (single) atomicAdd(&a.scal[SC_SINGLE], single);
         if (w) atomicAdd(&a.scal[SC_W], w);
         if (dups) atomicAdd(&a.scal[SC_DUPS], dups);
+    }
+}
+
+// ---- final buckets that do not fit shared memory (hashes held by thousands of genomes) ----------------------
+// Only their words leave the partition path: they are gathered into one compact array under the key
+// (bucket ordinal | remaining hash bits | genome id), sorted by one device-wide radix sort, and grouped by
+// neighbour comparison -- same outputs as k2_group (postings, work items appended to the genome lists, the
+// statistics), postings stored behind the T regular slots of d_post.  Everything else stays on the fast path.
+constexpr uint32_t BIG_MAX = 4096;      // more oversized buckets than this: the general (sort) path takes the database
+
+__global__ void __launch_bounds__(256) k2_big_list(const uint32_t* __restrict__ base, uint32_t b_lo, uint32_t b_hi,
+                                                   uint32_t* __restrict__ list, unsigned long long* __restrict__ scal) {
+    for (uint32_t b = b_lo + blockIdx.x * blockDim.x + threadIdx.x; b < b_hi; b += gridDim.x * blockDim.x) {
+        const uint32_t m = base[b + 1] - base[b];
+        if (m > BK_CAP) {
+            const unsigned long long k = atomicAdd(&scal[SCM_STREAM], 1ull);       // (slot unused outside stream mode)
+            if (k < BIG_MAX) list[k] = b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k2_big_gather(const uint64_t* __restrict__ ent, const uint32_t* __restrict__ base,
+                                                     const uint32_t* __restrict__ list, const uint64_t* __restrict__ cstart, uint32_t n_big,
+                                                     int low_bits, uint64_t* __restrict__ out) {
+    const uint64_t lowmask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
+    for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
+        const uint32_t b = list[j];
+        const uint64_t bb = base[b], m = base[b + 1] - base[b], dst = cstart[j];
+        const uint64_t tag = low_bits >= 64 ? 0ull : ((uint64_t)j << low_bits);
+        for (uint64_t i = threadIdx.x; i < m; i += blockDim.x) out[dst + i] = tag | (ent[bb + i] & lowmask);
+    }
+}
+
+// first slot e > s whose (word >> gb) differs (exponential probe, then bisection)
+__device__ __forceinline__ uint64_t big_run_end(const uint64_t* __restrict__ S, uint64_t s, uint64_t n, int gb) {
+    const uint64_t k = S[s] >> gb;
+    uint64_t lo = s, step = 1, hi = s + 1;
+    while (hi < n && (S[hi] >> gb) == k) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > n) hi = n;
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if ((S[mid] >> gb) == k) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+__global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict__ S, uint64_t n, int gb, uint64_t post_base, int can_inline,
+                                                     uint32_t* __restrict__ post, const uint64_t* __restrict__ row_off,
+                                                     unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items,
+                                                     unsigned long long* __restrict__ scal) {
+    const uint64_t gmask = gb ? ((1ull << gb) - 1ull) : 0ull;
+    unsigned long long heads = 0, singles = 0, dups = 0, w = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = S[i], k = x >> gb;
+        const bool peq = i > 0 && (S[i - 1] >> gb) == k;
+        const bool neq = i + 1 < n && (S[i + 1] >> gb) == k;
+        heads += !peq;
+        singles += !peq && !neq;
+        if (!peq && !neq) continue;
+        const uint32_t g = (uint32_t)(x & gmask);
+        const uint64_t rem = big_run_end(S, i, n, gb) - i - 1;
+        post[post_base + i] = g;
+        w += 2ull * rem + 1ull;                       // summed over a run of L members: L^2
+        if (peq && (uint32_t)(S[i - 1] & gmask) == g) dups++;
+        if (rem) {
+            uint64_t item;
+            if (can_inline && rem <= 3) {
+                item = rem | ((S[i + 1] & gmask) << 2);
+                if (rem >= 2) item |= (S[i + 2] & gmask) << 22;
+                if (rem >= 3) item |= (S[i + 3] & gmask) << 42;
+            } else {
+                item = ((post_base + i + 1) << 32) | (rem << 2);
+            }
+            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            row_items[row_off[g] + slot] = item;
+        }
+    }
+    heads = block_sum<256>(heads);
+    singles = block_sum<256>(singles);
+    dups = block_sum<256>(dups);
+    w = block_sum<256>(w);
+    if (threadIdx.x == 0) {
+        if (heads) atomicAdd(&scal[SC_HEADS], heads);
+        if (singles) atomicAdd(&scal[SC_SINGLE], singles);
+        if (dups) atomicAdd(&scal[SC_DUPS], dups);
+        if (w) atomicAdd(&scal[SC_W], w);
     }
 }
 
@@ -712,13 +798,47 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];   // (level-1 maximum: over all digits, a safe bound)
+    const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
+    uint32_t n_big = 0;
+    uint64_t N_big = 0;
+    std::vector<uint32_t> big_list;
+    std::vector<uint64_t> big_cstart;
+    const int low_bits = (p.kb1 - d2) + p.gb;          // what distinguishes two words of one final bucket
     if (largest > BK_CAP) {
-        ctx->msd_fallbacks++;
-        return 0;                                   // skewed: the general (sort) path handles it
+        // some final buckets do not fit shared memory.  Sharded builds and option big_buckets = 0 leave the whole
+        // database to the general (sort) path; otherwise only those buckets take the k2_big_* route.
+        bool ok = !stream && ctx->big_buckets != 0;
+        if (ok) {
+            YG_CHECK(dev_alloc(ctx, &ctx->d_big_list, (uint64_t)BIG_MAX));
+            YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_STREAM], 0, sizeof(unsigned long long), st));
+            k2_big_list<<<grid_for(ctx, nbuckets, 256, 8), 256, 0, st>>>(final_base, 0, nbuckets, ctx->d_big_list, ctx->d_scalars);
+            YG_CUDA(ctx, cudaGetLastError());
+            unsigned long long nb = 0;
+            YG_CUDA(ctx, cudaMemcpyAsync(&nb, &ctx->d_scalars[SCM_STREAM], sizeof nb, cudaMemcpyDeviceToHost, st));
+            YG_CUDA(ctx, cudaStreamSynchronize(st));
+            ok = nb >= 1 && nb <= BIG_MAX && low_bits + bitlen(nb - 1) <= 64;
+            if (ok) {
+                n_big = (uint32_t)nb;
+                big_list.resize(n_big);
+                YG_CUDA(ctx, cudaMemcpy(big_list.data(), ctx->d_big_list, (size_t)n_big * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+                std::sort(big_list.begin(), big_list.end());          // deterministic ordinals
+                std::vector<uint32_t> hb(nbuckets + 1);
+                YG_CUDA(ctx, cudaMemcpy(hb.data(), final_base, ((size_t)nbuckets + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+                big_cstart.assign((size_t)n_big + 1, 0);
+                for (uint32_t j = 0; j < n_big; j++) big_cstart[j + 1] = big_cstart[j] + (hb[big_list[j] + 1] - hb[big_list[j]]);
+                N_big = big_cstart[n_big];
+                ok = N_big < (1ull << 30) && T + N_big + 4 < (1ull << 32);
+            }
+            YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_STREAM], 0, sizeof(unsigned long long), st));
+        }
+        if (!ok) {
+            ctx->msd_fallbacks++;
+            return 0;                               // the general (sort) path handles it
+        }
     }
 
     // ---- buckets -> postings + per-genome work lists (or the group stream) ------------------------------
-    YG_CHECK(dev_alloc(ctx, &ctx->d_post, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_post, T + N_big));
     if (stream) {
         YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, T));
     } else {
@@ -752,6 +872,31 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
             ctx->tm.n_kernel_launches += 1;
         }
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
+    }
+    if (n_big) {
+        // oversized buckets: gather under (ordinal | remaining hash bits | genome id), one device-wide sort, neighbour grouping
+        YG_CHECK(dev_alloc(ctx, &ctx->d_big_a, N_big));
+        YG_CHECK(dev_alloc(ctx, &ctx->d_big_b, N_big));
+        YG_CHECK(dev_alloc(ctx, &ctx->d_big_cstart, (uint64_t)n_big + 1));
+        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_list, big_list.data(), (size_t)n_big * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_cstart, big_cstart.data(), ((size_t)n_big + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        k2_big_gather<<<(unsigned)std::min<uint32_t>(n_big, (uint32_t)ctx->num_sms * 8), 256, 0, st>>>(final_ent, final_base, ctx->d_big_list, ctx->d_big_cstart,
+                                                                                                    n_big, low_bits, ctx->d_big_a);
+        YG_CUDA(ctx, cudaGetLastError());
+        const int end_bit = std::min(64, low_bits + bitlen((uint64_t)n_big - 1));
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)N_big, 0, std::max(end_bit, 1), st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)N_big, 0, std::max(end_bit, 1), st));
+        ctx->tm.n_library_launches += 2 + (std::max(end_bit, 1) + 7) / 8;
+        k2_big_groups<<<grid_for(ctx, N_big, 256, 8), 256, 0, st>>>(ctx->d_big_b, N_big, p.gb, T, p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_post,
+                                                                    ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items, ctx->d_scalars);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 3;
+        ctx->msd_big_buckets = n_big;
+    } else {
+        ctx->msd_big_buckets = 0;
     }
     unsigned long long sc[16];
     YG_CUDA(ctx, cudaMemcpyAsync(sc, ctx->d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));

@@ -120,6 +120,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_post); dev_free(ctx, &ctx->d_rem); dev_free(ctx, &ctx->d_row_ptr); dev_free(ctx, &ctx->d_row_items);
     dev_free(ctx, &ctx->d_row_work); dev_free(ctx, &ctx->d_row_cnt);
     dev_free(ctx, &ctx->d_ovf_rows); dev_free(ctx, &ctx->d_st_rem); dev_free(ctx, &ctx->d_units);
+    dev_free(ctx, &ctx->d_big_list); dev_free(ctx, &ctx->d_big_cstart); dev_free(ctx, &ctx->d_big_a); dev_free(ctx, &ctx->d_big_b);
     dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
@@ -607,6 +608,7 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
             for (uint32_t v : sz) mx = std::max(mx, v);
             S.max_sketch = mx;
             S.index_path = 1;
+            S.big_buckets = ctx->msd_big_buckets;
             ctx->stats = S;
             ctx->indexed = true;
             ctx->last_index_path = 1;
@@ -1282,6 +1284,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "force_u16")) { ctx->force_u16 = (int)value; return 0; }
     if (!strcmp(name, "index_path")) { ctx->index_path = (int)value; return 0; }
     if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
+    if (!strcmp(name, "big_buckets")) { ctx->big_buckets = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

@@ -18,9 +18,10 @@ def _pairs_tuple(p):
     return [(int(a), int(b), int(c)) for a, b, c in zip(p["i"], p["j"], p["count"])]
 
 
-def _check(ctx, db, thr, expect_path=None):
+def _check(ctx, db, thr, expect_path=None, ref=None):
     """Both index builds (1 = MSD partition when the input qualifies, 0 = general sort path) against the oracle."""
-    ref = to.oracle_train(db.hashes, db.offsets, thr)
+    if ref is None:
+        ref = to.oracle_train(db.hashes, db.offsets, thr)
     out = None
     for path in (1, 0):
         ctx.set_option("index_path", path)
@@ -103,19 +104,22 @@ def test_skewed_long_postings(gpu_ctx):
     # conserved-core hashes present in many genomes: long posting lists, touched-list overflow.  The final buckets
     # holding them overflow shared memory: only those buckets leave the partition path (sort-based side route) ...
     db = synth.make_reference_db(6000, 9, mean_size=60, sd_size=10, min_size=20, core_hashes=6, core_lo=0.7, core_hi=0.95)
-    st, _ = _check(gpu_ctx, db, 0.05, expect_path=1)
+    st, got = _check(gpu_ctx, db, 0.05, expect_path=1)
     assert 1 <= st["big_buckets"] <= 6
-    # ... and with the side route switched off the whole database falls back to the general path
+    # ... and with the side route switched off the whole database falls back to the general path (same answer)
     gpu_ctx.set_option("big_buckets", 0)
     try:
-        _check(gpu_ctx, db, 0.05, expect_path=0)
+        gpu_ctx.load_sketches(db.hashes, db.offsets)
+        st0 = gpu_ctx.build_index()
+        assert st0["index_path"] == 0 and st0["big_buckets"] == 0
+        assert gpu_ctx.pairwise_flag(0.05).tobytes() == got.tobytes()
     finally:
         gpu_ctx.set_option("big_buckets", 1)
 
 
 def test_oversized_buckets_with_duplicates_and_two_levels(gpu_ctx):
-    # two partition levels (d2 > 0), several core hashes in > 3 072 genomes each, one sketch holding a core hash twice
-    db = synth.make_reference_db(9000, 23, mean_size=300, sd_size=60, min_size=100, core_hashes=4, core_lo=0.5, core_hi=0.9)
+    # two partition levels (d2 > 0), core hashes in 3 500-4 500 genomes each (> 3 072), one sketch holding a core hash twice
+    db = synth.make_reference_db(5000, 23, mean_size=300, sd_size=60, min_size=100, core_hashes=3, core_lo=0.7, core_hi=0.9)
     parts = [db.sketch(g) for g in range(db.n)]
     core = np.intersect1d(np.intersect1d(parts[0], parts[1]), parts[2])
     if core.size:

@@ -53,7 +53,18 @@ class TrainResult:
     n_index: int
     n_postings: int = 0
     n_increments: int = 0
-    lines: Optional[List[str]] = None   # pair-file lines, sorted
+    _lines: Optional[List[str]] = None
+
+    @property
+    def lines(self) -> List[str]:
+        """Pair-file lines, sorted (formatted on first use: a threshold-0 run can hold tens of millions of pairs)."""
+        if self._lines is None:
+            self._lines = sorted(format_pairs(self.pairs))
+        return self._lines
+
+    @lines.setter
+    def lines(self, value: List[str]) -> None:
+        self._lines = value
 
 
 def build(quiet: bool = True) -> None:
@@ -110,7 +121,6 @@ def oracle_train(hashes: np.ndarray, offsets: np.ndarray, thr: float) -> TrainRe
                           n_postings=int(res.n_postings), n_increments=int(res.n_increments))
     finally:
         lib.yo_free_result(ctypes.byref(res))
-    out.lines = sorted(format_pairs(out.pairs))
     return out
 
 
@@ -152,7 +162,7 @@ def parse_core_outputs(workdir: str, paths: List[str], selected_file: str, stdou
     return TrainResult(pairs=np.zeros(0, dtype=PAIR_DTYPE),
                        selected=np.array([idx[p] for p in sel_paths], dtype=np.int32),
                        n_distinct=stats["distinct"], n_singleton=stats["single"], n_index=stats["index"],
-                       lines=sorted(lines))
+                       _lines=sorted(lines))
 
 
 def run_core_binary(binary: str, filelist: str, workdir: str, thr: float, threads: int = 1, passes: int = 1,

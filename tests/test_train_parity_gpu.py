@@ -14,8 +14,22 @@ pytestmark = pytest.mark.gpu
 THR = 0.95 ** 31
 
 
+class _Pairs:
+    """(i, j, count) triples of a pair list, compared field by field with numpy (a threshold that flags most pairs
+    yields tens of millions of them); on a mismatch the assertion shows the first differing triples."""
+
+    def __init__(self, p):
+        self.t = np.stack([np.asarray(p[f], dtype=np.int64) for f in ("i", "j", "count")], axis=1) if len(p) else np.zeros((0, 3), np.int64)
+
+    def __eq__(self, other):
+        return self.t.shape == other.t.shape and bool(np.array_equal(self.t, other.t))
+
+    def __repr__(self):
+        return f"<{len(self.t)} pairs, first {self.t[:5].tolist()}>"
+
+
 def _pairs_tuple(p):
-    return [(int(a), int(b), int(c)) for a, b, c in zip(p["i"], p["j"], p["count"])]
+    return _Pairs(p)
 
 
 def _check(ctx, db, thr, expect_path=None, ref=None):

@@ -97,7 +97,7 @@ def load_sketches_sharded(ctx, pinned_slice, offsets: np.ndarray, total: int, ra
     if world > 1:
         dist.all_gather_into_tensor(full, mine, group=group)
     d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.uint64).view(np.int64)).to(device, non_blocking=True)
-    torch.cuda.current_stream(device).synchronize()      # the library works on its own stream
+    _sync(device)                                        # the library works on its own stream
     ctx.load_sketches_device(full.data_ptr(), d_off.data_ptr(), int(offsets.shape[0]) - 1)
     return full
 
@@ -109,6 +109,13 @@ def split_rows_by_size(offsets: np.ndarray, nparts: int) -> np.ndarray:
     """Contiguous row ranges holding nearly equal numbers of sketch hashes (known before any index exists)."""
     sizes = np.diff(np.asarray(offsets).astype(np.int64)).astype(np.float64)
     return split_rows_by_work(sizes, nparts)
+
+
+def _sync(device) -> None:
+    """Order torch's stream against the library's (CUDA devices only; the gloo tests run the same code on CPU tensors)."""
+    import torch
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
 
 
 _stream_buffers = {}     # (device index, world) -> (gid, rem) device tensors reused across builds
@@ -158,12 +165,12 @@ def build_index_sharded(ctx, offsets: np.ndarray, rank: int, world: int, device,
     mine_g, mine_r = gid[rank * m: (rank + 1) * m], rem[rank * m: (rank + 1) * m]
     if n_r < m:                                            # padding of this rank's slice: follow-count 0 = ignored
         mine_r[n_r:].zero_()
-    torch.cuda.current_stream(device).synchronize()        # the library writes on its own stream
+    _sync(device)                                          # the library writes on its own stream
     ctx.index_stream_copy(mine_g.data_ptr(), mine_r.data_ptr())
     if world > 1:
         dist.all_gather_into_tensor(gid, mine_g, group=group)
         dist.all_gather_into_tensor(rem.view(torch.uint8), mine_r.view(torch.uint8), group=group)   # NCCL has no int16
-        torch.cuda.current_stream(device).synchronize()
+        _sync(device)
     if bounds is None:
         bounds = split_rows_by_size(offsets, world)
     rb, re = int(bounds[rank]), int(bounds[rank + 1])

@@ -27,6 +27,8 @@ namespace sigscan {
 
 enum Status { OK = 0, CANNOT_OPEN = 1, MALFORMED = 2 };
 
+static const uint64_t kPow10[9] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull};
+
 struct Scanner {
     const char* p;
     const char* end;
@@ -78,19 +80,59 @@ struct Scanner {
         return true;
     }
 
-    // p at '[' of the mins array
+    // eight ASCII digits (first digit in the lowest byte) -> their value; SWAR, no per-digit loop
+    // number of leading (lowest-address) bytes of c that are ASCII digits, 0..8
+    static inline uint32_t leading_digits(uint64_t c) {
+        const uint64_t t = c ^ 0x3030303030303030ull;                                         // digits -> 0..9
+        const uint64_t nondigit = ((t + 0x7676767676767676ull) | t) & 0x8080808080808080ull;   // high bit where t >= 10
+        return nondigit ? (uint32_t)(__builtin_ctzll(nondigit) >> 3) : 8u;
+    }
+    // the k (1..7) leading digits of c as an eight-digit field with leading '0's
+    static inline uint64_t pad_digits(uint64_t c, uint32_t k) {
+        return k == 8 ? c : ((c << (8u * (8u - k))) | (0x3030303030303030ull >> (8u * k)));
+    }
+    static inline uint64_t parse_eight(uint64_t c) {
+        c -= 0x3030303030303030ull;
+        c = (c * 10u) + (c >> 8);                                            // pairs of digits
+        return (((c & 0x000000FF000000FFull) * (100u + (1000000ull << 32))) +
+                (((c >> 16) & 0x000000FF000000FFull) * (1u + (10000ull << 32)))) >> 32;
+    }
+
+    // p at '[' of the mins array.  Hashes at scaled = 1000 are 13-17 digit literals: the digits are converted eight
+    // at a time (same value modulo 2^64 as digit-by-digit accumulation); anything that is not a plain unsigned literal
+    // takes the general route below.
     bool uint_array(std::vector<uint64_t>& out) {
         if (p >= end || *p != '[') return fail("\"mins\" is not an array");
         p++;
         for (;;) {
-            ws();
+            if (p < end && *p == ',') p++;                    // the common separator, no whitespace
+            else {
+                ws();
+                if (p >= end) return fail("unterminated \"mins\" array");
+                if (*p == ']') { p++; return true; }
+                if (*p == ',') { p++; continue; }
+            }
             if (p >= end) return fail("unterminated \"mins\" array");
-            if (*p == ']') { p++; return true; }
-            if (*p == ',') { p++; continue; }
             const char* s = p;
             uint64_t v = 0;
+            if (end - p >= 16) {
+                uint64_t c;
+                memcpy(&c, p, 8);
+                uint32_t k = leading_digits(c);
+                if (k == 8) {
+                    v = parse_eight(c);
+                    p += 8;
+                    memcpy(&c, p, 8);
+                    k = leading_digits(c);
+                    if (k) { v = v * kPow10[k] + parse_eight(pad_digits(c, k)); p += k; }
+                } else if (k) {
+                    v = parse_eight(pad_digits(c, k));
+                    p += k;
+                }
+            }
             while (p < end && (unsigned)(*p - '0') <= 9u) { v = v * 10u + (uint64_t)(*p - '0'); p++; }
             if (p == s || (p < end && (*p == '.' || *p == 'e' || *p == 'E'))) {
+                if (p == s && (*p == ']' || *p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) continue;   // "[ ]", ", ]": the top of the loop decides
                 // signed or floating literal: the reference casts whatever number it finds
                 char* q = nullptr;
                 errno = 0;

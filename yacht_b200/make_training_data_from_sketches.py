@@ -51,14 +51,8 @@ def main(args):
     os.makedirs(path_to_temp_dir, exist_ok=True)
 
     _log("INFO", "Unzipping the sourmash signature file to the temporary directory")
-    with zipfile.ZipFile(ref_file, "r") as sourmash_db:
-        sourmash_db.extractall(path_to_temp_dir)
-    all_gz_files = glob.glob(f"{path_to_temp_dir}/signatures/*.sig.gz")
-    _log("INFO", f"Decompressing {len(all_gz_files)} .sig.gz files using {num_threads} threads.")
-    utils.decompress_all_sig_files(all_gz_files, num_threads)
-
-    _log("INFO", "Extracting signature information")
-    sig_info_dict = utils.collect_signature_info(num_threads, ksize, path_to_temp_dir)
+    # reference :109-119 (extractall, gunzip pool, collect_signature_info) as ONE parallel pass over the zip members
+    sig_info_dict = utils.extract_signatures_and_info(ref_file, path_to_temp_dir, ksize, num_threads)
     _log("INFO", "Checking if all signatures have the same scaled")
     scale_set = set([value[-2] for value in sig_info_dict.values()])
     if len(scale_set) != 1:

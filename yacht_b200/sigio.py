@@ -166,6 +166,19 @@ def sig_info(sig_file: str, ksize: int):
         return None
 
 
+def sig_info_from_text(text: str, sig_file: str, ksize: int):
+    """:func:`sig_info` for a signature document that is already in memory (`sig_file` is the path it was, or is
+    being, written to): same selection rule -- exactly one non-empty sketch of that k-mer size -- same tuple."""
+    try:
+        sigs = [s for s in parse_signature_json(text, sig_file) if s.ksize == ksize]
+        if len(sigs) != 1 or len(sigs[0]) == 0:
+            return None
+        sig = sigs[0]
+        return (sig_file, sig.name, sig.md5sum, sig.mean_abundance, len(sig), sig.scaled)
+    except Exception:
+        return None
+
+
 def signature_json(name: str, mins: Sequence[int], ksize: int = 31,
                    abundances: Optional[Sequence[int]] = None,
                    max_hash: int = MAX_HASH_SCALED_1000, filename: str = "") -> str:

@@ -13,6 +13,7 @@ Same names, argument meaning and error behaviour as the reference functions they
 from __future__ import annotations
 
 import gzip
+import zipfile
 import os
 import shutil
 import sys
@@ -70,6 +71,70 @@ def collect_signature_info(num_threads: int, ksize: int, path_to_temp_dir: str) 
     else:
         signatures = [get_info_from_single_sig(f, ksize) for f in files]
     return {sig[1]: (sig[2], sig[3], sig[4], sig[5], sig[0]) for sig in signatures if sig}
+
+
+# ---- `yacht train` ingest in one pass ----------------------------------------------------------------------------
+# The reference unzips the database (make_training_data_from_sketches.py:109-111), gunzips every member in a pool
+# (:115, utils.py:482-509) and then loads every file again through sourmash to collect its info (:119,
+# utils.py:201-221): three passes over ~85k files.  Here each worker takes a slice of the zip members and does
+# all of it while the bytes are in memory: read member -> gunzip -> write signatures/<name>.sig -> info tuple.
+# The directory ends up exactly as the reference leaves it.
+_zip_handle = None
+
+
+def _extract_chunk(args):
+    zip_path, members, dest, ksize = args
+    global _zip_handle
+    if _zip_handle is None or _zip_handle[0] != zip_path:
+        _zip_handle = (zip_path, zipfile.ZipFile(zip_path, "r"))
+    z = _zip_handle[1]
+    out = []
+    for m in members:
+        raw = z.read(m)
+        target = os.path.join(dest, m)
+        if m.endswith(".sig.gz"):
+            target = target[:-3]                                  # the reference gunzips in place and drops the .gz
+            if raw[:2] == b"\x1f\x8b":
+                raw = gzip.decompress(raw)
+        with open(target, "wb") as f:
+            f.write(raw)
+        try:
+            text = raw.decode()
+        except UnicodeDecodeError:
+            text = None
+        info = sigio.sig_info_from_text(text, target, ksize) if text is not None else None
+        out.append((target, info))
+    return out
+
+
+def extract_signatures_and_info(ref_zip: str, path_to_temp_dir: str, ksize: int, num_threads: int) -> Dict[str, Tuple[str, float, int, int, str]]:
+    """Unzip + gunzip + collect_signature_info in one parallel pass; returns what collect_signature_info returns."""
+    with zipfile.ZipFile(ref_zip, "r") as z:
+        names = z.namelist()
+        sig_members = [n for n in names if n.startswith("signatures/") and not n.endswith("/") and "/" not in n[len("signatures/"):]]
+        taken = set(sig_members)
+        for n in names:                                           # manifest and anything else: plain extraction
+            if n not in taken:
+                z.extract(n, path_to_temp_dir)
+    os.makedirs(os.path.join(path_to_temp_dir, "signatures"), exist_ok=True)
+    _log("INFO", f"Decompressing {sum(1 for n in sig_members if n.endswith('.sig.gz'))} .sig.gz files using {num_threads} threads.")
+    _log("INFO", "Extracting signature information")
+    nproc = max(1, int(num_threads))
+    chunk = max(1, min(256, (len(sig_members) + 4 * nproc - 1) // (4 * nproc)))
+    jobs = [(ref_zip, sig_members[a:a + chunk], path_to_temp_dir, ksize) for a in range(0, len(sig_members), chunk)]
+    if nproc > 1 and len(sig_members) > 64:
+        with Pool(nproc) as p:
+            parts = p.map(_extract_chunk, jobs)
+    else:
+        parts = [_extract_chunk(j) for j in jobs]
+    info = {}
+    for part in parts:
+        for target, sig in part:
+            if sig:
+                info[sig[1]] = (sig[2], sig[3], sig[4], sig[5], sig[0])
+            else:
+                _log("WARNING", f"CANNOT extract the relevant info from the signature file: {target}")
+    return info
 
 
 def _gunzip_one(path: str) -> str:

@@ -217,6 +217,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

@@ -10,16 +10,19 @@
 //      by the level-1 bucket, so 55 - d1 + ceil(log2 N) bits fit --
 //   2. partitions the words by the leading d1 and then the next d2 hash bits into ~T/1500 final
 //      buckets (two coalesced scatter passes of 8 bytes per element, tile-staged in shared memory),
-//   3. groups equal hashes inside each bucket with a shared-memory hash table (one 16-bit CAS per
-//      element; no ordering of the ~80 % singleton hashes is ever computed), sorts only the members
-//      of shared groups by genome id, and emits compact postings + per-genome work records.
+//   3. groups equal hashes inside each bucket in shared memory (k2_group: a counting filter over the next 11
+//      hash bits drops the ~70 % of words that are alone in their sub-bucket, the rest are scanned densely; no
+//      ordering of singleton hashes is ever computed), orders only the members of shared groups by genome id, and
+//      emits compact postings + per-genome work items -- or, when the build is sharded by hash range across GPUs,
+//      a compact group stream that the ranks exchange (ygpu_index_partial / _finish).
 // Algorithmic HBM traffic: 8T (histogram) + 12T + 8T (scatter 1) + 8T (histogram 2) + 16T (scatter 2)
 // + 8T (bucket read) + O(P) outputs ~= 60 bytes per hash, against ~176 for the 7-pass pair sort.
 //
-// The general path (yacht_gpu.cu, CUB radix sort) remains for inputs this one does not cover:
-// hash width + genome-id width too large to pack, or a final bucket that overflows shared memory
-// (heavily skewed posting lists).  The choice is made per database from the measured bucket
-// histogram -- "chosen by measured posting-list skew".
+// Skew: a final bucket that does not fit shared memory (a hash held by thousands of genomes) leaves this path
+// alone -- its words are sorted device-wide and grouped by neighbour comparison (k2_big_*).  The general path
+// (yacht_gpu.cu, CUB radix sort of all pairs) remains for inputs that do not pack (hash width + genome-id width),
+// for more than 4096 oversized buckets and for sharded builds that meet one.  The choice is made per database
+// from the measured bucket histogram -- "chosen by measured posting-list skew".
 #include "common.cuh"
 
 #include <cub/cub.cuh>

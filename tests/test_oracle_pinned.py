@@ -170,3 +170,40 @@ def test_run_known_answer_fixture20():
     # n_c == 0 sentinels
     r0 = ro.single_hyp_test((5, 0), 31, 0.99, 0.95, 0.1)
     assert (r0[3], r0[5], r0[6], r0[7], r0[1], r0[0]) == (0, 0.0, 0.0, -1.0, 1.0, False)
+
+
+# ---- randomised live pinning of the train restatement against the UNMODIFIED reference core ---------------------------
+@pytest.mark.skipif(not to.reference_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_train_port_matches_reference_on_random_small_databases():
+    """Hand-rolled fuzz (seeded): tiny databases built from a SMALL hash universe so that ties, twins, subsets,
+    in-sketch duplicates, empty sketches and thresholds sitting exactly on a containment value all occur; the
+    restatement must reproduce the reference binary's pair lines, retained genomes (order included) and the three
+    banner statistics, for any thread / pass split."""
+    rng = np.random.default_rng(20260101)
+    checked = 0
+    for case in range(40):
+        n = int(rng.integers(1, 14))
+        universe = rng.integers(1, 2 ** 63, size=int(rng.integers(3, 40)), dtype=np.uint64)
+        parts = []
+        for g in range(n):
+            k = int(rng.integers(0, min(len(universe), 12) + 1))
+            s = rng.choice(universe, size=k, replace=False) if k else np.zeros(0, dtype=np.uint64)
+            if k and rng.random() < 0.2:                       # the same hash twice inside one sketch
+                s = np.concatenate([s, s[: int(rng.integers(1, k + 1))]])
+            if g and rng.random() < 0.25:                      # an exact twin / subset of an earlier sketch
+                src = parts[int(rng.integers(0, g))]
+                s = src.copy() if rng.random() < 0.5 else src[: len(src) // 2]
+            parts.append(np.asarray(s, dtype=np.uint64))
+        db = synth.from_sketches(parts)
+        sizes = [len(p) for p in parts if len(p)]
+        thr = float(rng.choice([0.0, 1.0, 0.5, 1 / 3, 0.95 ** 31] + ([1.0 * int(rng.integers(1, max(sizes) + 1)) / max(sizes)] if sizes else [])))
+        t, p = int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        with tempfile.TemporaryDirectory() as d:
+            ref = to.reference_train(db.hashes, db.offsets, thr, d, threads=t, passes=p)
+        r = to.oracle_train(db.hashes, db.offsets, thr)
+        ctx = (case, n, thr, t, p, [p_.tolist() for p_ in parts])
+        assert r.lines == ref.lines, ctx
+        assert list(r.selected) == list(ref.selected), ctx
+        assert (r.n_distinct, r.n_singleton, r.n_index) == (ref.n_distinct, ref.n_singleton, ref.n_index), ctx
+        checked += 1
+    assert checked == 40

@@ -234,3 +234,27 @@ def test_streamed_ingest_matches_plain_load(gpu_ctx, per_block):
     st = gpu_ctx.build_index()
     assert (st["n_hashes"], st["n_distinct"], st["n_singleton"]) == (int(db2.offsets[-1]), ref.n_distinct, ref.n_singleton)
     assert _pairs_tuple(gpu_ctx.pairwise_flag(THR)) == _pairs_tuple(ref.pairs)
+
+
+def test_random_small_databases(gpu_ctx):
+    """Seeded fuzz over tiny databases drawn from a small hash universe (ties, twins, subsets, in-sketch duplicates,
+    empty sketches, thresholds sitting exactly on a containment value) -- the same generator that pins the oracle to
+    the reference binary in tests/test_oracle_pinned.py.  Both index paths, both count kernels, bit-exact."""
+    rng = np.random.default_rng(20260102)
+    for case in range(30):
+        n = int(rng.integers(1, 14))
+        universe = rng.integers(1, 2 ** 63, size=int(rng.integers(3, 40)), dtype=np.uint64)
+        parts = []
+        for g in range(n):
+            k = int(rng.integers(0, min(len(universe), 12) + 1))
+            s = rng.choice(universe, size=k, replace=False) if k else np.zeros(0, dtype=np.uint64)
+            if k and rng.random() < 0.2:
+                s = np.concatenate([s, s[: int(rng.integers(1, k + 1))]])
+            if g and rng.random() < 0.25:
+                src = parts[int(rng.integers(0, g))]
+                s = src.copy() if rng.random() < 0.5 else src[: len(src) // 2]
+            parts.append(np.asarray(s, dtype=np.uint64))
+        db = synth.from_sketches(parts)
+        sizes = [len(p) for p in parts if len(p)]
+        thr = float(rng.choice([0.0, 1.0, 0.5, 1 / 3, THR] + ([1.0 * int(rng.integers(1, max(sizes) + 1)) / max(sizes)] if sizes else [])))
+        _check(gpu_ctx, db, thr)

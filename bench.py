@@ -96,6 +96,11 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        self.sm, self.mx, self.reasons = sm, mx, reasons
+        return self.summary(sm, mx, reasons)
+
+    @staticmethod
+    def summary(sm, mx, reasons) -> dict:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -309,6 +314,8 @@ def run_b200_arm(args):
         n_r = ctx.pairwise_flag_device(THR, rb, re)
         return gather_pairs(n_r, True)
 
+    clock_samples = []      # samplers of both timed regions (resident, e2e): the step is short, so their samples are pooled
+
     def timed(fn, reload_first: bool):
         if reload_first:
             ctx.load_sketches_device(d_hashes.data_ptr(), d_offsets.data_ptr(), n)
@@ -335,6 +342,8 @@ def run_b200_arm(args):
         barrier()
         wall = time.perf_counter() - wall0
         clocks = sampler.stop() if sampler else None
+        if sampler and getattr(sampler, "sm", None) is not None:
+            clock_samples.append(sampler)
         tm = ctx.timings()
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -423,7 +432,9 @@ def run_b200_arm(args):
                     "phases_ms": {k: tm_e2e[k] / steps for k in ("ms_h2d", "ms_sort", "ms_index", "ms_count", "ms_pairsort", "ms_d2h")}},
             "gpu_launches": int(tm_res["n_kernel_launches"]),
             "library_launches": int(tm_res["n_library_launches"]),
-            "clocks": clocks,
+            "clocks": (dict(ClockSampler.summary([v for c in clock_samples for v in c.sm], [v for c in clock_samples for v in c.mx],
+                                                 set().union(*[c.reasons for c in clock_samples])),
+                            regions="resident + e2e timed regions pooled") if clock_samples else clocks),
             "roofline": dominant, "rooflines": rooflines, "index_path": "msd-partition" if msd else "general-sort",
             "index_mode": mode["index"],
             "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},

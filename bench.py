@@ -122,16 +122,20 @@ def independent_counts_torch(d_hashes, torch):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference core (oracle/_ref) -- or the oracle port when that binary is absent -- on a
-# bounded sample of the same workload.  Throughput counts the phases that correspond to the GPU
-# arm's e2e step (host buffers -> pair list + retained set): index + matrix + greedy; its JSON
-# ingest phase is reported separately.
+# CPU arm: the reference core (oracle/_ref) -- or the oracle port when that binary is absent.
+#   --impl reference : ONE run of the unmodified reference executable on the FULL configuration (same genomes, same
+#                      seed as the GPU arm): the database is written as signature files and the stock CLI is run with
+#                      every host thread.  Throughput counts the phases that correspond to the GPU arm's e2e step (host
+#                      buffers -> pair list + retained set): its own index + matrix + greedy timers; its JSON read
+#                      phase is reported separately.
+#   cpu_baseline     : (inside the GPU arm's line) a bounded sample of the same database, ~15 s of CPU work, labelled
+#                      with the sample size -- a reported baseline, never used for a ratio.
 # ------------------------------------------------------------------------------------------------
 def cpu_arm_setup(db, n_sample: int):
     from oracle import train_oracle as to
     tmp = tempfile.mkdtemp(prefix="yacht_cpu_arm_")
-    sub = db.subset(range(n_sample))
-    to.write_sig_dir(sub.hashes, sub.offsets, tmp)
+    sub = db if n_sample >= db.n else db.subset(range(n_sample))
+    to.write_sig_dir_parallel(sub, tmp)
     if to.reference_available():
         binary, kind = to.REF_BIN, "reference"
     else:
@@ -140,12 +144,12 @@ def cpu_arm_setup(db, n_sample: int):
     return tmp, binary, kind
 
 
-def cpu_arm_step(tmp: str, binary: str, cores: int):
+def cpu_arm_step(tmp: str, binary: str, cores: int, passes: int = 1):
     from oracle import train_oracle as to
     for f in os.listdir(tmp):
         if f.endswith(".txt"):
             os.remove(os.path.join(tmp, f))
-    out, wall = to.run_core_binary(binary, os.path.join(tmp, "training_sig_files.tsv"), tmp, THR, threads=cores, passes=1)
+    out, wall = to.run_core_binary(binary, os.path.join(tmp, "training_sig_files.tsv"), tmp, THR, threads=cores, passes=passes)
     ph = to.parse_phase_times(out)
     return ph, wall
 
@@ -157,40 +161,111 @@ def choose_cpu_sample(db, budget_s: float) -> int:
     return int(max(100, min(db.n, budget_s / max(per_genome, 1e-6))))
 
 
+def mem_available_bytes() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for l in f:
+                if l.startswith("MemAvailable:"):
+                    return int(l.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+def reference_plan(n: int, T: int):
+    """Passes (-p) and the memory the reference core needs: ~100 B per distinct hash in its unordered_map of vectors plus a
+    dense int matrix of ceil(n/p) x n (main.cpp:318-335).  Results do not depend on -p."""
+    avail = mem_available_bytes()
+    map_bytes = 110 * T
+    passes = 1
+    while passes < 64 and 4.0 * n * n / passes > max(0.15 * avail, 2e9):
+        passes += 1
+    need = map_bytes + 4.0 * n * n / passes + 8 * T
+    return passes, need, avail
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     db, gen_s = make_workload(args.genomes, args.seed)
+    n, T = db.n, int(db.offsets[-1])
     cores = os.cpu_count() or 1
-    budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))
-    n_s = args.cpu_sample or choose_cpu_sample(db, budget)
+    passes, need, avail = reference_plan(n, T)
+    full = not args.cpu_sample and (avail == 0 or need < 0.9 * avail)
+    n_s = n if full else (args.cpu_sample or choose_cpu_sample(db, 120.0))
+    t0 = time.time()
     tmp, binary, kind = cpu_arm_setup(db, n_s)
+    write_s = time.time() - t0
     try:
-        for _ in range(args.warmup):
-            cpu_arm_step(tmp, binary, cores)
-        tot = 0.0
-        phases = []
-        for _ in range(args.steps):
-            ph, wall = cpu_arm_step(tmp, binary, cores)
-            phases.append(ph)
-            t = (ph.get("index_ms", 0) + ph.get("matrix_ms", 0) + ph.get("greedy_ms", 0)) / 1e3 if ph else wall
-            tot += t
-        per = tot / max(args.steps, 1)
+        if not full:
+            passes = 1
+        ph, wall = cpu_arm_step(tmp, binary, cores, passes)          # ONE run: a second one would only repeat ~minutes of CPU work
+        per = (ph.get("index_ms", 0) + ph.get("matrix_ms", 0) + ph.get("greedy_ms", 0)) / 1e3 if ph else wall
         pairs = n_s * (n_s - 1)
         val = pairs / per if per > 0 else 0.0
-        sample = (f"first {n_s} of {db.n} genomes (file order), all-vs-all, {os.path.basename(binary)} -t {cores} -p 1; "
-                  f"time = its own index+matrix+greedy phase timers (JSON read phase excluded)")
+        cfg = workload_config(args, db)
+        sample = (f"{'ALL' if full else 'first'} {n_s} of {n} genomes (file order), all-vs-all, {os.path.basename(binary)} -t {cores} -p {passes}, "
+                  f"one run (steps_run = 1, no warm-up: a run is minutes of CPU); time = its own index+matrix+greedy phase timers "
+                  f"(JSON read phase {ph.get('read_ms', 0)} ms excluded: the GPU arm's e2e also starts from parsed arrays)")
+        if not full:
+            # not the same configuration: say so where the driver looks (config.genomes) and never publish a ratio from it
+            cfg = dict(cfg, genomes=n_s, hashes=int(db.offsets[n_s]), same_config=False,
+                       workload=cfg["workload"] + f" -- REFERENCE ARM RAN ONLY THE FIRST {n_s} GENOMES "
+                                                    f"(host memory available {avail / 1e9:.0f} GB < {need / 1e9:.0f} GB needed)")
         line = {"impl": "reference", "metric": "ref-pair containments/s (yacht train hot path)", "value": val, "unit": "pairs/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_run": 1, "warmup_run": 0,
+                "ms_per_step": per * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 (+f64 threshold)",
-                "data": "synthetic", "config": workload_config(args, db),
+                "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample,
-                                 "phases_ms_last": phases[-1] if phases else {}},
+                                 "phases_ms": ph, "wall_s": wall, "passes": passes, "write_sig_files_s": write_s,
+                                 "generate_s": gen_s},
                 "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if full:
+            # the reference's own outputs of this very run against the committed digests (same check as the GPU arm)
+            try:
+                from oracle import train_oracle as to
+                with open(os.path.join(tmp, "training_sig_files.tsv")) as f:
+                    paths = [l.rstrip("\n") for l in f if l.strip()]
+                got = to.parse_core_outputs(tmp, paths, os.path.join(tmp, "selected_result.tsv"), "")
+                line["parity"] = check_digest(args, n, len(got.lines), lines=got.lines, selected=got.selected)
+            except Exception as e:
+                line["parity"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def find_digest(args, n: int):
+    """The committed reference digest of this (genomes, seed) workload, if any (tests/golden/config_digests.json)."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "config_digests.json")) as f:
+            digests = json.load(f)
+    except Exception:
+        return None, None
+    for name, e in digests.items():
+        g = e.get("generator", {})
+        if set(g) == {"n", "seed"} and g["n"] == n and g["seed"] == args.seed and abs(e.get("threshold", -1) - THR) < 1e-15:
+            return name, e
+    return None, None
+
+
+def check_digest(args, n, F, lines=None, pairs=None, sizes=None, selected=None):
+    """Bit-exactness at the benchmarked size: F, sha256 of the sorted pair lines and of the retained ids against what the
+    UNMODIFIED reference core produced for the same seeded database."""
+    from yacht_b200 import pairfmt
+    name, e = find_digest(args, n)
+    if e is None:
+        return {"parity_digest_ok": None, "why": "no committed reference digest for this (genomes, seed)"}
+    if lines is None:
+        lines = pairfmt.pair_lines(pairs, sizes)
+    out = {"golden": f"tests/golden/config_digests.json[{name}] (unmodified reference core, {e.get('reference_cmd', '')})",
+           "F": int(F), "F_ok": int(F) == e["F"], "pairs_sha256_ok": pairfmt.digest_lines(lines) == e["pairs_sha256"],
+           "selected_sha256_ok": None if selected is None else pairfmt.digest_ids(selected) == e["selected_sha256"],
+           "n_selected": None if selected is None else int(len(selected))}
+    out["parity_digest_ok"] = bool(out["F_ok"] and out["pairs_sha256_ok"] and out["selected_sha256_ok"] is not False)
+    return out
 
 
 def workload_config(args, db):
@@ -440,6 +515,14 @@ def run_b200_arm(args):
             "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},
             "workload_counts": dict(counts, F=F, genomes=n), "wall_ms_per_step": wall_res * 1e3, "gen_seconds": gen_s,
         }
+        # ---- parity at the benchmarked size: the gathered pair list of the last e2e step against the reference digest ----
+        try:
+            sel = _lib.greedy_select(offsets, pairs_host)
+            line["parity"] = check_digest(args, n, F, pairs=pairs_host, sizes=db.sizes, selected=sel)
+            line["parity"]["n_flagged_resident_step"] = int(n_flagged)
+        except Exception as e:
+            line["parity"] = {"parity_digest_ok": False, "error": repr(e)}
+        line["parity_digest_ok"] = line["parity"].get("parity_digest_ok")
         # ---- CPU baseline: bounded sample on this box's host cores -------------------------------------
         if not args.no_cpu_baseline:
             try:
@@ -454,6 +537,9 @@ def run_b200_arm(args):
                 line["cpu_baseline"] = {"value": n_s * (n_s - 1) / max(t, 1e-9), "unit": "pairs/s", "cores": cores, "kind": kind,
                                         "sample": f"first {n_s} of {n} genomes (file order), all-vs-all, {os.path.basename(binary)} "
                                                   f"-t {cores} -p 1; time = its index+matrix+greedy phase timers",
+                                        "sample_genomes": n_s, "same_config": n_s == n,
+                                        "note": "pairs/s of the CPU core grows with N (its O(T) index build dominates): this bounded-sample figure is "
+                                                "NOT comparable with the full-size GPU value; the same-config CPU number is the --impl reference arm",
                                         "phases_ms": ph, "wall_s": wall}
             except Exception as e:  # the baseline must never take the GPU numbers down with it
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
@@ -473,7 +559,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genomes", type=int, default=85205, help="BASELINE.json configs[2]: GTDB-rs214-representatives shape")
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="genomes in the CPU sample (0 = size for ~15 s)")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="genomes in the CPU sample (cpu_baseline: 0 = size for ~15 s; --impl reference: 0 = the FULL configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -15,6 +15,7 @@
  *   ygpu_build_index        compute_index_from_sketches()                      main.cpp:215-246
  *   ygpu_pairwise_flag      compute_intersection_matrix[_by_sketches]()        main.cpp:249-366
  *                           counts (:252-262) fused with threshold/emit (:274-308)
+ *   ygpu_greedy_select      do_yacht_train(): greedy near-duplicate removal    main.cpp:371-420
  *   ygpu_row_partition      the contiguous row chunks per thread / per pass    main.cpp:338-349
  *   ygpu_index_partial / _stream_copy / _finish   compute_index_from_sketches() split by hash range across GPUs   main.cpp:215-246
  *                           (here: work-balanced row ranges per GPU)
@@ -185,6 +186,12 @@ int ygpu_pairwise_flag(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint
  * multi-GPU gather hands NCCL the device copy.                                                   */
 int ygpu_pairwise_flag_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, uint32_t row_end, uint64_t* n_out);
 int ygpu_pairs_copy(ygpu_ctx* ctx, void* dst, int dst_is_device);
+/* Host-side (sequential, milliseconds): the greedy selection of main.cpp:371-420 over the flagged pairs of the whole
+ * database (sorted by (i, j) as ygpu_pairwise_flag returns them).  offsets: the CSR offsets the sketches were loaded
+ * with (sketch sizes).  selected[0..*n_selected) = retained genome ids in the reference's visit order (ascending
+ * sketch size, ties as the reference's std::sort leaves them); `selected` must hold n entries.                    */
+int ygpu_greedy_select(const uint64_t* offsets, uint32_t n_genomes, const ygpu_pair* pairs, uint64_t n_pairs,
+                       int32_t* selected, uint32_t* n_selected);
 /* bounds[0..nparts] : contiguous row ranges of (nearly) equal pairwise-count work.               */
 int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds);
 

@@ -142,6 +142,41 @@ def write_sig_dir(hashes: np.ndarray, offsets: np.ndarray, workdir: str, names: 
     return paths
 
 
+_par_db = None
+_par_paths = None
+
+
+def _par_write(rng):
+    from yacht_b200 import sigio
+    for g in range(rng[0], rng[1]):
+        sigio.write_signature(_par_paths[g], f"genome_{g}", _par_db.hashes[int(_par_db.offsets[g]):int(_par_db.offsets[g + 1])])
+    return rng[1] - rng[0]
+
+
+def write_sig_dir_parallel(db, workdir: str, threads: Optional[int] = None) -> List[str]:
+    """write_sig_dir on all host cores (forked workers see `db` -- anything with .hashes / .offsets / .n -- without
+    copying it): 85 205 signature files (7.5 GB of JSON) take ~15 s instead of minutes."""
+    global _par_db, _par_paths
+    from multiprocessing import Pool
+    sys.path.insert(0, os.path.dirname(HERE))
+    threads = threads or os.cpu_count() or 8
+    n = int(db.n)
+    os.makedirs(os.path.join(workdir, "signatures"), exist_ok=True)
+    _par_db = db
+    _par_paths = [os.path.join(workdir, "signatures", f"g{g:07d}.sig") for g in range(n)]
+    if n < 2000:
+        _par_write((0, n))
+    else:
+        step = max(1, n // (4 * threads))
+        with Pool(threads) as pool:
+            pool.map(_par_write, [(a, min(n, a + step)) for a in range(0, n, step)])
+    with open(os.path.join(workdir, "training_sig_files.tsv"), "w") as f:
+        for q in _par_paths:
+            f.write(q + "\n")
+    paths, _par_db, _par_paths = _par_paths, None, None
+    return paths
+
+
 def parse_core_outputs(workdir: str, paths: List[str], selected_file: str, stdout: str) -> TrainResult:
     import glob
     lines: List[str] = []

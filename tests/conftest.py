@@ -19,3 +19,19 @@ def gpu_ctx():
     ctx = _lib.GpuContext(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def config_db():
+    """BASELINE.json's seeded databases (tests/golden/config_digests.json: generator arguments), generated once per session."""
+    import json
+    from yacht_b200 import synth
+    with open(os.path.join(ROOT, "tests", "golden", "config_digests.json")) as f:
+        digests = json.load(f)
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = synth.make_reference_db(**digests[name]["generator"])
+        return cache[name]
+    return get

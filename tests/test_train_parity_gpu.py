@@ -178,11 +178,11 @@ def test_count_kernel_tiled_and_u16_variants(gpu_ctx):
         gpu_ctx.set_option("force_u16", 0)
 
 
-def test_full_size_properties_85k(gpu_ctx):
+def test_full_size_properties_85k(gpu_ctx, config_db):
     """BASELINE.json's full size (85 205 genomes): properties that do not need the oracle --
     the two independent count kernels agree, flagged pairs are consistent with the sketch sizes,
     every planted twin pair above the threshold is found, and row-range shards union to the whole."""
-    db = synth.make_reference_db(85205, 3)
+    db = config_db("config3")
     gpu_ctx.load_sketches(db.hashes, db.offsets)
     st = gpu_ctx.build_index()
     assert st["index_path"] == 1 and st["n_hashes"] == int(db.offsets[-1])

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test", "ygpu_index_partial", "ygpu_index_stream_copy", "ygpu_index_finish",
-    "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish",
+    "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
     lib.ygpu_exclusive_hashes.argtypes = [vp, vp, u64, vp, vp]
     lib.ygpu_hyp_test.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, ctypes.c_double, vp, ctypes.c_int, vp]
+    lib.ygpu_greedy_select.argtypes = [vp, u32, vp, u64, vp, ctypes.POINTER(u32)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)  # AttributeError here means the .so does not match include/yacht_gpu.h
     _lib = lib
@@ -323,6 +324,22 @@ def read_signatures(paths: Sequence[str], threads: int = 1) -> Tuple[np.ndarray,
         return hashes, offsets, int(ss.n_unreadable)
     finally:
         lib.ygpu_sketch_set_free(ctypes.byref(ss))
+
+
+def greedy_select(offsets: np.ndarray, pairs: np.ndarray) -> np.ndarray:
+    """do_yacht_train (reference main.cpp:371-420) over the flagged pairs of the whole database: the retained genome
+    ids in the reference's visit order (host code inside the library: the same std::sort call as the reference)."""
+    lib = load_library()
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+    n = int(offsets.shape[0]) - 1
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    ns = ctypes.c_uint32(0)
+    rc = lib.ygpu_greedy_select(offsets.ctypes.data, n, pairs.ctypes.data if len(pairs) else None, len(pairs), out.ctypes.data,
+                                ctypes.byref(ns))
+    if rc != 0:
+        raise YgpuError(f"ygpu_greedy_select failed ({rc})")
+    return out[: int(ns.value)].copy()
 
 
 def device_count() -> int:

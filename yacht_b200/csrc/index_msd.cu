@@ -35,8 +35,10 @@ namespace {
 constexpr int SC_TILE = 4096;       // elements per scatter tile (512 threads x 8)
 constexpr int SC_THREADS = 512;
 constexpr int SC_ITEMS = SC_TILE / SC_THREADS;
+constexpr int SC_BUF = SC_TILE + 8; // words per tile buffer: the 16-byte aligned window around a tile may start one word early
+constexpr int SC_BND = 16;          // level 1: genome boundaries per tile resolved from shared memory (more: binary search in L2)
 constexpr int NB_MAX = 2048;        // digits per partition level
-constexpr uint32_t A_TARGET = 1200; // average elements per used final bucket
+constexpr uint32_t A_TARGET = 900;  // average elements per used final bucket (k2_group2 takes buckets of <= 1022)
 
 enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10, SCM_STREAM = 12 };   // extra slots of ctx->d_scalars (SCM_MAXB uses two)
 
@@ -60,16 +62,65 @@ __device__ __forceinline__ uint32_t digit2_of(uint64_t e, const MsdPlan& p) {
     return p.d2 ? (uint32_t)((e >> (p.gb + p.kb1 - p.d2)) & ((1u << p.d2) - 1u)) : 0u;
 }
 
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on a shared-memory mbarrier ---------------
+// One elected thread asks the copy engine for a whole tile; no thread holds the tile in registers while it is in
+// flight, so the next tile streams in behind the current one (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// dst / src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D;\n"
+        "bra W;\n"
+        "D:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // ---- level-1 histogram ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k2_hist1(const uint64_t* __restrict__ hashes, const MsdPlan p, uint32_t* __restrict__ hist) {
     extern __shared__ uint32_t sh[];
     for (uint32_t i = threadIdx.x; i < p.nb1; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.T; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&sh[digit1_of(hashes[i], p)], 1u);
+    const int shift = p.hb - p.d1;
+    const bool one = p.d1 == 0;
+    // 16-byte loads, four in flight per thread
+    const ulonglong2* h2 = reinterpret_cast<const ulonglong2*>(hashes);
+    const uint64_t n2 = p.T >> 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        const ulonglong2 a = h2[i], b = h2[i + stride], c = h2[i + 2 * stride], d = h2[i + 3 * stride];
+        atomicAdd(&sh[one ? 0u : (uint32_t)(a.x >> shift)], 1u); atomicAdd(&sh[one ? 0u : (uint32_t)(a.y >> shift)], 1u);
+        atomicAdd(&sh[one ? 0u : (uint32_t)(b.x >> shift)], 1u); atomicAdd(&sh[one ? 0u : (uint32_t)(b.y >> shift)], 1u);
+        atomicAdd(&sh[one ? 0u : (uint32_t)(c.x >> shift)], 1u); atomicAdd(&sh[one ? 0u : (uint32_t)(c.y >> shift)], 1u);
+        atomicAdd(&sh[one ? 0u : (uint32_t)(d.x >> shift)], 1u); atomicAdd(&sh[one ? 0u : (uint32_t)(d.y >> shift)], 1u);
+    }
+    for (; i < n2; i += stride) {
+        const ulonglong2 a = h2[i];
+        atomicAdd(&sh[one ? 0u : (uint32_t)(a.x >> shift)], 1u); atomicAdd(&sh[one ? 0u : (uint32_t)(a.y >> shift)], 1u);
+    }
+    if ((p.T & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sh[digit1_of(hashes[p.T - 1], p)], 1u);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < p.nb1; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    for (uint32_t k = threadIdx.x; k < p.nb1; k += blockDim.x)
+        if (sh[k]) atomicAdd(&hist[k], sh[k]);
 }
 
 // one CTA: bucket bases, tile prefix (for level-2 work units) and cursors from the level-1 histogram
@@ -101,7 +152,9 @@ __global__ void __launch_bounds__(1024) k2_prep1(const uint32_t* __restrict__ hi
 // ---- scatter (level 1: raw hashes -> packed words by leading digit; level 2: words -> final buckets)
 struct ScatterArgs {
     const uint64_t* hashes;      // level 1 input
-    const uint32_t* gid;
+    const uint64_t* offsets;     // level 1: CSR offsets of the sketches [n + 1] (the genome id of a hash slot is derived from them)
+    const uint32_t* tile_g0;     // level 1: genome holding the first hash of every tile [tiles + 1] (k2_tile_g0)
+    uint32_t n;
     const uint64_t* in_ent;      // level 2 input
     uint64_t* out_ent;
     const uint32_t* base1;       // level 2: level-1 bucket bases
@@ -112,16 +165,15 @@ struct ScatterArgs {
 };
 
 template <int LEVEL>
-__device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& p, uint32_t unit, uint64_t& begin, uint32_t& m,
-                                           uint32_t& b1) {
+__device__ __forceinline__ bool unit_range(const ScatterArgs& a, const MsdPlan& p, uint32_t unit, uint32_t n_units, uint64_t& begin,
+                                           uint32_t& m, uint32_t& b1) {
+    if (unit >= n_units) return false;
     if (LEVEL == 1) {
         begin = (uint64_t)unit * SC_TILE;
-        if (begin >= p.T) return false;
         m = (uint32_t)min((uint64_t)SC_TILE, p.T - begin);
         b1 = 0;
         return true;
     }
-    if (unit >= p.unit_hi || unit >= a.tile_start[p.nb1]) return false;
     const uint2 u = a.units[unit];      // resolved once by k2_units: a per-tile binary search here would put ~10 dependent
     begin = u.x;                        // L2 round trips on the critical path of every tile
     m = u.y & 0xffffu;
@@ -146,62 +198,155 @@ __global__ void __launch_bounds__(256) k2_units(const uint32_t* __restrict__ til
     }
 }
 
-__global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPlan p) {
-    extern __shared__ uint32_t sh[];
-    const uint32_t nd = 1u << p.d2;
-    for (uint32_t unit = p.unit_lo + blockIdx.x;; unit += gridDim.x) {
-        uint64_t begin; uint32_t m, b1;
-        if (!unit_range<2>(a, p, unit, begin, m, b1)) break;
-        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sh[i] = 0;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) atomicAdd(&sh[digit2_of(a.in_ent[begin + i], p)], 1u);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x)
-            if (sh[i]) atomicAdd(&a.hist2[((uint64_t)b1 << p.d2) + i], sh[i]);
-        __syncthreads();
+// largest g with offsets[g] <= idx, searched in [lo, hi] (offsets[lo] <= idx)
+__device__ __forceinline__ uint32_t genome_of(const uint64_t* __restrict__ offsets, uint32_t lo, uint32_t hi, uint64_t idx) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        if (offsets[mid] <= idx) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// one thread per level-1 tile: the genome that holds the tile's first hash slot (the last one holding slot T - 1 for
+// the entry behind the last tile).  Replaces a 4-byte genome id per hash slot read by the level-1 scatter.
+__global__ void __launch_bounds__(256) k2_tile_g0(const uint64_t* __restrict__ offsets, uint32_t n, uint64_t T, uint32_t n_tiles,
+                                                  uint32_t* __restrict__ tile_g0) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= n_tiles; t += gridDim.x * blockDim.x) {
+        const uint64_t idx = t < n_tiles ? (uint64_t)t * SC_TILE : T - 1;
+        tile_g0[t] = genome_of(offsets, 0, n - 1, idx);
     }
 }
 
+// Level-2 digit histogram.  A CTA walks a contiguous range of tiles, so its shared-memory counters are flushed only when
+// the level-1 bucket changes (once or twice per CTA), not once per tile.
+__global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPlan p, uint32_t unit_end) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t nd = 1u << p.d2;
+    unit_end = min(unit_end, a.tile_start[p.nb1]);
+    const uint32_t total = unit_end > p.unit_lo ? unit_end - p.unit_lo : 0u;
+    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+    const uint32_t u0 = p.unit_lo + blockIdx.x * per;
+    const uint32_t u1 = min(unit_end, u0 + per);
+    const int shift = p.gb + p.kb1 - p.d2;
+    const uint32_t mask = nd - 1u;
+    uint32_t cur = 0xFFFFFFFFu;
+    for (uint32_t unit = u0; unit < u1; unit++) {
+        const uint2 u = a.units[unit];
+        const uint64_t begin = u.x;
+        const uint32_t m = u.y & 0xffffu, b1 = u.y >> 16;
+        if (b1 != cur) {                    // uniform per CTA
+            __syncthreads();
+            if (cur != 0xFFFFFFFFu)
+                for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x)
+                    if (sh[i]) atomicAdd(&a.hist2[((uint64_t)cur << p.d2) + i], sh[i]);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sh[i] = 0;
+            __syncthreads();
+            cur = b1;
+        }
+        const uint64_t* src = a.in_ent + begin;
+        for (uint32_t i = threadIdx.x; i < m; i += 4 * 256) {
+            uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            const bool v1 = i + 256 < m, v2 = i + 512 < m, v3 = i + 768 < m;
+            e0 = src[i];
+            if (v1) e1 = src[i + 256];
+            if (v2) e2 = src[i + 512];
+            if (v3) e3 = src[i + 768];
+            atomicAdd(&sh[(uint32_t)(e0 >> shift) & mask], 1u);
+            if (v1) atomicAdd(&sh[(uint32_t)(e1 >> shift) & mask], 1u);
+            if (v2) atomicAdd(&sh[(uint32_t)(e2 >> shift) & mask], 1u);
+            if (v3) atomicAdd(&sh[(uint32_t)(e3 >> shift) & mask], 1u);
+        }
+    }
+    __syncthreads();
+    if (cur != 0xFFFFFFFFu)
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x)
+            if (sh[i]) atomicAdd(&a.hist2[((uint64_t)cur << p.d2) + i], sh[i]);
+}
+
+// Tile-staged scatter.  Tiles arrive through the copy engine (cp.async.bulk + mbarrier) into two ping-pong buffers:
+// while tile k is ranked, reordered and written out, tile k+1 is already streaming into the other buffer.  The
+// reordered words are staged in the buffer the tile came in (its words are in registers by then), so a CTA holds two
+// tile buffers, not three.  Level 1 derives the genome id of every hash slot from the CSR offsets (a few boundaries
+// per tile, kept in shared memory) instead of reading a 4-byte id per slot.
 template <int LEVEL>
-__global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t n_units_l1) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* stage = (uint64_t*)smem_raw;                         // [SC_TILE]
-    uint32_t* cnt = (uint32_t*)(stage + SC_TILE);                  // [nd]
+__global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t unit_first, uint32_t n_units) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* buf0 = (uint64_t*)smem_raw;                          // [2][SC_BUF]
     const uint32_t nd = LEVEL == 1 ? p.nb1 : (1u << p.d2);
+    uint32_t* cnt = (uint32_t*)(buf0 + 2 * SC_BUF);                // [nd]
     uint32_t* lbase = cnt + nd;                                    // [nd]
     uint32_t* gbase = lbase + nd;                                  // [nd]
     uint16_t* sdig = (uint16_t*)(gbase + nd);                      // [SC_TILE]
     typedef cub::BlockScan<uint32_t, SC_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_ts;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint64_t bnd[2][SC_BND];
+
+    const uint32_t tid = threadIdx.x;
+    if (LEVEL == 2) n_units = min(n_units, a.tile_start[p.nb1]);
+    const uint64_t* src_all = LEVEL == 1 ? a.hashes : a.in_ent;
+    // level 1: the genome boundaries of a tile are fetched one tile ahead (visible after the barrier that ends an iteration)
+    auto fetch_bnd = [&](uint32_t unit, uint32_t slot) {
+        if (LEVEL != 1 || unit >= n_units) return;
+        const uint32_t g0 = a.tile_g0[unit], nb = a.tile_g0[unit + 1] - g0;
+        if (nb <= SC_BND && tid < nb) bnd[slot][tid] = a.offsets[g0 + 1 + tid];
+    };
+    auto issue = [&](uint32_t unit, uint32_t slot) {              // thread 0 only
+        uint64_t begin; uint32_t m, b1;
+        if (!unit_range<LEVEL>(a, p, unit, n_units, begin, m, b1)) return;
+        const uint64_t w0 = begin & ~1ull, w1 = (begin + m + 1) & ~1ull;
+        bulk_load(buf0 + slot * SC_BUF, src_all + w0, (uint32_t)(w1 - w0) * 8u, &mbar[slot]);
+    };
+    for (uint32_t i = tid; i < nd; i += SC_THREADS) cnt[i] = 0;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_init_fence();
+    }
+    const uint32_t unit0 = unit_first + blockIdx.x;
+    fetch_bnd(unit0, 0);
+    __syncthreads();
+    if (tid == 0) {
+        issue(unit0, 0);
+        issue(unit0 + gridDim.x, 1);
+    }
 
     constexpr uint16_t SKIP = 0xFFFFu;     // not in the tile, or (level 1, sharded) a digit another rank owns
-    for (uint32_t unit = (LEVEL == 1 ? 0u : p.unit_lo) + blockIdx.x;; unit += gridDim.x) {
+    uint32_t it = 0;
+    for (uint32_t unit = unit0;; unit += gridDim.x, it++) {
         uint64_t begin; uint32_t m, b1;
-        if (LEVEL == 1 && unit >= n_units_l1) break;
-        if (!unit_range<LEVEL>(a, p, unit, begin, m, b1)) break;
-        for (uint32_t i = threadIdx.x; i < nd; i += SC_THREADS) cnt[i] = 0;
-        __syncthreads();
+        if (!unit_range<LEVEL>(a, p, unit, n_units, begin, m, b1)) break;
+        const uint32_t slot = it & 1u;
+        uint64_t* buf = buf0 + slot * SC_BUF;
+        // level 1: genome boundaries inside this tile
+        uint32_t g0 = 0, nbnd = 0;
+        if (LEVEL == 1) {
+            g0 = a.tile_g0[unit];
+            nbnd = a.tile_g0[unit + 1] - g0;
+        }
+        mbar_wait(&mbar[slot], (it >> 1) & 1u);
+        const uint32_t sh = (uint32_t)(begin & 1ull);
         uint64_t e[SC_ITEMS];
         uint16_t dg[SC_ITEMS], rk[SC_ITEMS];
-        uint32_t gi[SC_ITEMS];
-#pragma unroll
-        for (int k = 0; k < SC_ITEMS; k++) {      // all loads of the tile in flight before any is consumed
-            const uint32_t idx = k * SC_THREADS + threadIdx.x;
-            if (idx < m) {
-                if (LEVEL == 1) { e[k] = a.hashes[begin + idx]; gi[k] = a.gid[begin + idx]; }
-                else e[k] = a.in_ent[begin + idx];
-            }
-        }
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
-            const uint32_t idx = k * SC_THREADS + threadIdx.x;
+            const uint32_t idx = k * SC_THREADS + tid;
             dg[k] = SKIP;
             if (idx < m) {
+                e[k] = buf[sh + idx];
                 if (LEVEL == 1) {
                     const uint32_t d = digit1_of(e[k], p);
                     if (d >= p.dlo && d < p.dhi) {
+                        const uint64_t gi = begin + idx;
+                        uint32_t g = g0;
+                        if (nbnd <= SC_BND) {
+                            for (uint32_t j = 0; j < nbnd; j++) g += bnd[slot][j] <= gi ? 1u : 0u;
+                        } else {
+                            g = genome_of(a.offsets, g0, g0 + nbnd, gi);
+                        }
                         dg[k] = (uint16_t)d;
-                        e[k] = pack_entry(e[k], gi[k], p);
+                        e[k] = pack_entry(e[k], g, p);
                     }
                 } else {
                     dg[k] = (uint16_t)digit2_of(e[k], p);
@@ -211,12 +356,12 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++)
             if (dg[k] != SKIP) rk[k] = (uint16_t)atomicAdd(&cnt[dg[k]], 1u);
-        __syncthreads();
+        __syncthreads();                   // every word of the tile is in registers: the buffer becomes the staging area
         uint32_t mv = 0;     // words of this tile that are kept
-        // exclusive scan of cnt -> lbase; reserve global space per digit -> gbase
+        // exclusive scan of cnt -> lbase; reserve global space per digit -> gbase; counters back to zero
         {
             const uint32_t per = (nd + SC_THREADS - 1) / SC_THREADS;
-            const uint32_t d0 = threadIdx.x * per;
+            const uint32_t d0 = tid * per;
             uint32_t s = 0;
             for (uint32_t k = 0; k < per; k++) if (d0 + k < nd) s += cnt[d0 + k];
             uint32_t off;
@@ -230,6 +375,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
                     if (c) {
                         const uint64_t ci = LEVEL == 1 ? (uint64_t)d : (((uint64_t)b1 << p.d2) + d);
                         gbase[d] = atomicAdd(&a.cursor[ci], c);
+                        cnt[d] = 0;
                     }
                 }
             }
@@ -239,20 +385,25 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
         for (int k = 0; k < SC_ITEMS; k++) {
             if (dg[k] != SKIP) {
                 const uint32_t q = lbase[dg[k]] + rk[k];
-                stage[q] = e[k];
+                buf[q] = e[k];
                 sdig[q] = dg[k];
             }
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
-            const uint32_t q = k * SC_THREADS + threadIdx.x;
+            const uint32_t q = k * SC_THREADS + tid;
             if (q < mv) {
                 const uint32_t d = sdig[q];
-                a.out_ent[(uint64_t)gbase[d] + (q - lbase[d])] = stage[q];
+                a.out_ent[(uint64_t)gbase[d] + (q - lbase[d])] = buf[q];
             }
         }
-        __syncthreads();
+        fetch_bnd(unit + gridDim.x, slot ^ 1u);
+        __syncthreads();                   // the buffer is free again: fetch the tile after next into it
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (staging) before the async-proxy write
+            issue(unit + 2 * gridDim.x, slot);
+        }
     }
 }
 
@@ -288,6 +439,7 @@ struct GroupArgs {
     const uint32_t* base;        // [nb + 1]
     uint32_t nb;
     uint32_t b_lo, b_hi;         // final buckets this launch covers (all, or one rank's hash range)
+    uint32_t m_lo;               // k2_group: only buckets of more than m_lo words (the smaller ones went to k2_group2)
     int gb;
     int sub_shift;               // sub-bucket digit = (word >> sub_shift) & sub_mask
     uint32_t sub_mask;
@@ -431,7 +583,7 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     uint32_t* stg_g = sm.K2;                                                     // [BK_CAP]
     unsigned short* stg_rem = reinterpret_cast<unsigned short*>(sm.G2);          // [BK_CAP]
     const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
-    if (m_next && m_next <= GK_FAST * GK_THREADS) {      // start2 / SUB2 were last read in phase D: stage the next bucket there
+    if (m_next > a.m_lo && m_next <= GK_FAST * GK_THREADS) {      // start2 / SUB2 were last read in phase D: stage the next bucket there
         const uint64_t* nsrc = a.ent + bb_next + tid;
         const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage + tid);
 #pragma unroll
@@ -514,11 +666,11 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
         const uint32_t bn = b + gridDim.x;
         uint32_t bbn = 0, mn = 0;
         if (bn < a.b_hi) { bbn = a.base[bn]; mn = a.base[bn + 1] - bbn; }
-        if (m && m <= BK_CAP) {    // uniform per CTA (larger buckets: k2_big_*, below)
+        if (m > a.m_lo && m <= BK_CAP) {    // uniform per CTA (larger buckets: k2_big_*, below)
             if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, staged, bbn, mn);
             else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, false, bbn, mn);
             par ^= 1;
-            staged = mn && mn <= GK_FAST * GK_THREADS;
+            staged = mn > a.m_lo && mn <= GK_FAST * GK_THREADS;
         } else {
             staged = false;
         }
@@ -529,6 +681,229 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     const unsigned long long single = block_sum<GK_THREADS>(st.single);
     const unsigned long long w = block_sum<GK_THREADS>(st.w);
     const unsigned long long dups = block_sum<GK_THREADS>(st.dups);
+    if (threadIdx.x == 0) {
+        if (heads) atomicAdd(&a.scal[SC_HEADS], heads);
+        if (single) atomicAdd(&a.scal[SC_SINGLE], single);
+        if (w) atomicAdd(&a.scal[SC_W], w);
+        if (dups) atomicAdd(&a.scal[SC_DUPS], dups);
+    }
+}
+
+// ---- k2_group2: the grouping kernel for the common case ---------------------------------------------------------
+// Buckets of <= G2_MAXM words whose remaining hash bits (below the sub-bucket digit) fit 32 bits -- every bucket of a
+// database without extreme skew.  Same idea as k2_group (sub-bucket counting filter, dense candidate scan), rebuilt
+// around the instruction count, which is what bounds this step (not HBM):
+//   * the bucket's words arrive by ONE bulk asynchronous copy (cp.async.bulk + mbarrier) issued by one thread while
+//     the previous bucket is still being grouped; every thread then picks its four words with two 16-byte loads;
+//   * a candidate is one 64-bit word (remaining hash << 32 | genome id) plus the extent of its sub-bucket, so the scan
+//     of a sub-bucket is one load and three compares per word, branch-free and fixed-length (4) for sub-buckets of
+//     <= 4 words (all but a few per bucket);
+//   * no allocation of posting slots: a candidate's slot is its rank in the (hash, genome) order of its sub-bucket,
+//     which the same scan yields.  Groups come out contiguous and ordered; candidates that turn out to be alone leave
+//     a hole that the output phase skips.  One barrier and the per-group shared-memory atomics of k2_group disappear.
+constexpr int G2_THREADS = 256;
+constexpr int G2_WIN = 1024;                      // words of the 16-byte aligned window copied per bucket
+constexpr uint32_t G2_MAXM = G2_WIN - 2;          // largest bucket this kernel takes
+constexpr int G2_NSUB = 1 << GK_SUBBITS;          // 2048 sub-bucket counters = 8 per thread
+
+struct __align__(16) G2Smem {
+    uint64_t stage[G2_WIN];                       // the bucket's words (bulk copy target)
+    uint64_t cand[G2_WIN + 4];                    // candidates, sub-bucket by sub-bucket: remaining hash << 32 | genome id
+    uint32_t cnt[G2_NSUB];                        // sub-bucket sizes (zero between buckets)
+    uint32_t ext[G2_WIN];                         // per candidate: start of its sub-bucket | size << 16
+    uint32_t stg_g[G2_WIN + 4];                   // ordered groups: genome id
+    unsigned short start2[G2_NSUB + 8];           // candidate-array start of every sub-bucket
+    unsigned short stg_r[G2_WIN];                 // ordered groups: members that follow | 0x8000 posting wanted | 0x4000 hole
+    uint32_t wsum[G2_THREADS / 32];
+    uint32_t next[2][2];                          // [parity]{first word, words} of the bucket after this one (words = 0: none)
+    uint64_t mbar;
+};
+
+template <bool STREAM>
+__global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    G2Smem& sm = *reinterpret_cast<G2Smem*>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gmask = a.gb ? (uint32_t)((1ull << a.gb) - 1ull) : 0u;
+    const uint32_t kmask = (uint32_t)a.rest_mask;
+    const bool can_inline = a.gb <= YG_ITEM_INLINE_BITS;
+
+    // thread 0: the next bucket this CTA takes at or after `b` (stride gridDim.x) that is non-empty and fits; its
+    // extent goes to sm.next[par] and its words are requested from the copy engine
+    uint32_t b_next = a.b_lo + blockIdx.x;       // thread 0 only
+    auto advance = [&](uint32_t par) {
+        uint32_t bb = 0, m = 0;
+        while (b_next < a.b_hi) {
+            bb = a.base[b_next];
+            m = a.base[b_next + 1] - bb;
+            b_next += gridDim.x;
+            if (m && m <= G2_MAXM) break;
+            m = 0;
+        }
+        sm.next[par][0] = bb;
+        sm.next[par][1] = m;
+        if (m) {
+            const uint32_t w0 = bb & ~1u, w1 = (bb + m + 1u) & ~1u;
+            bulk_load(sm.stage, a.ent + w0, (w1 - w0) * 8u, &sm.mbar);
+        }
+    };
+    for (uint32_t i = tid; i < G2_NSUB; i += G2_THREADS) sm.cnt[i] = 0;
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        mbar_init_fence();
+        advance(0);
+    }
+    __syncthreads();
+
+    uint32_t n_heads = 0, n_single = 0, n_dups = 0;
+    unsigned long long n_w = 0;
+    GroupPending pd{0ull, 0u, 0u, false};
+    uint32_t par = 0, phase = 0;
+    for (;;) {
+        const uint32_t bb = sm.next[par][0], m = sm.next[par][1];
+        if (!m) break;
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1u;
+        // ---- A: four words per thread, sub-bucket rank -----------------------------------------------------------
+        const uint32_t wlo = bb & 1u, whi = wlo + m;                 // the bucket inside the copied window
+        uint64_t e[4];
+        {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
+            const uint4 v0 = s4[tid], v1 = s4[G2_THREADS + tid];
+            e[0] = (uint64_t)v0.x | ((uint64_t)v0.y << 32); e[1] = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
+            e[2] = (uint64_t)v1.x | ((uint64_t)v1.y << 32); e[3] = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+        }
+        uint32_t sr[4];                                              // sub-bucket | rank << 16, ~0 = not a word of the bucket
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t w = (k >> 1) * 512u + 2u * tid + (k & 1);
+            sr[k] = 0xFFFFFFFFu;
+            if (w >= wlo && w < whi) {
+                const uint32_t s = (uint32_t)(e[k] >> a.sub_shift) & a.sub_mask;
+                sr[k] = s | (atomicAdd(&sm.cnt[s], 1u) << 16);
+            }
+        }
+        __syncthreads();                                             // stage is free: request the next bucket
+        if (tid == 0) advance(par ^ 1u);
+        // ---- B: scan the sizes of sub-buckets with >= 2 words (and reset the counters for the next bucket) ----------
+        {
+            uint4* c4 = reinterpret_cast<uint4*>(&sm.cnt[8 * tid]);
+            uint4 c0 = c4[0], c1 = c4[1];
+            c4[0] = make_uint4(0u, 0u, 0u, 0u);
+            c4[1] = make_uint4(0u, 0u, 0u, 0u);
+            c0.x = c0.x >= 2 ? c0.x : 0u; c0.y = c0.y >= 2 ? c0.y : 0u; c0.z = c0.z >= 2 ? c0.z : 0u; c0.w = c0.w >= 2 ? c0.w : 0u;
+            c1.x = c1.x >= 2 ? c1.x : 0u; c1.y = c1.y >= 2 ? c1.y : 0u; c1.z = c1.z >= 2 ? c1.z : 0u; c1.w = c1.w >= 2 ? c1.w : 0u;
+            const uint32_t sum = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)lane >= o) inc += v;
+            }
+            if (lane == 31) sm.wsum[warp] = inc;
+            __syncthreads();
+            uint32_t wp = 0;
+#pragma unroll
+            for (int w = 0; w < G2_THREADS / 32 - 1; w++) wp += (w < (int)warp) ? sm.wsum[w] : 0u;
+            const uint32_t p0 = wp + inc - sum;
+            const uint32_t p1 = p0 + c0.x, p2 = p1 + c0.y, p3 = p2 + c0.z, p4 = p3 + c0.w, p5 = p4 + c1.x, p6 = p5 + c1.y, p7 = p6 + c1.z;
+            *reinterpret_cast<uint4*>(&sm.start2[8 * tid]) = make_uint4(p0 | (p1 << 16), p2 | (p3 << 16), p4 | (p5 << 16), p6 | (p7 << 16));
+            if (tid == G2_THREADS - 1) sm.start2[G2_NSUB] = (unsigned short)(p7 + c1.w);
+        }
+        __syncthreads();
+        // ---- C: candidates -> dense array, sub-bucket by sub-bucket; a word alone in its sub-bucket is a singleton ----
+        uint32_t solo = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (sr[k] != 0xFFFFFFFFu) {
+                const uint32_t s = sr[k] & 0xffffu;
+                const uint32_t lo = sm.start2[s], hi = sm.start2[s + 1];
+                if (hi > lo) {
+                    const uint32_t pos = lo + (sr[k] >> 16);
+                    const uint32_t K = (uint32_t)(e[k] >> a.gb) & kmask;
+                    const uint32_t G = (uint32_t)e[k] & gmask;
+                    sm.cand[pos] = ((uint64_t)K << 32) | (uint64_t)G;
+                    sm.ext[pos] = lo | ((hi - lo) << 16);
+                } else {
+                    solo++;
+                }
+            }
+        }
+        n_heads += solo;
+        n_single += solo;
+        __syncthreads();
+        // ---- D: every candidate scans its sub-bucket once: group size, rank in the group, rank in the sub-bucket -----
+        const uint32_t ncand = sm.start2[G2_NSUB];
+        for (uint32_t q = tid; q < ncand; q += G2_THREADS) {
+            const uint64_t wq = sm.cand[q];
+            const uint32_t x = sm.ext[q];
+            const uint32_t lo = x & 0xffffu, c = x >> 16;
+            const uint32_t Kq = (uint32_t)(wq >> 32);
+            uint32_t L = 0, rank = 0, rall = 0, dup = 0;
+            if (c <= 4) {
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++) {
+                    const uint64_t w = sm.cand[lo + j];
+                    const bool valid = j < c;
+                    const bool same = valid & ((uint32_t)(w >> 32) == Kq);
+                    const bool tie = valid & (w == wq) & (lo + j < q);           // same genome too: in-sketch duplicate
+                    const bool before = (valid & (w < wq)) | tie;
+                    L += same ? 1u : 0u;
+                    rank += (same & before) ? 1u : 0u;
+                    rall += before ? 1u : 0u;
+                    dup |= tie ? 1u : 0u;
+                }
+            } else {
+                for (uint32_t j = 0; j < c; j++) {
+                    const uint64_t w = sm.cand[lo + j];
+                    const bool same = (uint32_t)(w >> 32) == Kq;
+                    const bool tie = (w == wq) & (lo + j < q);
+                    const bool before = (w < wq) | tie;
+                    L += same ? 1u : 0u;
+                    rank += (same & before) ? 1u : 0u;
+                    rall += before ? 1u : 0u;
+                    dup |= tie ? 1u : 0u;
+                }
+            }
+            const uint32_t pos = lo + rall;
+            sm.stg_g[pos] = (uint32_t)wq;
+            sm.stg_r[pos] = L >= 2 ? (unsigned short)((L - 1 - rank) | ((!can_inline || L > 4) ? 0x8000u : 0u)) : (unsigned short)0x4000u;
+            n_heads += rank == 0;
+            n_single += L == 1;
+            n_dups += dup;
+            if (L >= 2 && rank == 0) n_w += (unsigned long long)L * L;
+        }
+        __syncthreads();
+        // ---- F: postings + work items, one thread per ordered slot ------------------------------------------------------
+        for (uint32_t x = tid; x < ncand; x += G2_THREADS) {
+            const uint32_t rr = sm.stg_r[x];
+            if (rr & 0x4000u) continue;
+            const uint32_t g = sm.stg_g[x];
+            const uint32_t rem = rr & 0x3fffu;
+            if (rr & 0x8000u) a.post[(uint64_t)bb + x] = g;
+            if (rem) {
+                uint64_t item;
+                if (can_inline && rem <= 3) {
+                    item = (uint64_t)rem | ((uint64_t)sm.stg_g[x + 1] << 2);
+                    if (rem >= 2) item |= (uint64_t)sm.stg_g[x + 2] << 22;
+                    if (rem >= 3) item |= (uint64_t)sm.stg_g[x + 3] << 42;
+                } else {
+                    item = (((uint64_t)bb + x + 1) << 32) | ((uint64_t)rem << 2);
+                }
+                const uint32_t slot = (uint32_t)atomicAdd(&a.row_cnt[g], 1ull);
+                const uint32_t dst = (uint32_t)a.row_off[g];
+                if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued one slot ago
+                pd.item = item; pd.dst = dst; pd.slot = slot; pd.has = true;
+            }
+        }
+        par ^= 1u;
+        // (the next bucket's phase A only touches stage / cnt; its barriers order everything else against this phase F)
+    }
+    if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;
+    const unsigned long long heads = block_sum<G2_THREADS>(n_heads);
+    const unsigned long long single = block_sum<G2_THREADS>(n_single);
+    const unsigned long long w = block_sum<G2_THREADS>(n_w);
+    const unsigned long long dups = block_sum<G2_THREADS>(n_dups);
     if (threadIdx.x == 0) {
         if (heads) atomicAdd(&a.scal[SC_HEADS], heads);
         if (single) atomicAdd(&a.scal[SC_SINGLE], single);
@@ -739,21 +1114,26 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         if (p.dlo >= p.dhi) { p.unit_lo = 0; p.unit_hi = 0; }
     }
     ScatterArgs a{};
-    a.hashes = ctx->d_hashes; a.gid = ctx->d_gid; a.out_ent = ctx->d_ent1; a.cursor = cursor;
+    a.hashes = ctx->d_hashes; a.offsets = ctx->d_offsets; a.n = n; a.out_ent = ctx->d_ent1; a.cursor = cursor;
     a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2;
     const uint32_t units1 = (uint32_t)((T + SC_TILE - 1) / SC_TILE);
     {
-        const size_t smem = (size_t)SC_TILE * 8 + (size_t)p.nb1 * 12 + (size_t)SC_TILE * 2;
+        // genome of the first hash slot of every level-1 tile (the scatter derives genome ids from the CSR offsets)
+        YG_CHECK(dev_alloc(ctx, &ctx->d_tile_g0, (uint64_t)units1 + 1));
+        k2_tile_g0<<<grid_for(ctx, (uint64_t)units1 + 1, 256, 8), 256, 0, st>>>(ctx->d_offsets, n, T, units1, ctx->d_tile_g0);
+        YG_CUDA(ctx, cudaGetLastError());
+        a.tile_g0 = ctx->d_tile_g0;
+        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)p.nb1 * 12 + (size_t)SC_TILE * 2;
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1>, SC_THREADS, smem));
         const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[2], st));
-        k2_scatter<1><<<grid, SC_THREADS, smem, st>>>(a, p, units1);
+        k2_scatter<1><<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[3], st));
     }
-    ctx->tm.n_kernel_launches += 3;
+    ctx->tm.n_kernel_launches += 4;
     const uint64_t* final_ent = ctx->d_ent1;
     const uint32_t* final_base = base1;
     // ---- level 2 ----------------------------------------------------------------------------------
@@ -766,7 +1146,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         ctx->tm.n_kernel_launches += 1;
         a.units = (const uint2*)ctx->d_units;
         const int grid_h = ctx->num_sms * 8;
-        k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p);
+        k2_hist2<<<grid_h, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p, p.unit_hi);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[4], st));
         // final-bucket bases: a rank's own buckets are contiguous, foreign ones are empty -> positions are local
@@ -782,13 +1162,13 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         ctx->tm.n_library_launches += 4;
         YG_CUDA(ctx, cudaMemcpyAsync(cursor, base2, ((uint64_t)p.nfb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         a.cursor = cursor;
-        const size_t smem = (size_t)SC_TILE * 8 + (size_t)(1u << d2) * 12 + (size_t)SC_TILE * 2;
+        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)(1u << d2) * 12 + (size_t)SC_TILE * 2;
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2>, SC_THREADS, smem));
         const int grid = ctx->num_sms * std::max(occ, 1);
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[5], st));
-        k2_scatter<2><<<grid, SC_THREADS, smem, st>>>(a, p, 0);
+        k2_scatter<2><<<grid, SC_THREADS, smem, st>>>(a, p, p.unit_lo, p.unit_hi);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[6], st));
         ctx->tm.n_kernel_launches += 2;
@@ -861,14 +1241,28 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         if (g.sub_shift > 63) { g.sub_shift = 0; g.sub_mask = 0; }
         g.post = ctx->d_post; g.row_off = ctx->d_offsets; g.row_cnt = ctx->d_row_cnt; g.row_items = ctx->d_row_items;
         g.st_gid = ctx->d_post; g.st_rem = ctx->d_st_rem; g.scal = ctx->d_scalars;
-        const size_t smem = (size_t)GK_NSUB * 4 + (size_t)BK_CAP * 8 + (size_t)(GK_NSUB + 8) * 2 + (size_t)BK_CAP * 4;
-        auto kern = stream ? k2_group<true> : k2_group<false>;
-        YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GK_THREADS, smem));
         const uint64_t nbk = g.b_hi > g.b_lo ? g.b_hi - g.b_lo : 0;
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[7], st));
-        if (nbk) {
+        // the common case (remaining hash bits fit 32, bucket <= G2_MAXM words) goes to k2_group2; k2_group takes the rest
+        const bool fast2 = !stream && rest_bits <= 32 && ctx->group_kernel != 1;
+        g.m_lo = 0;
+        if (fast2 && nbk) {
+            const size_t smem2 = sizeof(G2Smem);
+            YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            int occ2 = 1;
+            YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2_group2<false>, G2_THREADS, smem2));
+            const int grid2 = (int)std::min<uint64_t>(nbk, (uint64_t)ctx->num_sms * std::max(occ2, 1));
+            k2_group2<false><<<grid2, G2_THREADS, smem2, st>>>(g);
+            YG_CUDA(ctx, cudaGetLastError());
+            ctx->tm.n_kernel_launches += 1;
+            g.m_lo = G2_MAXM;
+        }
+        if (nbk && (!fast2 || largest > G2_MAXM)) {
+            const size_t smem = (size_t)GK_NSUB * 4 + (size_t)BK_CAP * 8 + (size_t)(GK_NSUB + 8) * 2 + (size_t)BK_CAP * 4;
+            auto kern = stream ? k2_group<true> : k2_group<false>;
+            YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GK_THREADS, smem));
             const int grid = (int)std::min<uint64_t>(nbk, (uint64_t)ctx->num_sms * std::max(occ, 1));
             kern<<<grid, GK_THREADS, smem, st>>>(g);
             YG_CUDA(ctx, cudaGetLastError());

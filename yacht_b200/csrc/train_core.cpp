@@ -339,7 +339,6 @@ int main(int argc, char** argv) {
         });
 
     // ---- pair files: same file partition as main.cpp:318,338-349, same line format as :305 --------
-    std::vector<std::vector<int>> similars(n);
     {
         const int P = args.num_of_passes, Tn = args.number_of_threads;
         const int per_pass = (int)std::ceil(1.0 * n / P);
@@ -365,7 +364,6 @@ int main(int argc, char** argv) {
                     const double c_ij = 1.0 * m / ni;
                     const double c_ji = 1.0 * m / nj;
                     outfile << pr.i << "," << pr.j << "," << jaccard << "," << c_ij << "," << c_ji << std::endl;
-                    similars[pr.i].push_back(pr.j);
                 }
                 outfile.close();
             }
@@ -378,25 +376,15 @@ int main(int argc, char** argv) {
     auto t_train = std::chrono::high_resolution_clock::now();
     std::cout << "Starting yacht train..." << std::endl;
     std::cout << "Starting yacht train..." << std::endl;
-    // Same element type, same initial order (file-list order), same comparator and the same
-    // std::sort as the reference, so genomes of equal size are visited in the same order.
-    std::vector<std::pair<int, int>> genome_id_size_pairs(n);
-    for (uint32_t g = 0; g < n; g++) genome_id_size_pairs[g] = {(int)g, (int)(in.offsets[g + 1] - in.offsets[g])};
-    std::sort(genome_id_size_pairs.begin(), genome_id_size_pairs.end(),
-              [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second < b.second; });
-    std::vector<bool> excluded(n, false);
-    std::vector<int> selected;
-    for (uint32_t v = 0; v < n; v++) {
-        const int g = genome_id_size_pairs[v].first;
-        const int size_this = genome_id_size_pairs[v].second;
-        bool keep = true;
-        for (int o : similars[g]) {
-            if (excluded[o]) continue;
-            if ((int)(in.offsets[o + 1] - in.offsets[o]) >= size_this) { keep = false; break; }
-        }
-        if (keep) selected.push_back(g);
-        else excluded[g] = true;
+    // ygpu_greedy_select (host code of the library): same element type, initial order (file-list order), comparator
+    // and std::sort call as the reference, so genomes of equal size are visited in the same order.
+    std::vector<int32_t> selected(std::max<uint32_t>(n, 1));
+    uint32_t n_selected = 0;
+    if (ygpu_greedy_select(in.offsets.data(), n, pairs.data(), pairs.size(), selected.data(), &n_selected)) {
+        std::cerr << "run_yacht_train_core: greedy selection failed" << std::endl;
+        return 5;
     }
+    selected.resize(n_selected);
     std::cout << "Writing to output file.." << std::endl;
     {
         std::ofstream outfile(args.output_filename);

@@ -275,8 +275,8 @@ def workload_config(args, db):
                         f"all-vs-all train hot path, k={KSIZE}, ani_thresh={ANI}",
             "genomes": db.n, "hashes": T, "seed": args.seed, "containment_threshold": THR,
             "parallelism": "1 GPU" if args.gpus == 1 else
-                           f"{args.gpus} GPUs: index build sharded by hash range (group streams all-gathered over NCCL), "
-                           f"pairwise count sharded by query rows, pair lists all-gathered",
+                           f"{args.gpus} GPUs: sketches resident by genome range, index build sharded by hash range (words and group streams "
+                           f"stored into peer buffers over NVLink by the kernels), pairwise count sharded by query rows, pair lists all-gathered (NCCL)",
             "l2": f"inputs {8 * T / 1e9:.2f} GB > L2 {L2_BYTES / 1e6:.0f} MB: no flush needed" if 8 * T > L2_BYTES
                   else "inputs fit L2: an L2 flush (write of 256 MB) runs before every timed step"}
 
@@ -310,90 +310,73 @@ def run_b200_arm(args):
     lib = _lib.load_library()
     ctx = _lib.GpuContext(local)
 
-    # pinned host staging for the e2e arm
-    hp = lib.ygpu_host_alloc(max(T, 1) * 8)
-    if not hp:
-        raise SystemExit("ygpu_host_alloc failed")
-    pinned = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_uint64)), shape=(max(T, 1),))[:T]
-    pinned[:] = db.hashes
     offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
-
-    # device-resident copy (torch owns it; the library copies device-to-device once, outside the timed region)
-    d_hashes = torch.from_numpy(db.hashes.view(np.int64)).to(dev)
-    d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
-    counts = independent_counts_torch(d_hashes, torch) if rank == 0 else None
+    hp = pinned = d_hashes = d_offsets = None
+    if world == 1:
+        # pinned host staging for the e2e arm
+        hp = lib.ygpu_host_alloc(max(T, 1) * 8)
+        if not hp:
+            raise SystemExit("ygpu_host_alloc failed")
+        pinned = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_uint64)), shape=(max(T, 1),))[:T]
+        pinned[:] = db.hashes
+    # device-resident copy (torch owns it; the library copies device-to-device once, outside the timed region); with N > 1
+    # only rank 0 needs the whole array, for the implementation-independent workload counts, and drops it again
+    counts = None
+    if world == 1 or rank == 0:
+        d_hashes = torch.from_numpy(db.hashes.view(np.int64)).to(dev)
+        d_offsets = torch.from_numpy(offsets.view(np.int64)).to(dev)
+        counts = independent_counts_torch(d_hashes, torch)
+        if world > 1:
+            d_hashes = d_offsets = None
+            torch.cuda.empty_cache()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if 8 * T <= L2_BYTES else None
-
-    def gather_pairs(n_r: int, to_host: bool):
-        """pair lists -> every rank (NCCL all-gather of counts, then of the padded lists)."""
-        if world == 1:
-            if to_host:
-                buf = np.empty(n_r, dtype=_lib.PAIR_DTYPE)
-                ctx.pairs_copy(buf.ctypes.data, False)
-                return buf
-            return n_r
-        mine = torch.zeros(max(n_r, 1) * 3, dtype=torch.int32, device=dev)
-        if n_r:
-            ctx.pairs_copy(mine.data_ptr(), True)
-        if to_host:
-            return sharding.all_gather_pairs(mine, n_r, world)      # NCCL all-gather, merged + ordered on the host
-        cnt = torch.tensor([n_r], dtype=torch.int64, device=dev)
-        allc = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, cnt)
-        sizes = allc.tolist()
-        m = max(max(sizes), 1)
-        padded = torch.zeros(m * 3, dtype=torch.int32, device=dev)
-        padded[: 3 * n_r] = mine[: 3 * n_r]
-        allp = torch.empty(world * m * 3, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allp, padded)
-        torch.cuda.synchronize()   # the NCCL gather runs on torch's stream: finish it inside the timed step
-        return sum(sizes)
 
     index_stats = {}
     mode = {"index": "single GPU"}
-    # N > 1, e2e: every rank copies only its slice of the hash array over its own PCIe link (pinned, torch-owned)
-    pinned_slice = None
+    row_bounds = sharding.split_rows_by_size(offsets, world)     # contiguous genome ranges of nearly equal hash counts
+    g0, g1 = int(row_bounds[rank]), int(row_bounds[rank + 1])
+    lo, hi = int(offsets[g0]), int(offsets[g1])
+    pinned_slice = d_slice = None
     if world > 1:
-        sb = sharding.slice_bounds(T, world)
-        pinned_slice = torch.empty(int(sb[rank + 1] - sb[rank]), dtype=torch.int64, pin_memory=True)
-        pinned_slice.numpy()[:] = db.hashes[int(sb[rank]):int(sb[rank + 1])].view(np.int64)
-
-    row_bounds = sharding.split_rows_by_size(offsets, world)     # depends on the sketch sizes only: once per database
-
-    def index_and_rows():
-        """index build + this rank's row range: hash-range sharded across the ranks when the database qualifies
-        (group streams all-gathered over NCCL), else replicated with rows split by measured work."""
-        if world > 1:
-            res = sharding.build_index_sharded(ctx, offsets, rank, world, dev, bounds=row_bounds)
-            if res is not None:
-                rb, re, total = res
-                index_stats.update(total, index_path=1)
-                mode["index"] = "hash-range sharded build, group streams all-gathered (NCCL)"
-                return rb, re
-            mode["index"] = "replicated build (database does not qualify for the partition path)"
-        index_stats.update(ctx.build_index())
-        b = ctx.row_partition(world)
-        return int(b[rank]), int(b[rank + 1])
+        # N > 1: the library's own sharded step (C++ host layer + NCCL + stores into peer buffers over NVLink): every rank is
+        # resident with the sketches of ITS genome range only; torch.distributed is used for the unique-id hand-over, the
+        # barrier around the timed region and the max over ranks, nothing on the data path
+        uid = [_lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+        pinned_slice = torch.empty(max(hi - lo, 1), dtype=torch.int64, pin_memory=True)
+        pinned_slice.numpy()[: hi - lo] = db.hashes[lo:hi].view(np.int64)
+        d_slice = torch.from_numpy(db.hashes[lo:hi].view(np.int64)).to(dev)
+        mode["index"] = ("sharded residency (each rank holds its genome range); level-1 words and group streams stored into the owners' "
+                         "buffers over NVLink by the partition / grouping kernels; NCCL for histograms, lengths, statistics, pair lists")
 
     def step_resident():
-        rb, re = index_and_rows()
-        n_r = ctx.pairwise_flag_device(THR, rb, re)
-        return gather_pairs(n_r, False)
+        if world > 1:
+            st, F = ctx.train_step_sharded(THR)
+            index_stats.update(st)
+            return F
+        index_stats.update(ctx.build_index())
+        return ctx.pairwise_flag_device(THR, 0, n)
 
     def step_e2e():
         if world > 1:
-            sharding.load_sketches_sharded(ctx, pinned_slice, offsets, T, rank, world, dev)
-        else:
-            ctx.load_sketches(pinned, offsets)
-        rb, re = index_and_rows()
-        n_r = ctx.pairwise_flag_device(THR, rb, re)
-        return gather_pairs(n_r, True)
+            ctx.load_sketches_sharded_ptr(pinned_slice.data_ptr(), False, offsets, g0, g1)
+            st, F = ctx.train_step_sharded(THR)
+            index_stats.update(st)
+            return ctx.pairs_host(F)                       # every rank reads the complete, ordered pair list back
+        ctx.load_sketches(pinned, offsets)
+        index_stats.update(ctx.build_index())
+        F = ctx.pairwise_flag_device(THR, 0, n)
+        return ctx.pairs_host(F)
 
     clock_samples = []      # samplers of both timed regions (resident, e2e): the step is short, so their samples are pooled
 
     def timed(fn, reload_first: bool):
         if reload_first:
-            ctx.load_sketches_device(d_hashes.data_ptr(), d_offsets.data_ptr(), n)
+            if world > 1:
+                ctx.load_sketches_sharded_ptr(d_slice.data_ptr(), True, offsets, g0, g1)
+            else:
+                ctx.load_sketches_device(d_hashes.data_ptr(), d_offsets.data_ptr(), n)
         for _ in range(args.warmup):
             if flush_buf is not None:
                 flush_buf.fill_(1)
@@ -454,16 +437,17 @@ def run_b200_arm(args):
                                  (8 * Tn + 4 * Wn + 12 * F) * share, k3_ms, "8*T + 4*W + 12*F (SURVEY.md 8d), x rank share"),
             "index_partition": rl("k2_hist1 + k2_scatter<1> + k2_hist2 + k2_scatter<2> (K2: MSD radix partition)" if msd
                                   else "CUB DeviceRadixSort of (hash, genome) pairs (general path)",
-                                  (52 * Tn if world == 1 else 20 * Tn + 32 * Tn / world) if msd else 12 * Tn * 2 * 7, part_ms,
-                                  ("8T + (12T+8T) + 8T + (8T+8T) = 52*T" if world == 1 else
-                                   "this rank: 8T + 12T read by every rank, 8T/N written, level 2 (8+16)T/N = 20*T + 32*T/N") if msd
+                                  48 * Tn / world if msd else 12 * Tn * 2 * 7, part_ms,
+                                  ("8T + (8T+8T) + 8T + (8T+8T) = 48*T" + ("" if world == 1 else
+                                   " /N: every rank partitions only its own slice; level-1 words are stored into the owners' buffers over NVLink")) if msd
                                   else "12*T*2*7 (SURVEY.md 8d)"),
             "index_grouping": rl("k2_group (K2: sub-bucket counting filter + dense candidate scan -> postings + per-genome work lists)" if msd
                                  else "k_flag_runs + scan + k_post_compact + k_items_scatter (general path)",
-                                 (8 * Tn + 4 * Pn + 8 * In if world == 1 else (8 * Tn + 6 * Pn + 8 * In) / world + 6 * Pn) if msd
+                                 (8 * Tn + 4 * Pn + 8 * In if world == 1 else (8 * Tn + 8 * In) / world + 12 * Pn) if msd
                                  else 12 * Tn + 4 * Pn + 16 * In, bucket_ms,
                                  ("8*T (words) + 4*P (postings) + 8*I (items)" if world == 1 else
-                                  "this rank: (8*T words + 6*P stream out + 8*I items)/N + 6*P gathered stream in (k2_group<stream> + k2_items)") if msd
+                                  "this rank: 8*T/N words in, 6*P/N stream entries stored to each of N ranks (6*P out), 6*P complete stream in, "
+                                  "8*I/N items (k2_group2<stream> + k2_items_regions + the control collectives)") if msd
                                  else "12*T + 4*P + 16*I"),
         }
         # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), when they were taken
@@ -483,17 +467,18 @@ def run_b200_arm(args):
             # the partition phase kernel by kernel (CUDA events around each launch, ygpu_timings.ms_hist1 ...)
             wsh = 1.0 if world == 1 else 1.0 / world
             for key, kern, nbytes, formula in (
-                    ("part_hist1", "k2_hist1 (level-1 digit histogram)", 8 * Tn, "8*T"),
-                    ("part_scatter1", "k2_scatter<1> (pack (hash, genome) words, scatter to level-1 buckets)", 12 * Tn + 8 * Tn * wsh,
-                     "12*T read + 8*T written" + ("" if world == 1 else "/N")),
+                    ("part_hist1", "k2_hist1 (level-1 digit histogram)", 8 * Tn * wsh, "8*T" + ("" if world == 1 else "/N")),
+                    ("part_scatter1", "k2_scatter<1> (pack (hash, genome) words, scatter to level-1 buckets"
+                                      + (")" if world == 1 else "; stores into the owner ranks' buffers over NVLink)"), 16 * Tn * wsh,
+                     "8*T read + 8*T written" + ("" if world == 1 else ", /N")),
                     ("part_hist2", "k2_hist2 (level-2 digit histogram)", 8 * Tn * wsh, "8*T" + ("" if world == 1 else "/N")),
                     ("part_scatter2", "k2_scatter<2> (scatter to final buckets)", 16 * Tn * wsh, "16*T" + ("" if world == 1 else "/N"))):
                 ms = tm_res["ms_" + key.split("_", 1)[1]] / steps
                 if ms > 0:
                     rooflines[key] = rl(kern, nbytes, ms, formula)
             if tm_res.get("ms_group", 0) > 0 and world > 1:
-                rooflines["index_grouping_k2_group"] = rl("k2_group<stream> alone", (8 * Tn + 6 * Pn) / world, tm_res["ms_group"] / steps,
-                                                          "(8*T words + 6*P stream)/N")
+                rooflines["index_grouping_k2_group"] = rl("k2_group2<stream> alone", 8 * Tn / world + 6 * Pn, tm_res["ms_group"] / steps,
+                                                          "8*T/N words in + 6*P/N stream entries stored to each of the N ranks")
         dominant = max((r for r in rooflines.values() if r.get("kernels", 1) == 1), key=lambda r: r["ms_per_launch"])
         line = {
             "metric": "ref-pair containments/s (yacht train hot path)", "value": pairs_total / (ms_res * 1e-3), "unit": "pairs/s",
@@ -503,7 +488,7 @@ def run_b200_arm(args):
             "e2e": {"value": pairs_total / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 * T + world * 8 * (n + 1), "d2h_bytes_per_step": 12 * F * world,
                     "ingest": "whole array from pinned host memory" if world == 1 else
-                              f"each rank copies 1/{world} of the hash array over its own PCIe link, slices all-gathered over NVLink (NCCL)",
+                              f"each rank copies the sketches of its genome range (1/{world} of the hashes) over its own PCIe link; no raw all-gather",
                     "phases_ms": {k: tm_e2e[k] / steps for k in ("ms_h2d", "ms_sort", "ms_index", "ms_count", "ms_pairsort", "ms_d2h")}},
             "gpu_launches": int(tm_res["n_kernel_launches"]),
             "library_launches": int(tm_res["n_library_launches"]),
@@ -545,7 +530,8 @@ def run_b200_arm(args):
                 line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line), flush=True)
 
-    lib.ygpu_host_free(hp)
+    if hp:
+        lib.ygpu_host_free(hp)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

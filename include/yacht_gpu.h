@@ -215,6 +215,33 @@ int ygpu_index_stream_copy(ygpu_ctx* ctx, uint32_t* d_gid_dst, uint16_t* d_rem_d
 int ygpu_index_finish(ygpu_ctx* ctx, const uint32_t* d_gid, const uint16_t* d_rem, uint64_t n_entries,
                       uint32_t row_begin, uint32_t row_end, const ygpu_index_stats* total);
 
+/* ---- sharded train step: one rank per GPU (threads of one process or one process per GPU, one node) ---------
+ * The reference's only parallelism is its contiguous row chunks per thread / pass over ONE shared index
+ * (main.cpp:338-349).  Across GPUs every rank holds the sketches of its own genome range only; the index build is
+ * split by hash range and exchanged by the kernels themselves (stores into the peers' buffers over NVLink), the
+ * pairwise count by query rows; NCCL (loaded on demand) carries the control data and the final pair lists.
+ *   rank 0:      ygpu_comm_get_unique_id(id)  -> hand `id` to every rank (any transport)
+ *   every rank:  ygpu_comm_init(ctx, rank, nranks, id)                              collective
+ *                ygpu_load_sketches_sharded(ctx, my hashes, ALL offsets, n, g_begin, g_end)   collective
+ *                ygpu_train_step_sharded(ctx, threshold, &stats, &n_pairs)          collective; then on every rank
+ *                ygpu_pairs_copy(ctx, dst, 0)   copies the COMPLETE pair list (all ranks' rows), sorted by (i, j)
+ * The genome ranges must be contiguous, in rank order, and cover [0, n).  Databases whose buckets outgrow shared
+ * memory (extreme skew) are refused with YGPU_ERR_STATE: use the replicated ygpu_build_index + row ranges.      */
+#define YGPU_COMM_ID_BYTES 128
+int ygpu_comm_get_unique_id(uint8_t* id /* [YGPU_COMM_ID_BYTES] */);
+int ygpu_comm_init(ygpu_ctx* ctx, int rank, int nranks, const uint8_t* id);
+int ygpu_comm_destroy(ygpu_ctx* ctx);
+int ygpu_load_sketches_sharded(ygpu_ctx* ctx, const uint64_t* hashes_slice, const uint64_t* offsets, uint32_t n_genomes,
+                               uint32_t g_begin, uint32_t g_end);
+/* same, the slice already on ctx's device (offsets stay a HOST pointer) */
+int ygpu_load_sketches_sharded_device(ygpu_ctx* ctx, const uint64_t* d_hashes_slice, const uint64_t* offsets, uint32_t n_genomes,
+                                      uint32_t g_begin, uint32_t g_end);
+/* streaming ingest (ygpu_upload_begin / _block) into a sharded residency: only the blocks of genomes [g_begin, g_end)
+ * were uploaded to this rank; block_dst[id] is relative to the first hash of genome g_begin                       */
+int ygpu_upload_finish_sharded(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n_genomes,
+                               uint32_t g_begin, uint32_t g_end);
+int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats /* may be NULL */, uint64_t* n_pairs_total);
+
 /* ---- run path ------------------------------------------------------------------------------ */
 /* sample: HOST pointer to the sample sketch hashes (any order).  Fills counts[n_genomes].
  * Step 1 (multisearch -t 0): n_overlap.  Step 2 (get_exclusive_hashes): among the genomes with

@@ -1,0 +1,84 @@
+"""The library's sharded train step (ygpu_comm_init / ygpu_load_sketches_sharded / ygpu_train_step_sharded): every rank
+resident with its own genome range, index build split by hash range with the words and group streams stored into the
+peers' buffers by the kernels, pairwise count by query rows, pair lists gathered over NCCL.  Bit-exact against the oracle
+on every rank.  One rank runs anywhere; 2 / 4 / 8 ranks need that many GPUs (threads of one process here, as the drop-in
+executable runs them; bench.py runs the same entry points with one process per GPU)."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import train_oracle as to
+from yacht_b200 import _lib, sharding, synth
+
+pytestmark = pytest.mark.gpu
+THR = 0.95 ** 31
+
+
+def _run_ranks(db, nranks, thr):
+    offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+    bounds = sharding.split_rows_by_size(offsets, nranks)
+    uid = _lib.comm_unique_id()
+    out = [None] * nranks
+    err = [None] * nranks
+
+    def work(r):
+        try:
+            with _lib.GpuContext(r) as ctx:
+                ctx.comm_init(r, nranks, uid)
+                g0, g1 = int(bounds[r]), int(bounds[r + 1])
+                sl = db.hashes[int(offsets[g0]):int(offsets[g1])]
+                for rep in range(2):            # the second step reuses the shared exchange buffers
+                    ctx.load_sketches_sharded(sl, offsets, g0, g1)
+                    st, F = ctx.train_step_sharded(thr)
+                out[r] = (st, ctx.pairs_host(F))
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def _check(db, nranks, thr):
+    ref = to.oracle_train(db.hashes, db.offsets, thr)
+    res = _run_ranks(db, nranks, thr)
+    for st, pairs in res:
+        assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index)
+        assert (st["n_postings"], st["n_increments"]) == (ref.n_postings, ref.n_increments)
+        assert len(pairs) == len(ref.pairs)
+        assert np.array_equal(pairs["i"], ref.pairs["i"]) and np.array_equal(pairs["j"], ref.pairs["j"])
+        assert np.array_equal(pairs["count"], ref.pairs["count"])
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+def test_sharded_step_matches_oracle(nranks):
+    if _lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    # large enough for two partition levels and 32-bit remaining keys (the sharded path refuses tiny databases)
+    db = synth.make_reference_db(6000, 11, mean_size=3000, sd_size=800)
+    _check(db, nranks, THR)
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_sharded_step_edge_rows(nranks):
+    if _lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    # empty sketches, tiny genomes (many genome boundaries per tile), threshold 0 (every overlapping pair is flagged)
+    rng = np.random.default_rng(5)
+    base = synth.make_reference_db(3000, 12, mean_size=4000, sd_size=500)
+    parts = [base.sketch(g) for g in range(base.n)]
+    parts[0] = np.zeros(0, dtype=np.uint64)
+    parts[1500] = np.zeros(0, dtype=np.uint64)
+    parts[-1] = np.zeros(0, dtype=np.uint64)
+    for k in range(200):
+        parts.append(np.unique(rng.choice(parts[7 + k], size=int(rng.integers(1, 20)), replace=False)))
+    db = synth.from_sketches(parts)
+    _check(db, nranks, 0.0)
+    _check(db, nranks, THR)

@@ -22,7 +22,10 @@ ABI_SYMBOLS = [
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test", "ygpu_index_partial", "ygpu_index_stream_copy", "ygpu_index_finish",
     "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
+    "ygpu_comm_get_unique_id", "ygpu_comm_init", "ygpu_comm_destroy", "ygpu_load_sketches_sharded", "ygpu_load_sketches_sharded_device",
+    "ygpu_train_step_sharded", "ygpu_upload_finish_sharded",
 ]
+COMM_ID_BYTES = 128
 
 
 class YgpuError(RuntimeError):
@@ -119,6 +122,13 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_exclusive_hashes.argtypes = [vp, vp, u64, vp, vp]
     lib.ygpu_hyp_test.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, ctypes.c_double, vp, ctypes.c_int, vp]
     lib.ygpu_greedy_select.argtypes = [vp, u32, vp, u64, vp, ctypes.POINTER(u32)]
+    lib.ygpu_comm_get_unique_id.argtypes = [vp]
+    lib.ygpu_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.ygpu_comm_destroy.argtypes = [vp]
+    lib.ygpu_load_sketches_sharded.argtypes = [vp, vp, vp, u32, u32, u32]
+    lib.ygpu_load_sketches_sharded_device.argtypes = [vp, vp, vp, u32, u32, u32]
+    lib.ygpu_upload_finish_sharded.argtypes = [vp, vp, u32, vp, u32, u32, u32]
+    lib.ygpu_train_step_sharded.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)  # AttributeError here means the .so does not match include/yacht_gpu.h
     _lib = lib
@@ -251,6 +261,37 @@ class GpuContext:
                                                        ctypes.byref(n_out)), "ygpu_pairwise_flag_device")
         return int(n_out.value)
 
+    # ---- sharded train step: one rank per GPU (include/yacht_gpu.h) ----------------------------------------
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes) -> None:
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self.lib.ygpu_comm_init(self.h, int(rank), int(nranks), ctypes.cast(buf, ctypes.c_void_p)), "ygpu_comm_init")
+
+    def load_sketches_sharded(self, hashes_slice: np.ndarray, offsets: np.ndarray, g_begin: int, g_end: int) -> None:
+        """hashes_slice = hashes[offsets[g_begin]:offsets[g_end]] (HOST); offsets = the offsets of ALL genomes."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        hashes_slice = np.ascontiguousarray(hashes_slice, dtype=np.uint64)
+        self._check(self.lib.ygpu_load_sketches_sharded(self.h, hashes_slice.ctypes.data if hashes_slice.size else None, offsets.ctypes.data,
+                                                        int(offsets.shape[0]) - 1, int(g_begin), int(g_end)), "ygpu_load_sketches_sharded")
+
+    def load_sketches_sharded_ptr(self, slice_ptr: int, on_device: bool, offsets: np.ndarray, g_begin: int, g_end: int) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        fn = self.lib.ygpu_load_sketches_sharded_device if on_device else self.lib.ygpu_load_sketches_sharded
+        self._check(fn(self.h, ctypes.c_void_p(slice_ptr), offsets.ctypes.data, int(offsets.shape[0]) - 1, int(g_begin), int(g_end)),
+                    "ygpu_load_sketches_sharded")
+
+    def train_step_sharded(self, threshold: float) -> Tuple[dict, int]:
+        """Index build + pairwise count/flag over all ranks; afterwards pairs_copy()/pairs_host() give the COMPLETE sorted pair list."""
+        st = IndexStats()
+        n_out = ctypes.c_uint64(0)
+        self._check(self.lib.ygpu_train_step_sharded(self.h, float(threshold), ctypes.byref(st), ctypes.byref(n_out)), "ygpu_train_step_sharded")
+        return st.as_dict(), int(n_out.value)
+
+    def pairs_host(self, n_pairs: int) -> np.ndarray:
+        buf = np.empty(n_pairs, dtype=PAIR_DTYPE)
+        if n_pairs:
+            self.pairs_copy(buf.ctypes.data, False)
+        return buf
+
     def pairs_copy(self, dst_ptr: int, dst_is_device: bool) -> None:
         self._check(self.lib.ygpu_pairs_copy(self.h, dst_ptr, 1 if dst_is_device else 0), "ygpu_pairs_copy")
 
@@ -340,6 +381,17 @@ def greedy_select(offsets: np.ndarray, pairs: np.ndarray) -> np.ndarray:
     if rc != 0:
         raise YgpuError(f"ygpu_greedy_select failed ({rc})")
     return out[: int(ns.value)].copy()
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to every rank)."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.ygpu_comm_get_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+    if rc != 0:
+        msg = lib.ygpu_last_error(None)
+        raise YgpuError(f"ygpu_comm_get_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+    return buf.raw
 
 
 def device_count() -> int:

@@ -7,6 +7,9 @@
 #include <algorithm>
 #include "../../include/yacht_gpu.h"
 
+struct ygpu_comm;
+#define YG_MAX_RANKS 16
+
 struct ygpu_ctx {
     int device = 0;
     int num_sms = 148;
@@ -84,6 +87,27 @@ struct ygpu_ctx {
     uint64_t n_pairs = 0;
     uint32_t force_tile_w = 0;      // test hook: cap the accumulator tile width (0 = automatic)
     int force_u16 = 0;              // test hook: packed 16-bit counters even when 32-bit ones fit
+
+    // ---- sharded residency + multi-GPU train step (comm.cu, index_msd.cu: ygpu_train_step_sharded) ----------------
+    ygpu_comm* comm = nullptr;
+    bool sharded = false;           // this context holds only the sketches of genomes [g_begin, g_end)
+    uint32_t g_begin = 0, g_end = 0;
+    uint64_t T_global = 0;
+    uint32_t max_sketch_global = 0;
+    uint64_t* d_offsets_local = nullptr;    // [g_end - g_begin + 1] offsets relative to the resident slice
+    uint64_t* d_row_begin_local = nullptr;  // [n] start of row g's work list in d_row_items (rows of the slice only)
+    uint64_t sh_cap = 0;            // per-rank capacity (words / stream entries) of the exchange buffers
+    uint32_t* d_sh_hist_all = nullptr;      // [nranks][NB_MAX] level-1 histograms of every rank's slice
+    uint32_t* d_sh_owner = nullptr;         // [NB_MAX] owner rank of every level-1 digit
+    unsigned long long* d_sh_info = nullptr;// small device block: digit range, word count, stream lengths ...
+    void* sh_peer_ent1[YG_MAX_RANKS] = {};  // peers' level-1 exchange buffers (d_ent1)
+    void* sh_peer_gid[YG_MAX_RANKS] = {};   // peers' group-stream buffers (d_post / d_st_rem)
+    void* sh_peer_rem[YG_MAX_RANKS] = {};
+    void* sh_shared_ent1 = nullptr;         // which allocations the peer pointers above refer to (re-shared when they move)
+    void* sh_shared_gid = nullptr;
+    void* sh_shared_rem = nullptr;
+    ygpu_pair* d_pairs_local = nullptr;     // this rank's pairs before the gather
+    uint64_t pairs_local_cap = 0;
 
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
     void* upload = nullptr;         // streaming ingest state (yacht_gpu.cu: ygpu_upload_*)

@@ -162,6 +162,11 @@ struct ScatterArgs {
     uint32_t* cursor;            // per output bucket
     uint32_t* hist2;             // hist2 kernel only
     const uint2* units;          // level 2: per tile {first word, words | level-1 bucket << 16} (k2_units)
+    // sharded build across GPUs (level 1, PEER): a word goes to the rank that owns its leading digit, stored straight into
+    // that rank's level-1 buffer over NVLink (peer_ent: the ranks' d_ent1 as mapped into this process)
+    uint32_t gid_base;           // genome id of the first resident sketch (sharded residency: offsets are slice-relative)
+    const uint32_t* owner;       // [nb1] owner rank of every level-1 digit
+    uint64_t* peer_ent[YG_MAX_RANKS];
 };
 
 template <int LEVEL>
@@ -269,19 +274,20 @@ __global__ void __launch_bounds__(256) k2_hist2(const ScatterArgs a, const MsdPl
 // reordered words are staged in the buffer the tile came in (its words are in registers by then), so a CTA holds two
 // tile buffers, not three.  Level 1 derives the genome id of every hash slot from the CSR offsets (a few boundaries
 // per tile, kept in shared memory) instead of reading a 4-byte id per slot.
-template <int LEVEL>
+template <int LEVEL, bool PEER>
 __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a, const MsdPlan p, uint32_t unit_first, uint32_t n_units) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* buf0 = (uint64_t*)smem_raw;                          // [2][SC_BUF]
     const uint32_t nd = LEVEL == 1 ? p.nb1 : (1u << p.d2);
-    uint32_t* cnt = (uint32_t*)(buf0 + 2 * SC_BUF);                // [nd]
+    uint64_t** gptr = (uint64_t**)(buf0 + 2 * SC_BUF);             // [nd] PEER only: where this tile's run of digit d goes
+    uint32_t* cnt = (uint32_t*)(gptr + (PEER ? nd : 0));           // [nd]
     uint32_t* lbase = cnt + nd;                                    // [nd]
     uint32_t* gbase = lbase + nd;                                  // [nd]
     uint16_t* sdig = (uint16_t*)(gbase + nd);                      // [SC_TILE]
     typedef cub::BlockScan<uint32_t, SC_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_ts;
     __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint64_t bnd[2][SC_BND];
+    __shared__ uint32_t bnd[2][SC_BND];       // level 1: genome boundaries inside a tile, relative to its first hash slot
 
     const uint32_t tid = threadIdx.x;
     if (LEVEL == 2) n_units = min(n_units, a.tile_start[p.nb1]);
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
     auto fetch_bnd = [&](uint32_t unit, uint32_t slot) {
         if (LEVEL != 1 || unit >= n_units) return;
         const uint32_t g0 = a.tile_g0[unit], nb = a.tile_g0[unit + 1] - g0;
-        if (nb <= SC_BND && tid < nb) bnd[slot][tid] = a.offsets[g0 + 1 + tid];
+        if (nb <= SC_BND && tid < nb) bnd[slot][tid] = (uint32_t)min(a.offsets[g0 + 1 + tid] - (uint64_t)unit * SC_TILE, (uint64_t)SC_TILE);
     };
     auto issue = [&](uint32_t unit, uint32_t slot) {              // thread 0 only
         uint64_t begin; uint32_t m, b1;
@@ -338,15 +344,14 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
                 if (LEVEL == 1) {
                     const uint32_t d = digit1_of(e[k], p);
                     if (d >= p.dlo && d < p.dhi) {
-                        const uint64_t gi = begin + idx;
                         uint32_t g = g0;
                         if (nbnd <= SC_BND) {
-                            for (uint32_t j = 0; j < nbnd; j++) g += bnd[slot][j] <= gi ? 1u : 0u;
+                            for (uint32_t j = 0; j < nbnd; j++) g += bnd[slot][j] <= idx ? 1u : 0u;
                         } else {
-                            g = genome_of(a.offsets, g0, g0 + nbnd, gi);
+                            g = genome_of(a.offsets, g0, g0 + nbnd, begin + idx);
                         }
                         dg[k] = (uint16_t)d;
-                        e[k] = pack_entry(e[k], g, p);
+                        e[k] = pack_entry(e[k], a.gid_base + g, p);
                     }
                 } else {
                     dg[k] = (uint16_t)digit2_of(e[k], p);
@@ -358,25 +363,31 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
             if (dg[k] != SKIP) rk[k] = (uint16_t)atomicAdd(&cnt[dg[k]], 1u);
         __syncthreads();                   // every word of the tile is in registers: the buffer becomes the staging area
         uint32_t mv = 0;     // words of this tile that are kept
-        // exclusive scan of cnt -> lbase; reserve global space per digit -> gbase; counters back to zero
+        // exclusive scan of cnt -> lbase; reserve global space per digit (the cursor atomics' answers are only needed for the
+        // write-out: they travel while the tile is being reordered); counters back to zero
+        constexpr uint32_t PER_MAX = (NB_MAX + SC_THREADS - 1) / SC_THREADS;
+        uint32_t gb0[PER_MAX], lb0[PER_MAX];
+        const uint32_t per = (nd + SC_THREADS - 1) / SC_THREADS;
+        const uint32_t d0 = tid * per;
         {
-            const uint32_t per = (nd + SC_THREADS - 1) / SC_THREADS;
-            const uint32_t d0 = tid * per;
             uint32_t s = 0;
             for (uint32_t k = 0; k < per; k++) if (d0 + k < nd) s += cnt[d0 + k];
             uint32_t off;
             Scan(scan_ts).ExclusiveSum(s, off, mv);
-            for (uint32_t k = 0; k < per; k++) {
+#pragma unroll
+            for (uint32_t k = 0; k < PER_MAX; k++) {
                 const uint32_t d = d0 + k;
-                if (d < nd) {
+                gb0[k] = 0; lb0[k] = 0xFFFFFFFFu;
+                if (k < per && d < nd) {
                     const uint32_t c = cnt[d];
                     lbase[d] = off;
-                    off += c;
                     if (c) {
                         const uint64_t ci = LEVEL == 1 ? (uint64_t)d : (((uint64_t)b1 << p.d2) + d);
-                        gbase[d] = atomicAdd(&a.cursor[ci], c);
+                        gb0[k] = atomicAdd(&a.cursor[ci], c);
+                        lb0[k] = off;
                         cnt[d] = 0;
                     }
+                    off += c;
                 }
             }
         }
@@ -389,13 +400,23 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k2_scatter(const ScatterArgs a,
                 sdig[q] = dg[k];
             }
         }
+        // where the run of digit d goes: slot q of the reordered tile lands at gbase[d] + q (PEER: in the owner's buffer)
+#pragma unroll
+        for (uint32_t k = 0; k < PER_MAX; k++) {
+            if (lb0[k] != 0xFFFFFFFFu) {
+                const uint32_t d = d0 + k;
+                if (PEER) gptr[d] = a.peer_ent[a.owner[d]] + gb0[k] - lb0[k];
+                else gbase[d] = gb0[k] - lb0[k];
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < SC_ITEMS; k++) {
             const uint32_t q = k * SC_THREADS + tid;
             if (q < mv) {
                 const uint32_t d = sdig[q];
-                a.out_ent[(uint64_t)gbase[d] + (q - lbase[d])] = buf[q];
+                if (PEER) gptr[d][q] = buf[q];                               // a store over NVLink when the owner is a peer
+                else a.out_ent[(uint64_t)(uint32_t)(gbase[d] + q)] = buf[q];
             }
         }
         fetch_bnd(unit + gridDim.x, slot ^ 1u);
@@ -452,6 +473,13 @@ struct GroupArgs {
     uint32_t* st_gid;            // genome ids, group by group, ascending inside a group
     unsigned short* st_rem;      // members of the same group that follow
     unsigned long long* scal;
+    // sharded build across GPUs: the bucket range comes from device memory (k2s_prep), and k2_group2<STREAM> stores every
+    // bucket's groups into ALL ranks' stream buffers (region of this rank) -- the exchange is part of the kernel
+    const unsigned long long* range;   // {first bucket, end bucket} or NULL (then b_lo / b_hi)
+    int n_peers;
+    uint64_t region_base;              // first stream entry of this rank's region in every rank's buffer
+    uint32_t* peer_gid[YG_MAX_RANKS];
+    unsigned short* peer_rem[YG_MAX_RANKS];
 };
 
 struct GroupStats { uint32_t heads, single, dups; unsigned long long w; };   // postings = T - singles, items = postings - shared groups
@@ -730,15 +758,23 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
 
     // thread 0: the next bucket this CTA takes at or after `b` (stride gridDim.x) that is non-empty and fits; its
     // extent goes to sm.next[par] and its words are requested from the copy engine
-    uint32_t b_next = a.b_lo + blockIdx.x;       // thread 0 only
+    const uint32_t b_end = a.range ? (uint32_t)a.range[1] : a.b_hi;
+    uint32_t b_next = (a.range ? (uint32_t)a.range[0] : a.b_lo) + blockIdx.x;       // thread 0 only
+    // the extent of bucket b_next is fetched one phase before it is needed, so that the two dependent loads never sit between
+    // two barriers of the whole CTA
+    uint32_t pre_lo = 0, pre_hi = 0;
+    auto preload = [&]() {
+        if (b_next < b_end) { pre_lo = a.base[b_next]; pre_hi = a.base[b_next + 1]; }
+    };
     auto advance = [&](uint32_t par) {
         uint32_t bb = 0, m = 0;
-        while (b_next < a.b_hi) {
-            bb = a.base[b_next];
-            m = a.base[b_next + 1] - bb;
+        while (b_next < b_end) {
+            bb = pre_lo;
+            m = pre_hi - pre_lo;
             b_next += gridDim.x;
             if (m && m <= G2_MAXM) break;
             m = 0;
+            preload();
         }
         sm.next[par][0] = bb;
         sm.next[par][1] = m;
@@ -751,17 +787,19 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
         mbar_init_fence();
+        preload();
         advance(0);
     }
     __syncthreads();
 
     uint32_t n_heads = 0, n_single = 0, n_dups = 0;
     unsigned long long n_w = 0;
-    GroupPending pd{0ull, 0u, 0u, false};
+    GroupPending pd{0ull, 0u, 0u, false}, pd2{0ull, 0u, 0u, false};   // two appends in flight: the atomic's answer is consumed two items later
     uint32_t par = 0, phase = 0;
     for (;;) {
         const uint32_t bb = sm.next[par][0], m = sm.next[par][1];
         if (!m) break;
+        if (tid == 0) preload();
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
         // ---- A: four words per thread, sub-bucket rank -----------------------------------------------------------
@@ -802,9 +840,9 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             }
             if (lane == 31) sm.wsum[warp] = inc;
             __syncthreads();
-            uint32_t wp = 0;
-#pragma unroll
-            for (int w = 0; w < G2_THREADS / 32 - 1; w++) wp += (w < (int)warp) ? sm.wsum[w] : 0u;
+            const uint4 wa = *reinterpret_cast<const uint4*>(&sm.wsum[0]), wb = *reinterpret_cast<const uint4*>(&sm.wsum[4]);
+            const uint32_t wp = (warp > 0 ? wa.x : 0u) + (warp > 1 ? wa.y : 0u) + (warp > 2 ? wa.z : 0u) + (warp > 3 ? wa.w : 0u) +
+                                (warp > 4 ? wb.x : 0u) + (warp > 5 ? wb.y : 0u) + (warp > 6 ? wb.z : 0u);
             const uint32_t p0 = wp + inc - sum;
             const uint32_t p1 = p0 + c0.x, p2 = p1 + c0.y, p3 = p2 + c0.z, p4 = p3 + c0.w, p5 = p4 + c1.x, p6 = p5 + c1.y, p7 = p6 + c1.z;
             *reinterpret_cast<uint4*>(&sm.start2[8 * tid]) = make_uint4(p0 | (p1 << 16), p2 | (p3 << 16), p4 | (p5 << 16), p6 | (p7 << 16));
@@ -840,25 +878,17 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             const uint32_t lo = x & 0xffffu, c = x >> 16;
             const uint32_t Kq = (uint32_t)(wq >> 32);
             uint32_t L = 0, rank = 0, rall = 0, dup = 0;
-            if (c <= 4) {
+            // four words of the sub-bucket per trip, branch-free: nearly every sub-bucket is done after one trip, clusters of
+            // 5..8 genomes after two; lanes only diverge on the trip count
+            for (uint32_t j0 = 0; j0 < c; j0 += 4) {
 #pragma unroll
                 for (uint32_t j = 0; j < 4; j++) {
-                    const uint64_t w = sm.cand[lo + j];
-                    const bool valid = j < c;
+                    const uint32_t jj = j0 + j;
+                    const uint64_t w = sm.cand[lo + jj];
+                    const bool valid = jj < c;
                     const bool same = valid & ((uint32_t)(w >> 32) == Kq);
-                    const bool tie = valid & (w == wq) & (lo + j < q);           // same genome too: in-sketch duplicate
+                    const bool tie = valid & (w == wq) & (lo + jj < q);          // same genome too: in-sketch duplicate
                     const bool before = (valid & (w < wq)) | tie;
-                    L += same ? 1u : 0u;
-                    rank += (same & before) ? 1u : 0u;
-                    rall += before ? 1u : 0u;
-                    dup |= tie ? 1u : 0u;
-                }
-            } else {
-                for (uint32_t j = 0; j < c; j++) {
-                    const uint64_t w = sm.cand[lo + j];
-                    const bool same = (uint32_t)(w >> 32) == Kq;
-                    const bool tie = (w == wq) & (lo + j < q);
-                    const bool before = (w < wq) | tie;
                     L += same ? 1u : 0u;
                     rank += (same & before) ? 1u : 0u;
                     rall += before ? 1u : 0u;
@@ -874,6 +904,44 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             if (L >= 2 && rank == 0) n_w += (unsigned long long)L * L;
         }
         __syncthreads();
+        if (STREAM) {
+            // ---- F': the groups, holes squeezed out, go to every rank's stream buffer (NVLink stores for the peers) -----
+            uint32_t* cg = reinterpret_cast<uint32_t*>(sm.cand);                     // the candidate array is dead: compact copy
+            unsigned short* cr = reinterpret_cast<unsigned short*>(cg + G2_WIN);
+            uint32_t np = 0;
+            for (uint32_t x0 = 0; x0 < ncand; x0 += G2_THREADS) {
+                const uint32_t x = x0 + tid;
+                const uint32_t rr = x < ncand ? sm.stg_r[x] : 0x4000u;
+                const bool member = !(rr & 0x4000u);
+                const uint32_t bal = __ballot_sync(0xffffffffu, member);
+                if (lane == 0) sm.wsum[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t off = np, tot = 0;
+#pragma unroll
+                for (int w = 0; w < G2_THREADS / 32; w++) {
+                    const uint32_t c = sm.wsum[w];
+                    off += (w < (int)warp) ? c : 0u;
+                    tot += c;
+                }
+                if (member) {
+                    const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
+                    cg[pos] = sm.stg_g[x];
+                    cr[pos] = (unsigned short)(rr & 0x3fffu);
+                }
+                np += tot;
+                __syncthreads();
+            }
+            if (tid == 0) sm.wsum[0] = np ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np) : 0u;
+            __syncthreads();
+            const uint64_t gpos = a.region_base + sm.wsum[0];
+            for (int q = 0; q < a.n_peers; q++) {
+                uint32_t* dg = a.peer_gid[q] + gpos;
+                unsigned short* dr = a.peer_rem[q] + gpos;
+                for (uint32_t i = tid; i < np; i += G2_THREADS) { dg[i] = cg[i]; dr[i] = cr[i]; }
+            }
+            par ^= 1u;
+            continue;          // (wsum[0] is rewritten in the next bucket's phase B, two barriers from here)
+        }
         // ---- F: postings + work items, one thread per ordered slot ------------------------------------------------------
         for (uint32_t x = tid; x < ncand; x += G2_THREADS) {
             const uint32_t rr = sm.stg_r[x];
@@ -892,14 +960,16 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
                 }
                 const uint32_t slot = (uint32_t)atomicAdd(&a.row_cnt[g], 1ull);
                 const uint32_t dst = (uint32_t)a.row_off[g];
-                if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued one slot ago
-                pd.item = item; pd.dst = dst; pd.slot = slot; pd.has = true;
+                if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued two items ago
+                pd = pd2;
+                pd2.item = item; pd2.dst = dst; pd2.slot = slot; pd2.has = true;
             }
         }
         par ^= 1u;
         // (the next bucket's phase A only touches stage / cnt; its barriers order everything else against this phase F)
     }
     if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;
+    if (pd2.has) a.row_items[(uint64_t)pd2.dst + pd2.slot] = pd2.item;
     const unsigned long long heads = block_sum<G2_THREADS>(n_heads);
     const unsigned long long single = block_sum<G2_THREADS>(n_single);
     const unsigned long long w = block_sum<G2_THREADS>(n_w);
@@ -917,15 +987,14 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
 // (bucket ordinal | remaining hash bits | genome id), sorted by one device-wide radix sort, and grouped by
 // neighbour comparison -- same outputs as k2_group (postings, work items appended to the genome lists, the
 // statistics), postings stored behind the T regular slots of d_post.  Everything else stays on the fast path.
-constexpr uint32_t BIG_MAX = 4096;      // more oversized buckets than this: the general (sort) path takes the database
 
 __global__ void __launch_bounds__(256) k2_big_list(const uint32_t* __restrict__ base, uint32_t b_lo, uint32_t b_hi,
-                                                   uint32_t* __restrict__ list, unsigned long long* __restrict__ scal) {
+                                                   uint32_t* __restrict__ list, uint32_t list_cap, unsigned long long* __restrict__ scal) {
     for (uint32_t b = b_lo + blockIdx.x * blockDim.x + threadIdx.x; b < b_hi; b += gridDim.x * blockDim.x) {
         const uint32_t m = base[b + 1] - base[b];
         if (m > BK_CAP) {
             const unsigned long long k = atomicAdd(&scal[SCM_STREAM], 1ull);       // (slot unused outside stream mode)
-            if (k < BIG_MAX) list[k] = b;
+            if (k < list_cap) list[k] = b;
         }
     }
 }
@@ -1018,6 +1087,131 @@ __global__ void __launch_bounds__(256) k2_items(const uint32_t* __restrict__ gid
         }
         const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
         row_items[row_off[g] + slot] = item;
+    }
+}
+
+// sharded build: the stream is N regions (one per producing rank) of `cap` slots each, region q holding lens[q] entries
+__global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem,
+                                                        const unsigned long long* __restrict__ lens, int n_regions, uint64_t cap,
+                                                        uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_off,
+                                                        unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items) {
+    for (int q = 0; q < n_regions; q++) {
+        const uint64_t base = (uint64_t)q * cap, len = lens[q];
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t x = base + i;
+            const uint32_t r = rem[x];
+            if (!r) continue;
+            const uint32_t g = gid[x];
+            if (g < row_begin || g >= row_end) continue;
+            uint64_t item;
+            if (can_inline && r <= 3) {
+                item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
+                if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
+                if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
+            } else {
+                item = ((x + 1) << 32) | ((uint64_t)r << 2);
+            }
+            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            row_items[row_off[g] + slot] = item;
+        }
+    }
+}
+
+// ---- sharded build: one CTA turns the all-gathered level-1 histograms into the exchange plan --------------------------
+// Every rank computes the same plan from the same table: digit d belongs to rank floor(N * hashes before d / T) (contiguous
+// digit ranges of nearly equal hash counts); inside its owner's level-1 buffer the words of digit d lie at (hashes of the
+// owner's earlier digits) + (words of digit d from lower ranks), so every source rank knows exactly where its words go and
+// the level-1 scatter can store them there directly.  For the digits this rank owns it also lays out level 2 (bucket
+// bases and tile prefix in the GLOBAL digit numbering: foreign digits are simply empty).
+enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_LENS = 8 };   // slots of ctx->d_sh_info (LENS: [nranks])
+
+__global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hist_all, uint32_t nb, int nranks, int rank, int d2,
+                                                 uint32_t* __restrict__ owner, uint32_t* __restrict__ cursor, uint32_t* __restrict__ base,
+                                                 uint32_t* __restrict__ tile_start, unsigned long long* __restrict__ info,
+                                                 unsigned long long* __restrict__ scal) {
+    typedef cub::BlockScan<unsigned long long, 1024> Scan64;
+    typedef cub::BlockScan<uint32_t, 1024> Scan32;
+    __shared__ typename Scan64::TempStorage ts0;
+    __shared__ typename Scan32::TempStorage ts1, ts2;
+    __shared__ unsigned char s_own[NB_MAX];
+    __shared__ unsigned long long s_start[YG_MAX_RANKS];
+    __shared__ uint32_t s_lo, s_hi;
+    constexpr int per = (NB_MAX + 1023) / 1024;
+    unsigned long long g[per], pre[per], gs = 0;
+    for (int k = 0; k < per; k++) {
+        const uint32_t d = threadIdx.x * per + k;
+        g[k] = 0; pre[k] = 0;
+        if (d < nb)
+            for (int q = 0; q < nranks; q++) {
+                const uint32_t h = hist_all[(size_t)q * NB_MAX + d];
+                g[k] += h;
+                if (q < rank) pre[k] += h;
+            }
+        gs += g[k];
+    }
+    unsigned long long acc, total;
+    Scan64(ts0).ExclusiveSum(gs, acc, total);
+    if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0; }
+    unsigned long long ex[per];
+    uint32_t own[per];
+    for (int k = 0; k < per; k++) {
+        const uint32_t d = threadIdx.x * per + k;
+        ex[k] = acc;
+        acc += g[k];
+        own[k] = total ? (uint32_t)min((unsigned long long)(nranks - 1), ex[k] * (unsigned long long)nranks / total) : 0u;
+        if (d < nb) s_own[d] = (unsigned char)own[k];
+    }
+    __syncthreads();
+    for (int k = 0; k < per; k++) {
+        const uint32_t d = threadIdx.x * per + k;
+        if (d < nb && (d == 0 || s_own[d - 1] != own[k])) s_start[own[k]] = ex[k];
+    }
+    __syncthreads();
+    uint32_t hm[per], tl[per], hs = 0, tsum = 0, mx = 0;
+    for (int k = 0; k < per; k++) {
+        const uint32_t d = threadIdx.x * per + k;
+        hm[k] = 0;
+        if (d < nb) {
+            owner[d] = own[k];
+            cursor[d] = (uint32_t)(ex[k] - s_start[own[k]] + pre[k]);
+            if ((int)own[k] == rank) {
+                hm[k] = (uint32_t)g[k];
+                atomicMin(&s_lo, d);
+                atomicMax(&s_hi, d + 1);
+            }
+        }
+        tl[k] = (hm[k] + SC_TILE - 1) / SC_TILE;
+        hs += hm[k]; tsum += tl[k]; mx = max(mx, hm[k]);
+    }
+    uint32_t hoff, toff, htot, ttot;
+    Scan32(ts1).ExclusiveSum(hs, hoff, htot);
+    Scan32(ts2).ExclusiveSum(tsum, toff, ttot);
+    for (int k = 0; k < per; k++) {
+        const uint32_t d = threadIdx.x * per + k;
+        if (d < nb) { base[d] = hoff; tile_start[d] = toff; }
+        hoff += hm[k]; toff += tl[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        base[nb] = htot; tile_start[nb] = ttot;
+        const uint32_t lo = s_lo == 0xFFFFFFFFu ? 0u : s_lo, hi = s_lo == 0xFFFFFFFFu ? 0u : s_hi;
+        info[SHI_DLO] = lo; info[SHI_DHI] = hi; info[SHI_TMINE] = htot;
+        info[SHI_BLO] = (unsigned long long)lo << d2; info[SHI_BHI] = (unsigned long long)hi << d2;
+    }
+    if (mx) atomicMax(&scal[SCM_MAXB], (unsigned long long)mx);
+}
+
+// sketch sizes of ALL genomes and the work-list starts of the resident rows (sharded residency)
+__global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ offsets, uint32_t n, uint32_t g_begin, uint32_t g_end,
+                                                 uint32_t* __restrict__ sizes, uint64_t* __restrict__ row_begin_local,
+                                                 uint64_t* __restrict__ offsets_local) {
+    const uint64_t o0 = offsets[g_begin];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g <= n; g += gridDim.x * blockDim.x) {
+        if (g < n) {
+            sizes[g] = (uint32_t)(offsets[g + 1] - offsets[g]);
+            row_begin_local[g] = (g >= g_begin && g < g_end) ? offsets[g] - o0 : 0ull;
+        }
+        if (g >= g_begin && g <= g_end) offsets_local[g - g_begin] = offsets[g] - o0;
     }
 }
 
@@ -1124,12 +1318,12 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         YG_CUDA(ctx, cudaGetLastError());
         a.tile_g0 = ctx->d_tile_g0;
         const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)p.nb1 * 12 + (size_t)SC_TILE * 2;
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1>, SC_THREADS, smem));
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1, false>, SC_THREADS, smem));
         const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[2], st));
-        k2_scatter<1><<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
+        k2_scatter<1, false><<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[3], st));
     }
@@ -1163,12 +1357,12 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         YG_CUDA(ctx, cudaMemcpyAsync(cursor, base2, ((uint64_t)p.nfb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         a.cursor = cursor;
         const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)(1u << d2) * 12 + (size_t)SC_TILE * 2;
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2>, SC_THREADS, smem));
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2, false>, SC_THREADS, smem));
         const int grid = ctx->num_sms * std::max(occ, 1);
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[5], st));
-        k2_scatter<2><<<grid, SC_THREADS, smem, st>>>(a, p, p.unit_lo, p.unit_hi);
+        k2_scatter<2, false><<<grid, SC_THREADS, smem, st>>>(a, p, p.unit_lo, p.unit_hi);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[6], st));
         ctx->tm.n_kernel_launches += 2;
@@ -1192,14 +1386,14 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         // database to the general (sort) path; otherwise only those buckets take the k2_big_* route.
         bool ok = !stream && ctx->big_buckets != 0;
         if (ok) {
-            YG_CHECK(dev_alloc(ctx, &ctx->d_big_list, (uint64_t)BIG_MAX));
+            YG_CHECK(dev_alloc(ctx, &ctx->d_big_list, (uint64_t)nbuckets));
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_STREAM], 0, sizeof(unsigned long long), st));
-            k2_big_list<<<grid_for(ctx, nbuckets, 256, 8), 256, 0, st>>>(final_base, 0, nbuckets, ctx->d_big_list, ctx->d_scalars);
+            k2_big_list<<<grid_for(ctx, nbuckets, 256, 8), 256, 0, st>>>(final_base, 0, nbuckets, ctx->d_big_list, nbuckets, ctx->d_scalars);
             YG_CUDA(ctx, cudaGetLastError());
             unsigned long long nb = 0;
             YG_CUDA(ctx, cudaMemcpyAsync(&nb, &ctx->d_scalars[SCM_STREAM], sizeof nb, cudaMemcpyDeviceToHost, st));
             YG_CUDA(ctx, cudaStreamSynchronize(st));
-            ok = nb >= 1 && nb <= BIG_MAX && low_bits + bitlen(nb - 1) <= 64;
+            ok = nb >= 1 && nb <= nbuckets && low_bits < 64;
             if (ok) {
                 n_big = (uint32_t)nb;
                 big_list.resize(n_big);
@@ -1210,7 +1404,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
                 big_cstart.assign((size_t)n_big + 1, 0);
                 for (uint32_t j = 0; j < n_big; j++) big_cstart[j + 1] = big_cstart[j] + (hb[big_list[j] + 1] - hb[big_list[j]]);
                 N_big = big_cstart[n_big];
-                ok = N_big < (1ull << 30) && T + N_big + 4 < (1ull << 32);
+                ok = T + N_big + 4 < (1ull << 32);
             }
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_STREAM], 0, sizeof(unsigned long long), st));
         }
@@ -1271,26 +1465,46 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
     }
     if (n_big) {
-        // oversized buckets: gather under (ordinal | remaining hash bits | genome id), one device-wide sort, neighbour grouping
-        YG_CHECK(dev_alloc(ctx, &ctx->d_big_a, N_big));
-        YG_CHECK(dev_alloc(ctx, &ctx->d_big_b, N_big));
+        // oversized buckets: gather under (ordinal | remaining hash bits | genome id), a device-wide sort, neighbour grouping.
+        // The ordinal must fit beside the low_bits that tell two words of a bucket apart, and a sort handles < 2^30 words:
+        // the list is worked off in chunks of consecutive buckets that satisfy both.
+        const uint32_t ord_cap = (64 - low_bits) >= 31 ? 0x7FFFFFFFu : (1u << (64 - low_bits));
+        uint64_t chunk_words_max = 0;
+        std::vector<std::pair<uint32_t, uint32_t>> chunks;
+        for (uint32_t c0 = 0; c0 < n_big;) {
+            uint32_t c1 = c0;
+            while (c1 < n_big && c1 - c0 < ord_cap && big_cstart[c1 + 1] - big_cstart[c0] < (1ull << 30)) c1++;
+            if (c1 == c0) c1 = c0 + 1;          // a single bucket of >= 2^30 words cannot occur (T < 2^32 is split over >= 2 buckets) -- keep going anyway
+            chunks.emplace_back(c0, c1);
+            chunk_words_max = std::max<uint64_t>(chunk_words_max, big_cstart[c1] - big_cstart[c0]);
+            c0 = c1;
+        }
+        YG_CHECK(dev_alloc(ctx, &ctx->d_big_a, chunk_words_max));
+        YG_CHECK(dev_alloc(ctx, &ctx->d_big_b, chunk_words_max));
         YG_CHECK(dev_alloc(ctx, &ctx->d_big_cstart, (uint64_t)n_big + 1));
         YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_list, big_list.data(), (size_t)n_big * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_cstart, big_cstart.data(), ((size_t)n_big + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        k2_big_gather<<<(unsigned)std::min<uint32_t>(n_big, (uint32_t)ctx->num_sms * 8), 256, 0, st>>>(final_ent, final_base, ctx->d_big_list, ctx->d_big_cstart,
-                                                                                                    n_big, low_bits, ctx->d_big_a);
-        YG_CUDA(ctx, cudaGetLastError());
-        const int end_bit = std::min(64, low_bits + bitlen((uint64_t)n_big - 1));
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)N_big, 0, std::max(end_bit, 1), st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)N_big, 0, std::max(end_bit, 1), st));
-        ctx->tm.n_library_launches += 2 + (std::max(end_bit, 1) + 7) / 8;
-        k2_big_groups<<<grid_for(ctx, N_big, 256, 8), 256, 0, st>>>(ctx->d_big_b, N_big, p.gb, T, p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_post,
-                                                                    ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items, ctx->d_scalars);
-        YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches += 3;
+        std::vector<uint64_t> rel((size_t)n_big + 1);
+        for (const auto& ch : chunks) {
+            const uint32_t c0 = ch.first, c1 = ch.second, nc = c1 - c0;
+            const uint64_t words = big_cstart[c1] - big_cstart[c0];
+            for (uint32_t j = 0; j <= nc; j++) rel[j] = big_cstart[c0 + j] - big_cstart[c0];
+            YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_big_cstart, rel.data(), ((size_t)nc + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            k2_big_gather<<<(unsigned)std::min<uint32_t>(nc, (uint32_t)ctx->num_sms * 8), 256, 0, st>>>(final_ent, final_base, ctx->d_big_list + c0, ctx->d_big_cstart,
+                                                                                                     nc, low_bits, ctx->d_big_a);
+            YG_CUDA(ctx, cudaGetLastError());
+            const int end_bit = std::min(64, low_bits + bitlen((uint64_t)nc - 1));
+            size_t tb = 0;
+            YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)words, 0, std::max(end_bit, 1), st));
+            YG_CHECK(ygpu_temp_reserve(ctx, tb));
+            tb = ctx->temp_bytes;
+            YG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->d_temp, tb, ctx->d_big_a, ctx->d_big_b, (int64_t)words, 0, std::max(end_bit, 1), st));
+            ctx->tm.n_library_launches += 2 + (std::max(end_bit, 1) + 7) / 8;
+            k2_big_groups<<<grid_for(ctx, words, 256, 8), 256, 0, st>>>(ctx->d_big_b, words, p.gb, T + big_cstart[c0], p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_post,
+                                                                        ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items, ctx->d_scalars);
+            YG_CUDA(ctx, cudaGetLastError());
+            ctx->tm.n_kernel_launches += 2;
+            YG_CUDA(ctx, cudaStreamSynchronize(st));      // `rel` is reused by the next chunk
+        }
         ctx->msd_big_buckets = n_big;
     } else {
         ctx->msd_big_buckets = 0;
@@ -1414,5 +1628,377 @@ extern "C" int ygpu_index_finish(ygpu_ctx* ctx, const uint32_t* d_gid, const uin
     ctx->row_work_valid = false;
     ctx->last_index_path = 1;
     ctx->indexed = true;
+    return 0;
+}
+
+// ============================================================================================================
+// Sharded train step: one rank per GPU, every rank resident with the sketches of ITS genome range only.
+//
+//   reference: compute_index_from_sketches() builds ONE hash map on one thread and the row chunks of
+//   compute_intersection_matrix() share it read-only (src/cpp/main.cpp:215-246, 338-349).  Here
+//     1. every rank histograms and partitions (level 1) only its own sketches; the packed words go STRAIGHT into the
+//        level-1 buffer of the rank that owns their hash range -- stores over NVLink from inside k2_scatter<1, PEER>,
+//        at positions every rank derives from the all-gathered histograms (k2s_prep): no all-to-all collective, no
+//        send buffer, no replicated read of the sketches;
+//     2. every rank runs level 2 and the grouping on its 1/N of the hash space; k2_group2<STREAM> stores each bucket's
+//        groups into ALL ranks' stream buffers while the next bucket is grouped (again plain stores, NVLink for peers);
+//     3. every rank turns the complete stream into the work lists of its own query rows (k2_items_regions) and counts /
+//        flags those rows (K3+K4); the per-rank pair lists are all-gathered (NCCL) and ordered.
+//   NCCL carries only the control data (histograms, stream lengths, statistics, pair lists) and separates the phases.
+//   The host does not wait for the device between the first kernel and the statistics read-back.
+// ============================================================================================================
+#include "comm.cuh"
+
+int ygpu_sort_pairs_device(ygpu_ctx* ctx, ygpu_pair* d_pairs, uint64_t n);      // yacht_gpu.cu
+
+// everything after the slice's hashes are in d_hashes: global offsets, sizes, slice-relative offsets, the global largest hash
+int ygpu_sharded_finish(ygpu_ctx* ctx, const uint64_t* offsets, uint32_t n, uint32_t g_begin, uint32_t g_end) {
+    if (!ctx->comm) return ygpu_fail(ctx, YGPU_ERR_STATE, "sharded load: ygpu_comm_init first");
+    cudaStream_t st = ctx->stream;
+    ctx->loaded = false; ctx->indexed = false; ctx->sorted = false; ctx->maxkey_valid = false; ctx->row_work_valid = false;
+    ctx->P = 0; ctx->n_items = 0;
+    const uint64_t Tg = offsets[n];
+    if (offsets[0] != 0) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets[0] must be 0");
+    uint32_t mx = 0;
+    for (uint32_t g = 0; g < n; g++) {
+        if (offsets[g + 1] < offsets[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+        mx = std::max<uint32_t>(mx, (uint32_t)std::min<uint64_t>(offsets[g + 1] - offsets[g], 0xFFFFFFFFull));
+    }
+    if (Tg >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)Tg);
+    const uint64_t T = offsets[g_end] - offsets[g_begin];
+    ctx->n = n; ctx->T = T; ctx->T_global = Tg; ctx->g_begin = g_begin; ctx->g_end = g_end; ctx->sharded = true;
+    ctx->max_sketch_global = mx;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sizes, n));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_begin_local, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets_local, (uint64_t)(g_end - g_begin) + 1));
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    k2s_sizes<<<grid_for(ctx, (uint64_t)n + 1, 256, 8), 256, 0, st>>>(ctx->d_offsets, n, g_begin, g_end, ctx->d_sizes, ctx->d_row_begin_local, ctx->d_offsets_local);
+    YG_CUDA(ctx, cudaGetLastError());
+    ctx->tm.n_kernel_launches++;
+    // the largest hash over ALL ranks decides the partition plan
+    uint64_t* d_max = (uint64_t*)&ctx->d_scalars[SC_MAXKEY];
+    YG_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(uint64_t), st));
+    if (T) {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, d_max, (int64_t)T, st));
+        ctx->tm.n_library_launches += 2;
+    }
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_max, d_max, 1, true));
+    YG_CUDA(ctx, cudaMemcpyAsync(&ctx->maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->maxkey_valid = true;
+    ctx->loaded = true;
+    return 0;
+}
+
+static int sharded_load(ygpu_ctx* ctx, const uint64_t* hashes_slice, const uint64_t* offsets, uint32_t n, uint32_t g_begin, uint32_t g_end,
+                        bool from_device) {
+    if (!ctx || !offsets) return YGPU_ERR_ARG;
+    if (!ctx->comm) return ygpu_fail(ctx, YGPU_ERR_STATE, "load_sketches_sharded: ygpu_comm_init first");
+    if (g_begin > g_end || g_end > n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad genome range [%u,%u) of %u", g_begin, g_end, n);
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t T = offsets[g_end] - offsets[g_begin];
+    if (T && !hashes_slice) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_sharded: NULL hashes");
+    if (T >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes >= 2^32 not supported");
+    ctx->loaded = false;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_hashes, T + 2));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (T) YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_hashes, hashes_slice, T * sizeof(uint64_t), from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    YG_CHECK(ygpu_sharded_finish(ctx, offsets, n, g_begin, g_end));
+    ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
+    return 0;
+}
+
+extern "C" int ygpu_load_sketches_sharded(ygpu_ctx* ctx, const uint64_t* hashes_slice, const uint64_t* offsets, uint32_t n_genomes,
+                                          uint32_t g_begin, uint32_t g_end) {
+    return sharded_load(ctx, hashes_slice, offsets, n_genomes, g_begin, g_end, false);
+}
+extern "C" int ygpu_load_sketches_sharded_device(ygpu_ctx* ctx, const uint64_t* d_hashes_slice, const uint64_t* offsets, uint32_t n_genomes,
+                                                 uint32_t g_begin, uint32_t g_end) {
+    return sharded_load(ctx, d_hashes_slice, offsets, n_genomes, g_begin, g_end, true);
+}
+
+extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats, uint64_t* n_pairs_total) {
+    if (!ctx || !n_pairs_total) return YGPU_ERR_ARG;
+    *n_pairs_total = 0;
+    if (!ctx->comm || !ctx->sharded || !ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: ygpu_comm_init and ygpu_load_sketches_sharded first");
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ygpu_comm* C = ctx->comm;
+    const int N = C->nranks, rank = C->rank;
+    const uint64_t T = ctx->T, Tg = ctx->T_global;
+    const uint32_t n = ctx->n;
+    ctx->indexed = false; ctx->row_work_valid = false; ctx->n_pairs = 0;
+    ygpu_index_stats S{};
+    S.n_hashes = Tg;
+    S.max_sketch = ctx->max_sketch_global;
+    S.index_path = 1;
+    if (Tg < 2 || n < 2) {
+        ctx->stats = S; ctx->indexed = true; ctx->n_items = 0;
+        if (stats) *stats = S;
+        return 0;
+    }
+    // ---- plan (same rules as msd_build, bucket sizes by the GLOBAL hash count) --------------------------------------
+    const uint64_t maxkey = ctx->maxkey;
+    MsdPlan p{};
+    p.T = T;
+    p.hb = std::max(1, bitlen(maxkey));
+    p.gb = bitlen((uint64_t)n - 1);
+    auto used_buckets = [&](int D) -> uint64_t { return D == 0 ? 1ull : (maxkey >> (p.hb - D)) + 1ull; };
+    int D = 0;
+    while (D < p.hb && D < 22 && Tg / used_buckets(D) > A_TARGET) D++;
+    int d1 = D <= 8 ? D : (D + 1) / 2;
+    const int need = p.hb + p.gb - 64;
+    if (need > d1) d1 = need;
+    int d2 = std::max(0, D - d1);
+    const char* why = nullptr;
+    if (d1 > 11 || d1 > p.hb || d2 > 11) why = "hash and genome-id width do not pack into 64-bit words";
+    p.d1 = d1; p.d2 = d2; p.kb1 = p.hb - d1;
+    p.nb1 = d1 ? (uint32_t)(maxkey >> (p.hb - d1)) + 1 : 1u;
+    if (!why && p.nb1 > NB_MAX) why = "too many level-1 buckets";
+    p.nfb = p.nb1 << d2;
+    p.dlo = 0; p.dhi = p.nb1; p.unit_lo = 0; p.unit_hi = 0xFFFFFFFFu;
+    const int key_bits = p.kb1 - d2;
+    const int sbits = std::max(0, std::min(GK_SUBBITS, key_bits));
+    const int rest_bits = key_bits - sbits;
+    if (!why && rest_bits > 32) why = "remaining hash bits exceed 32 (database too small for its hash width)";
+    if (why) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: this database does not qualify for the sharded partition path: %s", why);
+
+    // ---- buffers; the exchange targets are (re)shared with the peers when they move ------------------------------------
+    const uint64_t cap = Tg / N + 2 * (Tg / std::max<uint32_t>(p.nb1, 1)) + 3 * SC_TILE;        // words a rank can own: its share + digit granularity
+    if ((uint64_t)N * cap + 8 >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "stream of %llu entries >= 2^32 not supported", (unsigned long long)N * cap);
+    ctx->sh_cap = cap;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_ent1, cap + 2));
+    if (d2) YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, cap + 2));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_post, (uint64_t)N * cap + 8));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, (uint64_t)N * cap + 8));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, std::max<uint64_t>(T, 1)));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_hist_all, (uint64_t)(N + 1) * NB_MAX));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_owner, (uint64_t)NB_MAX));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)64));
+    const uint64_t aux_words = 3ull * (NB_MAX + 2) + 3ull * ((uint64_t)p.nfb + 2);
+    YG_CHECK(dev_alloc(ctx, &ctx->d_msd_aux, aux_words));
+    const uint32_t units1 = (uint32_t)((T + SC_TILE - 1) / SC_TILE);
+    YG_CHECK(dev_alloc(ctx, &ctx->d_tile_g0, (uint64_t)units1 + 2));
+    const uint64_t max_units = cap / SC_TILE + p.nb1 + 2;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_units, 2 * max_units));
+    {
+        // collective: every rank evaluates the same conditions in the same order (allocations move together or a rank re-shares alone
+        // harmlessly -- the exchange is an all-gather every rank takes part in, so the decision must be global)
+        unsigned long long moved = (ctx->sh_shared_ent1 != ctx->d_ent1) || (ctx->sh_shared_gid != ctx->d_post) || (ctx->sh_shared_rem != ctx->d_st_rem);
+        unsigned long long* d_flag = &ctx->d_sh_info[40];
+        YG_CUDA(ctx, cudaMemcpyAsync(d_flag, &moved, sizeof moved, cudaMemcpyHostToDevice, st));
+        YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_flag, d_flag, 1, true));
+        YG_CUDA(ctx, cudaMemcpyAsync(&moved, d_flag, sizeof moved, cudaMemcpyDeviceToHost, st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (moved) {
+            YG_CHECK(ygpu_comm_share(ctx, ctx->d_ent1, ctx->sh_peer_ent1));
+            YG_CHECK(ygpu_comm_share(ctx, ctx->d_post, ctx->sh_peer_gid));
+            YG_CHECK(ygpu_comm_share(ctx, ctx->d_st_rem, ctx->sh_peer_rem));
+            ctx->sh_shared_ent1 = ctx->d_ent1; ctx->sh_shared_gid = ctx->d_post; ctx->sh_shared_rem = ctx->d_st_rem;
+        }
+    }
+    uint32_t* hist1 = ctx->d_msd_aux;
+    uint32_t* base1 = hist1 + (NB_MAX + 2);
+    uint32_t* tile_start = base1 + (NB_MAX + 2);
+    uint32_t* hist2 = tile_start + (NB_MAX + 2);
+    uint32_t* base2 = hist2 + ((uint64_t)p.nfb + 2);
+    uint32_t* cursor = base2 + ((uint64_t)p.nfb + 2);
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+
+    // ---- 1. level 1 on the resident slice, words stored into their owners' buffers ---------------------------------------
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[0], st));
+    if (T) {
+        k2_hist1<<<ctx->num_sms * 8, 256, p.nb1 * sizeof(uint32_t), st>>>(ctx->d_hashes, p, hist1);
+        YG_CUDA(ctx, cudaGetLastError());
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[1], st));
+    YG_CHECK(ygpu_comm_allgather(ctx, hist1, ctx->d_sh_hist_all, (size_t)NB_MAX * sizeof(uint32_t)));
+    k2s_prep<<<1, 1024, 0, st>>>(ctx->d_sh_hist_all, p.nb1, N, rank, d2, ctx->d_sh_owner, cursor, base1, tile_start, ctx->d_sh_info, ctx->d_scalars);
+    YG_CUDA(ctx, cudaGetLastError());
+    ScatterArgs a{};
+    a.hashes = ctx->d_hashes; a.offsets = ctx->d_offsets_local; a.n = ctx->g_end - ctx->g_begin; a.gid_base = ctx->g_begin;
+    a.out_ent = ctx->d_ent1; a.cursor = cursor; a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2; a.owner = ctx->d_sh_owner;
+    for (int q = 0; q < N; q++) a.peer_ent[q] = (uint64_t*)ctx->sh_peer_ent1[q];
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[2], st));
+    if (T) {
+        k2_tile_g0<<<grid_for(ctx, (uint64_t)units1 + 1, 256, 8), 256, 0, st>>>(ctx->d_offsets_local, a.n, T, units1, ctx->d_tile_g0);
+        YG_CUDA(ctx, cudaGetLastError());
+        a.tile_g0 = ctx->d_tile_g0;
+        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)p.nb1 * 20 + (size_t)SC_TILE * 2;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1, true>, SC_THREADS, smem));
+        const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
+        k2_scatter<1, true><<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
+        YG_CUDA(ctx, cudaGetLastError());
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[3], st));
+    // every rank's words have landed once every rank has passed this point (the collective also orders the peer stores)
+    unsigned long long* d_sync = &ctx->d_sh_info[41];
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_sync, d_sync, 1, true));
+    ctx->tm.n_kernel_launches += 4;
+
+    // ---- 2. level 2 + grouping on this rank's share of the hash space; groups stored into every rank's stream ---------
+    const uint64_t* final_ent = ctx->d_ent1;
+    const uint32_t* final_base = base1;
+    if (d2) {
+        a.in_ent = ctx->d_ent1; a.out_ent = ctx->d_ent2;
+        k2_units<<<grid_for(ctx, max_units, 256, 8), 256, 0, st>>>(tile_start, base1, p.nb1, (uint2*)ctx->d_units);
+        YG_CUDA(ctx, cudaGetLastError());
+        a.units = (const uint2*)ctx->d_units;
+        k2_hist2<<<ctx->num_sms * 8, 256, (size_t)(1u << d2) * sizeof(uint32_t), st>>>(a, p, 0xFFFFFFFFu);
+        YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[4], st));
+        size_t tb = 0, tb2 = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist2, base2, (int64_t)p.nfb + 1, st));
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb2, hist2, (uint32_t*)&ctx->d_scalars[SCM_MAXB + 1], (int64_t)p.nfb, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, std::max(tb, tb2)));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, hist2, base2, (int64_t)p.nfb + 1, st));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, hist2, (uint32_t*)&ctx->d_scalars[SCM_MAXB + 1], (int64_t)p.nfb, st));
+        ctx->tm.n_library_launches += 4;
+        YG_CUDA(ctx, cudaMemcpyAsync(cursor, base2, ((uint64_t)p.nfb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        a.cursor = cursor;
+        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)(1u << d2) * 12 + (size_t)SC_TILE * 2;
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<2, false>, SC_THREADS, smem));
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[5], st));
+        k2_scatter<2, false><<<ctx->num_sms * std::max(occ, 1), SC_THREADS, smem, st>>>(a, p, 0u, 0xFFFFFFFFu);
+        YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[6], st));
+        ctx->tm.n_kernel_launches += 3;
+        final_ent = ctx->d_ent2;
+        final_base = base2;
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    {
+        GroupArgs g{};
+        g.ent = final_ent; g.base = final_base; g.gb = p.gb;
+        g.nb = d2 ? p.nfb : p.nb1;
+        g.b_lo = 0; g.b_hi = g.nb; g.m_lo = 0;
+        g.range = d2 ? &ctx->d_sh_info[SHI_BLO] : &ctx->d_sh_info[SHI_DLO];
+        g.sub_shift = p.gb + rest_bits;
+        g.sub_mask = (1u << sbits) - 1u;
+        g.rest_mask = rest_bits >= 64 ? ~0ull : ((1ull << rest_bits) - 1ull);
+        if (g.sub_shift > 63) { g.sub_shift = 0; g.sub_mask = 0; }
+        g.scal = ctx->d_scalars;
+        g.n_peers = N;
+        g.region_base = (uint64_t)rank * cap;
+        for (int q = 0; q < N; q++) { g.peer_gid[q] = (uint32_t*)ctx->sh_peer_gid[q]; g.peer_rem[q] = (unsigned short*)ctx->sh_peer_rem[q]; }
+        const size_t smem2 = sizeof(G2Smem);
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        int occ2 = 1;
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2_group2<true>, G2_THREADS, smem2));
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[7], st));
+        k2_group2<true><<<ctx->num_sms * std::max(occ2, 1), G2_THREADS, smem2, st>>>(g);
+        YG_CUDA(ctx, cudaGetLastError());
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
+        ctx->tm.n_kernel_launches += 1;
+    }
+    // stream lengths of all ranks (the all-gather is also the barrier behind the stream stores)
+    unsigned long long* d_lens = &ctx->d_sh_info[SHI_LENS];
+    YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_scalars[SCM_STREAM], d_lens, sizeof(unsigned long long)));
+
+    // ---- 3. work lists of this rank's rows from the complete stream; statistics over all ranks ---------------------------
+    k2_items_regions<<<grid_for(ctx, std::max<uint64_t>(Tg / 4, 1), 256, 16), 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end,
+                                                                                      p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_row_begin_local,
+                                                                                      ctx->d_row_cnt, ctx->d_row_items);
+    YG_CUDA(ctx, cudaGetLastError());
+    ctx->tm.n_kernel_launches += 1;
+    // scalars 0..3 (heads, singles, dups, W) summed over the ranks; slot SCM_MAXB(+1) = largest bucket (max)
+    unsigned long long* d_tot = &ctx->d_sh_info[24];
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, ctx->d_scalars, d_tot, 4, false));
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, &ctx->d_scalars[SCM_MAXB], d_tot + 4, 2, true));
+    unsigned long long tot[6], info[8];
+    YG_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_sh_info, sizeof info, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_sort += elapsed(ctx, 0, 1);
+    ctx->tm.ms_index += elapsed(ctx, 1, 2);
+    {
+        auto el = [&](int x, int y) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->evp[x], ctx->evp[y]); return (double)ms; };
+        ctx->tm.ms_hist1 += el(0, 1);
+        ctx->tm.ms_scatter1 += el(2, 3);
+        if (d2) { ctx->tm.ms_hist2 += el(3, 4); ctx->tm.ms_scatter2 += el(5, 6); }
+        ctx->tm.ms_group += el(7, 8);
+    }
+    if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d owns %llu words, exchange buffer holds %llu", rank, info[SHI_TMINE], (unsigned long long)cap);
+    const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
+    if (largest > G2_MAXM)
+        return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a final bucket holds %llu words (> %u): skewed databases take the replicated build (ygpu_build_index)",
+                         (unsigned long long)largest, G2_MAXM);
+    S.n_distinct = tot[SC_HEADS];
+    S.n_singleton = tot[SC_SINGLE];
+    S.n_index = S.n_distinct - S.n_singleton;
+    S.n_postings = Tg - tot[SC_SINGLE];
+    S.n_increments = tot[SC_W];
+    S.n_row_items = S.n_postings - S.n_index;
+    S.has_duplicates = tot[SC_DUPS] ? 1u : 0u;
+    ctx->stats = S;
+    ctx->P = (uint64_t)N * cap;
+    ctx->n_items = S.n_row_items;
+    ctx->d_row_begin = ctx->d_row_begin_local;
+    ctx->last_index_path = 1;
+    ctx->indexed = true;
+    if (stats) *stats = S;
+
+    // ---- 4. K3 + K4 on this rank's rows, then the pair lists of all ranks on every rank, ordered by (i, j) ---------------
+    uint64_t n_r = 0;
+    YG_CHECK(ygpu_pairwise_flag_device(ctx, threshold, ctx->g_begin, ctx->g_end, &n_r));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    unsigned long long mine = n_r, counts[YG_MAX_RANKS];
+    unsigned long long* d_cnt = &ctx->d_sh_info[44];
+    YG_CUDA(ctx, cudaMemcpyAsync(d_cnt, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allgather(ctx, d_cnt, d_cnt + 1, sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt + 1, (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    uint64_t total = 0, mxc = 0;
+    for (int q = 0; q < N; q++) { total += counts[q]; mxc = std::max<uint64_t>(mxc, counts[q]); }
+    if (total) {
+        // padded all-gather, then the ranks' lists are squeezed together and ordered
+        const uint64_t need_all = (uint64_t)N * mxc + total + 16;
+        if (need_all > ctx->pairs_local_cap) {
+            if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);
+            ctx->d_pairs_local = nullptr; ctx->pairs_local_cap = 0;
+            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs_local, (need_all + need_all / 8 + 1024) * sizeof(ygpu_pair)));
+            ctx->pairs_local_cap = need_all + need_all / 8 + 1024;
+        }
+        ygpu_pair* pad = ctx->d_pairs_local;                 // [N][mxc] gathered, then [total] compact behind it
+        ygpu_pair* out = pad + (uint64_t)N * mxc;
+        if (n_r) YG_CUDA(ctx, cudaMemcpyAsync(pad + (uint64_t)rank * mxc, ctx->d_pairs, n_r * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+        YG_CHECK(ygpu_comm_allgather(ctx, pad + (uint64_t)rank * mxc, pad, (size_t)mxc * sizeof(ygpu_pair)));
+        uint64_t pos = 0;
+        for (int q = 0; q < N; q++) {
+            if (counts[q]) YG_CUDA(ctx, cudaMemcpyAsync(out + pos, pad + (uint64_t)q * mxc, counts[q] * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+            pos += counts[q];
+        }
+        if (N > 1) YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
+        if (total > ctx->pairs_cap) {
+            if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+            ctx->d_pairs = nullptr; ctx->pairs_cap = 0;
+            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs, (total + 1024) * sizeof(ygpu_pair)));
+            ctx->pairs_cap = total + 1024;
+        }
+        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, out, total * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_pairsort += elapsed(ctx, 2, 3);
+    ctx->n_pairs = total;
+    *n_pairs_total = total;
     return 0;
 }

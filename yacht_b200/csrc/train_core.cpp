@@ -13,9 +13,10 @@
 // behind the C ABI of include/yacht_gpu.h; there is no CPU implementation of them here, and the
 // program exits non-zero if no B200 is available.
 //
-// Multi-GPU: every visible device (or the first YACHT_NUM_GPUS of them) gets the full sketch set
-// and builds the index (replicated), then flags the pairs of its own work-balanced row range;
-// the per-device pair lists are merged on the host.
+// Multi-GPU: every visible device (or the first YACHT_NUM_GPUS of them) is one rank (a host thread) of the library's
+// sharded train step: it holds the sketches of a contiguous range of files only, the index build is split by hash
+// range and exchanged by the kernels over NVLink, the pairwise count by query rows, the pair lists are gathered over
+// NCCL (include/yacht_gpu.h: ygpu_comm_init / ygpu_upload_finish_sharded / ygpu_train_step_sharded).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -194,6 +195,12 @@ int main(int argc, char** argv) {
     bool q_done = false;
     std::atomic<int> upload_rc{0};
     std::vector<std::thread> uploaders;
+    // Multi-GPU: rank d (one thread per GPU) holds the sketches of a contiguous range of file BLOCKS -- the split is by file
+    // count, fixed before any file is parsed, so parsed blocks can travel to their GPU while later files are still read.
+    const uint32_t nblocks_total = (n + yingest::kFilesPerBlock - 1) / yingest::kFilesPerBlock;
+    std::vector<uint32_t> blk_lo;        // first block of rank d (ndev + 1 entries)
+    auto owner_of_block = [&](uint32_t b) { return (int)(std::upper_bound(blk_lo.begin(), blk_lo.end(), b) - blk_lo.begin()) - 1; };
+    uint8_t comm_id[YGPU_COMM_ID_BYTES];
     if (stream_upload)
         in.on_block = [&](uint32_t b) {
             { std::lock_guard<std::mutex> lk(q_mu); q_blocks.push_back(b); }
@@ -203,15 +210,26 @@ int main(int argc, char** argv) {
         int nd = ygpu_device_count();
         if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) nd = std::min(nd, v); }
         if (nd < 1) return;
-        nd = std::max(1, std::min<int>(nd, (int)std::max<uint32_t>(n, 1)));
+        nd = std::max(1, std::min<int>(nd, (int)std::max<uint32_t>(nblocks_total, 1)));
         ctxs.assign(nd, nullptr);
         res.resize(nd);
+        blk_lo.resize(nd + 1);
+        for (int d = 0; d <= nd; d++) blk_lo[d] = (uint32_t)((uint64_t)nblocks_total * d / nd);
+        if (nd > 1 && ygpu_comm_get_unique_id(comm_id)) {
+            res[0].rc = -1; res[0].err = ygpu_last_error(nullptr);
+            ndev = nd;
+            return;
+        }
         std::vector<std::thread> th;
         for (int d = 0; d < nd; d++)
             th.emplace_back([&, d]() {
                 res[d].rc = ygpu_ctx_create(&ctxs[d], d);
-                if (res[d].rc) res[d].err = ygpu_last_error(nullptr);
-                else if (stream_upload) {
+                if (res[d].rc) { res[d].err = ygpu_last_error(nullptr); return; }
+                if (nd > 1) {
+                    res[d].rc = ygpu_comm_init(ctxs[d], d, nd, comm_id);
+                    if (res[d].rc) { res[d].err = ygpu_last_error(ctxs[d]); return; }
+                }
+                if (stream_upload) {
                     res[d].rc = ygpu_upload_begin(ctxs[d]);
                     if (res[d].rc) res[d].err = ygpu_last_error(ctxs[d]);
                 }
@@ -222,7 +240,7 @@ int main(int argc, char** argv) {
         for (int d = 0; d < nd; d++) if (res[d].rc) return;
         const int nu = std::max(2, std::min(4, args.number_of_threads / 4));
         for (int k = 0; k < nu; k++)
-            uploaders.emplace_back([&, k, nu, nd]() {
+            uploaders.emplace_back([&, k, nu]() {
                 yingest::pin_worker(k * std::max(1, args.number_of_threads / nu));   // unpinned helper threads starve here
                 for (;;) {
                     uint32_t b;
@@ -233,10 +251,8 @@ int main(int argc, char** argv) {
                         b = q_blocks.front();
                         q_blocks.pop_front();
                     }
-                    for (int d = 0; d < nd; d++) {
-                        const int rc = ygpu_upload_block(ctxs[d], b, in.blocks[b].data(), in.blocks[b].size());
-                        if (rc) upload_rc = rc;
-                    }
+                    const int rc = ygpu_upload_block(ctxs[owner_of_block(b)], b, in.blocks[b].data(), in.blocks[b].size());
+                    if (rc) upload_rc = rc;
                 }
             });
     });
@@ -267,76 +283,96 @@ int main(int argc, char** argv) {
     // ---- index + pairwise on the GPU(s) ----------------------------------------------------------
     auto t_index = std::chrono::high_resolution_clock::now();
     std::cout << "Building index from sketches..." << std::endl;
-    std::vector<uint64_t> block_dst(in.blocks.size());
-    for (size_t b = 0; b < in.blocks.size(); b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)];
-    std::vector<const uint64_t*> block_ptrs(in.blocks.size());
-    std::vector<uint64_t> block_lens(in.blocks.size());
-    for (size_t b = 0; b < in.blocks.size(); b++) { block_ptrs[b] = in.blocks[b].data(); block_lens[b] = in.blocks[b].size(); }
+    for (int d = 0; d < ndev; d++)
+        if (res[d].rc) {
+            std::cerr << "run_yacht_train_core: GPU " << d << ": " << res[d].err << std::endl;
+            return 5;
+        }
+    const size_t nb = in.blocks.size();
+    std::vector<uint32_t> g_lo(ndev + 1);            // genome range of rank d
+    for (int d = 0; d <= ndev; d++) g_lo[d] = (uint32_t)std::min<uint64_t>((uint64_t)blk_lo[d] * yingest::kFilesPerBlock, n);
+    std::vector<const uint64_t*> block_ptrs(nb);
+    std::vector<uint64_t> block_lens(nb);
+    for (size_t b = 0; b < nb; b++) { block_ptrs[b] = in.blocks[b].data(); block_lens[b] = in.blocks[b].size(); }
+    // One thread per GPU from here on.  With several GPUs each rank finishes its sharded load (collective), then runs the
+    // library's sharded train step; every rank ends up with the complete pair list and rank 0's is written out.
+    std::vector<ygpu_pair> pairs;
+    ygpu_index_stats S{};
+    bool sharded_refused = false;
+    auto t_mat = t_index;
     {
         std::vector<std::thread> th;
         for (int d = 0; d < ndev; d++)
             th.emplace_back([&, d]() {
                 DeviceResult& r = res[d];
-                if (r.rc) return;
-                if (stream_upload)
-                    r.rc = upload_rc ? (int)upload_rc : ygpu_upload_finish(ctxs[d], block_dst.data(), (uint32_t)block_dst.size(), in.offsets.data(), n);
-                else
-                    r.rc = ygpu_load_sketch_blocks(ctxs[d], block_ptrs.data(), block_lens.data(), (uint32_t)block_ptrs.size(),
-                                                   in.offsets.data(), n);
-                if (!r.rc) r.rc = ygpu_build_index(ctxs[d], &r.stats);
-                if (r.rc) r.err = ygpu_last_error(ctxs[d]);
+                ygpu_ctx* c = ctxs[d];
+                std::vector<uint64_t> block_dst(nb, 0);
+                const uint64_t slice0 = in.offsets[g_lo[d]];
+                for (size_t b = blk_lo[d]; b < blk_lo[d + 1]; b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)] - slice0;
+                if (ndev == 1) {
+                    if (stream_upload)
+                        r.rc = upload_rc ? (int)upload_rc : ygpu_upload_finish(c, block_dst.data(), (uint32_t)nb, in.offsets.data(), n);
+                    else
+                        r.rc = ygpu_load_sketch_blocks(c, block_ptrs.data(), block_lens.data(), (uint32_t)nb, in.offsets.data(), n);
+                    if (!r.rc) r.rc = ygpu_build_index(c, &r.stats);
+                    if (!r.rc) r.rc = ygpu_pairwise_flag(c, args.containment_threshold, 0, n, &r.pairs, &r.n_pairs);
+                } else {
+                    if (stream_upload) {
+                        r.rc = upload_rc ? (int)upload_rc
+                                         : ygpu_upload_finish_sharded(c, block_dst.data(), (uint32_t)nb, in.offsets.data(), n, g_lo[d], g_lo[d + 1]);
+                    } else {
+                        // (debug path) assemble this rank's slice on the host
+                        std::vector<uint64_t> flat;
+                        flat.reserve(in.offsets[g_lo[d + 1]] - slice0);
+                        for (size_t b = blk_lo[d]; b < blk_lo[d + 1]; b++) flat.insert(flat.end(), in.blocks[b].begin(), in.blocks[b].end());
+                        r.rc = ygpu_load_sketches_sharded(c, flat.data(), in.offsets.data(), n, g_lo[d], g_lo[d + 1]);
+                    }
+                    if (!r.rc) {
+                        r.rc = ygpu_train_step_sharded(c, args.containment_threshold, &r.stats, &r.n_pairs);
+                        if (!r.rc && d == 0 && r.n_pairs) {
+                            r.pairs = (ygpu_pair*)malloc(r.n_pairs * sizeof(ygpu_pair));
+                            r.rc = r.pairs ? ygpu_pairs_copy(c, r.pairs, 0) : -5;
+                        }
+                    }
+                }
+                if (r.rc) r.err = ygpu_last_error(c);
+                ygpu_get_timings(c, &r.tm);
             });
         for (auto& t : th) t.join();
+    }
+    if (ndev > 1) {
+        // the sharded step refuses databases it does not cover (extreme skew, tiny inputs): the same answer on every rank.
+        // One GPU then takes the whole database through the general entry points.
+        bool refused = false, failed = false;
+        for (int d = 0; d < ndev; d++) { if (res[d].rc == -4) refused = true; else if (res[d].rc) failed = true; }
+        if (refused && !failed) {
+            sharded_refused = true;
+            std::cout << "[multi-gpu] sharded step not applicable (" << res[0].err << "); running on GPU 0 alone" << std::endl;
+            DeviceResult& r = res[0];
+            r.rc = ygpu_load_sketch_blocks(ctxs[0], block_ptrs.data(), block_lens.data(), (uint32_t)nb, in.offsets.data(), n);
+            if (!r.rc) r.rc = ygpu_build_index(ctxs[0], &r.stats);
+            if (!r.rc) r.rc = ygpu_pairwise_flag(ctxs[0], args.containment_threshold, 0, n, &r.pairs, &r.n_pairs);
+            if (r.rc) r.err = ygpu_last_error(ctxs[0]);
+            ygpu_get_timings(ctxs[0], &r.tm);
+            for (int d = 1; d < ndev; d++) { res[d].rc = 0; res[d].n_pairs = 0; }
+        }
     }
     for (int d = 0; d < ndev; d++)
         if (res[d].rc) {
             std::cerr << "run_yacht_train_core: GPU " << d << ": " << res[d].err << std::endl;
             return 5;
         }
-    const ygpu_index_stats& S = res[0].stats;
+    S = res[0].stats;
     std::cout << "Total number of distinct hashes: " << S.n_distinct << std::endl;                                       // main.cpp:242
     std::cout << "Total number of distinct hashes that appear in only one sketch: " << S.n_singleton << std::endl;      // :243
     std::cout << "Size of the index: " << S.n_index << std::endl;                                                       // :244
     std::cout << "Time taken to build index: " << ms_since(t_index) << " milliseconds" << std::endl;
 
-    auto t_mat = std::chrono::high_resolution_clock::now();
+    t_mat = std::chrono::high_resolution_clock::now();
     std::cout << "Computing intersection matrix..." << std::endl;
-    std::vector<uint32_t> bounds(ndev + 1, 0);
-    if (ygpu_row_partition(ctxs[0], (uint32_t)ndev, bounds.data())) {
-        std::cerr << "run_yacht_train_core: " << ygpu_last_error(ctxs[0]) << std::endl;
-        return 5;
-    }
-    {
-        std::vector<std::thread> th;
-        for (int d = 0; d < ndev; d++)
-            th.emplace_back([&, d]() {
-                DeviceResult& r = res[d];
-                r.rc = ygpu_pairwise_flag(ctxs[d], args.containment_threshold, bounds[d], bounds[d + 1], &r.pairs, &r.n_pairs);
-                if (r.rc) r.err = ygpu_last_error(ctxs[d]);
-                ygpu_get_timings(ctxs[d], &r.tm);
-            });
-        for (auto& t : th) t.join();
-    }
-    for (int d = 0; d < ndev; d++)
-        if (res[d].rc) {
-            std::cerr << "run_yacht_train_core: GPU " << d << ": " << res[d].err << std::endl;
-            return 5;
-        }
-    // merge the per-device lists (each is sorted by (i, j); ranges interleave because the owner of
-    // row a also reports (b, a))
-    uint64_t F = 0;
-    for (auto& r : res) F += r.n_pairs;
-    std::vector<ygpu_pair> pairs;
-    pairs.reserve(F);
-    for (auto& r : res) {
-        pairs.insert(pairs.end(), r.pairs, r.pairs + r.n_pairs);
-        ygpu_free(r.pairs);
-        r.pairs = nullptr;
-    }
-    if (ndev > 1)
-        std::sort(pairs.begin(), pairs.end(), [](const ygpu_pair& a, const ygpu_pair& b) {
-            return a.i != b.i ? a.i < b.i : a.j < b.j;
-        });
+    pairs.assign(res[0].pairs, res[0].pairs + res[0].n_pairs);       // sorted by (i, j): the complete list
+    if (res[0].pairs) { ygpu_free(res[0].pairs); res[0].pairs = nullptr; }
+    (void)sharded_refused;
 
     // ---- pair files: same file partition as main.cpp:318,338-349, same line format as :305 --------
     {
@@ -363,7 +399,7 @@ int main(int argc, char** argv) {
                     const double jaccard = 1.0 * m / (ni + nj - m);
                     const double c_ij = 1.0 * m / ni;
                     const double c_ji = 1.0 * m / nj;
-                    outfile << pr.i << "," << pr.j << "," << jaccard << "," << c_ij << "," << c_ji << std::endl;
+                    outfile << pr.i << "," << pr.j << "," << jaccard << "," << c_ij << "," << c_ji << "\n";
                 }
                 outfile.close();
             }
@@ -396,7 +432,7 @@ int main(int argc, char** argv) {
     // extra (not in the reference): device-side timings, for apples-to-apples phase accounting
     for (int d = 0; d < ndev; d++) {
         const ygpu_timings& t = res[d].tm;
-        std::cout << "[gpu " << d << "] rows [" << bounds[d] << "," << bounds[d + 1] << ") h2d " << t.ms_h2d << " ms, sort "
+        std::cout << "[gpu " << d << "] rows [" << g_lo[d] << "," << g_lo[d + 1] << ") h2d " << t.ms_h2d << " ms, sort "
                   << t.ms_sort << " ms, index " << t.ms_index << " ms, count+flag " << t.ms_count << " ms, d2h " << t.ms_d2h
                   << " ms, pairs " << res[d].n_pairs << std::endl;
     }

@@ -111,6 +111,7 @@ static void release_index(ygpu_ctx* ctx) {   // invalidate only: the buffers are
 static void release_sketches(ygpu_ctx* ctx) {
     release_index(ctx);
     ctx->loaded = false;
+    ctx->sharded = false;
     ctx->maxkey_valid = false;
     ctx->n = 0; ctx->T = 0;
 }
@@ -123,6 +124,8 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_big_list); dev_free(ctx, &ctx->d_big_cstart); dev_free(ctx, &ctx->d_big_a); dev_free(ctx, &ctx->d_big_b);
     dev_free(ctx, &ctx->d_ent1); dev_free(ctx, &ctx->d_ent2); dev_free(ctx, &ctx->d_msd_aux);
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
+    dev_free(ctx, &ctx->d_offsets_local); dev_free(ctx, &ctx->d_row_begin_local); dev_free(ctx, &ctx->d_sh_hist_all);
+    dev_free(ctx, &ctx->d_sh_owner); dev_free(ctx, &ctx->d_sh_info);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
 }
 
@@ -134,6 +137,8 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     free_all(ctx);
     ygpu_run_release(ctx);
     ygpu_upload_release(ctx);
+    ygpu_comm_destroy(ctx);
+    if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);
     if (ctx->d_pairs) cudaFree(ctx->d_pairs);
     if (ctx->d_temp) cudaFree(ctx->d_temp);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
@@ -379,20 +384,17 @@ extern "C" int ygpu_upload_block(ygpu_ctx* ctx, uint32_t block_id, const uint64_
     return 0;
 }
 
-// block_dst[id] = position of block `id` in the flat hash array; offsets / n as for ygpu_load_sketches.
-extern "C" int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n) {
-    if (!ctx || !offsets || (nblocks && !block_dst)) return YGPU_ERR_ARG;
+// Place the uploaded blocks: block_dst[id] = position of block `id` in the resident hash array of T hashes (the whole
+// flat array, or -- sharded residency -- this rank's slice).  Leaves d_hashes filled; the caller finishes the load.
+static int upload_place(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, uint64_t T) {
     UploadState* u = (UploadState*)ctx->upload;
     if (!u) return ygpu_fail(ctx, YGPU_ERR_STATE, "upload_finish: ygpu_upload_begin first");
     YG_CUDA(ctx, cudaSetDevice(ctx->device));
     for (int b = 0; b < UploadState::NB; b++) YG_CUDA(ctx, cudaStreamSynchronize(u->bst[b]));
-    const uint64_t T = offsets[n];
     int rc = 0;
     if (u->failed) rc = ygpu_fail(ctx, YGPU_ERR_CUDA, "upload_finish: an upload failed");
-    else if (u->total != T || offsets[0] != 0) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "upload_finish: %llu hashes uploaded, offsets say %llu", (unsigned long long)u->total, (unsigned long long)T);
+    else if (u->total != T) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "upload_finish: %llu hashes uploaded, offsets say %llu", (unsigned long long)u->total, (unsigned long long)T);
     else if (T >= (1ull << 32)) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)T);
-    for (uint32_t g = 0; g < n && !rc; g++)
-        if (offsets[g + 1] < offsets[g]) rc = ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
     std::vector<PlaceDesc> desc;
     for (const UploadBlk& k : u->blocks) {
         if (rc) break;
@@ -400,10 +402,7 @@ extern "C" int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint
         desc.push_back(PlaceDesc{k.src, block_dst[k.id], k.len});
     }
     if (!rc) {
-        ctx->n = n;
-        ctx->T = T;
-        rc = dev_alloc(ctx, &ctx->d_hashes, T);
-        if (!rc) rc = dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1);
+        rc = dev_alloc(ctx, &ctx->d_hashes, T + 2);
         if (!rc) rc = ygpu_temp_reserve(ctx, std::max<size_t>(desc.size(), 1) * sizeof(PlaceDesc));
     }
     if (!rc) {
@@ -417,15 +416,41 @@ extern "C" int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint
                 ctx->tm.n_kernel_launches++;
             }
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[1], st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // desc is a host temporary
         if (e != cudaSuccess) rc = ygpu_fail(ctx, YGPU_ERR_CUDA, "upload_finish: %s", cudaGetErrorString(e));
     }
-    if (!rc) rc = finish_load(ctx);
     if (!rc) ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
     ygpu_upload_release(ctx);
     return rc;
+}
+
+// block_dst[id] = position of block `id` in the flat hash array; offsets / n as for ygpu_load_sketches.
+extern "C" int ygpu_upload_finish(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n) {
+    if (!ctx || !offsets || (nblocks && !block_dst)) return YGPU_ERR_ARG;
+    if (offsets[0] != 0) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets[0] must be 0");
+    for (uint32_t g = 0; g < n; g++)
+        if (offsets[g + 1] < offsets[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+    const uint64_t T = offsets[n];
+    YG_CHECK(upload_place(ctx, block_dst, nblocks, T));
+    ctx->n = n;
+    ctx->T = T;
+    ctx->sharded = false;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    return finish_load(ctx);
+}
+
+int ygpu_sharded_finish(ygpu_ctx* ctx, const uint64_t* offsets, uint32_t n, uint32_t g_begin, uint32_t g_end);   // index_msd.cu
+
+// Sharded residency: the uploaded blocks are the sketches of genomes [g_begin, g_end) only; block_dst is relative to
+// the first hash of genome g_begin.  Collective over the communicator (like ygpu_load_sketches_sharded).
+extern "C" int ygpu_upload_finish_sharded(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n,
+                                          uint32_t g_begin, uint32_t g_end) {
+    if (!ctx || !offsets || (nblocks && !block_dst)) return YGPU_ERR_ARG;
+    if (g_begin > g_end || g_end > n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad genome range [%u,%u) of %u", g_begin, g_end, n);
+    YG_CHECK(upload_place(ctx, block_dst, nblocks, offsets[g_end] - offsets[g_begin]));
+    return ygpu_sharded_finish(ctx, offsets, n, g_begin, g_end);
 }
 
 extern "C" int ygpu_load_sketches_device(ygpu_ctx* ctx, const uint64_t* d_hashes, const uint64_t* d_offsets, uint32_t n) {
@@ -1086,6 +1111,36 @@ __global__ void __launch_bounds__(256) k_pack_pairs(const uint64_t* __restrict__
         pr.count = (int32_t)cnt[k];
         out[k] = pr;
     }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_pairs(const ygpu_pair* __restrict__ in, uint64_t n, uint64_t* __restrict__ key,
+                                                       uint32_t* __restrict__ cnt) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        const ygpu_pair pr = in[k];
+        key[k] = ((uint64_t)(uint32_t)pr.i << 32) | (uint64_t)(uint32_t)pr.j;
+        cnt[k] = (uint32_t)pr.count;
+    }
+}
+
+static int ensure_out(ygpu_ctx* ctx, uint64_t cap);
+
+// order a device-resident pair list by (i, j) in place (the gathered lists of several ranks interleave)
+int ygpu_sort_pairs_device(ygpu_ctx* ctx, ygpu_pair* d_pairs, uint64_t n) {
+    if (n < 2) return 0;
+    cudaStream_t st = ctx->stream;
+    YG_CHECK(ensure_out(ctx, std::max<uint64_t>(ctx->out_cap, n)));
+    k_unpack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(d_pairs, n, ctx->d_out_key, ctx->d_out_cnt);
+    YG_CUDA(ctx, cudaGetLastError());
+    size_t tb = 0;
+    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 64, st));
+    YG_CHECK(ygpu_temp_reserve(ctx, tb));
+    tb = ctx->temp_bytes;
+    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 64, st));
+    k_pack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, n, d_pairs);
+    YG_CUDA(ctx, cudaGetLastError());
+    ctx->tm.n_kernel_launches += 2;
+    ctx->tm.n_library_launches += 10;
+    return 0;
 }
 
 static int ensure_out(ygpu_ctx* ctx, uint64_t cap) {

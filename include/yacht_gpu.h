@@ -91,6 +91,7 @@ typedef struct {
     /* partition path, per kernel (their sum + the small scans in between = ms_sort):              */
     double ms_hist1, ms_scatter1, ms_hist2, ms_scatter2;
     double ms_group;        /* k2_group alone (ms_index additionally holds k2_items when sharded)  */
+    double ms_sample_kernels; /* K5: the two probe passes over the partitioned reference alone (inside ms_sample) */
 } ygpu_timings;
 
 /* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */
@@ -144,7 +145,8 @@ int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
  * "index_path" = 0 forces the general sort-based index build (1 = automatic choice, default);
  * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic);
  * "big_buckets" = 0 sends a database with ANY oversized final bucket to the general path (default 1:
- * only those buckets leave the partition path).                                                  */
+ * only those buckets leave the partition path); "group_kernel" = 1 forces the general grouping kernel;
+ * "run_path" = 0 forces the general sort-based run path (default 1: probe the partitioned reference).  */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

@@ -109,6 +109,12 @@ struct ygpu_ctx {
     ygpu_pair* d_pairs_local = nullptr;     // this rank's pairs before the gather
     uint64_t pairs_local_cap = 0;
 
+    void* part_state = nullptr;     // the MSD partition of the resident sketches (index_msd.cu: MsdPartState), reused by the run path
+    bool part_valid = false;
+    void* run_part_scratch = nullptr;   // sample buckets / nontrivial bitmap of the partition-probe run path
+    int run_path = 1;               // 1: partition-probe run path when the database qualifies, 0: always the general sort-based one
+    int last_run_path = 0;
+
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
     void* upload = nullptr;         // streaming ingest state (yacht_gpu.cu: ygpu_upload_*)
 
@@ -203,6 +209,9 @@ int ygpu_max_hash(ygpu_ctx* ctx, uint64_t* maxkey);   // largest resident hash (
 // MSD-partition index build (index_msd.cu): *used = 0 when the input does not qualify for it
 int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used);
 
+// run path on the partitioned reference (index_msd.cu): *used = 0 when the database / sample does not qualify
+int ygpu_run_counts_buckets(ygpu_ctx* ctx, const uint64_t* d_sample, uint64_t n_sample, const uint8_t* d_mask, ygpu_genome_counts* d_counts, int* used);
+void ygpu_part_release(ygpu_ctx* ctx);
 // run path (run_kernels.cu)
 void ygpu_run_release(ygpu_ctx* ctx);
 void ygpu_upload_release(ygpu_ctx* ctx);

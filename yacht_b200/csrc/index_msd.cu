@@ -782,6 +782,7 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             const uint32_t w0 = bb & ~1u, w1 = (bb + m + 1u) & ~1u;
             bulk_load(sm.stage, a.ent + w0, (w1 - w0) * 8u, &sm.mbar);
         }
+        preload();          // the extent of the bucket after that one: in flight during phases B..F, consumed after the next phase A
     };
     for (uint32_t i = tid; i < G2_NSUB; i += G2_THREADS) sm.cnt[i] = 0;
     if (tid == 0) {
@@ -799,7 +800,6 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
     for (;;) {
         const uint32_t bb = sm.next[par][0], m = sm.next[par][1];
         if (!m) break;
-        if (tid == 0) preload();
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
         // ---- A: four words per thread, sub-bucket rank -----------------------------------------------------------
@@ -1215,6 +1215,16 @@ __global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ of
     }
 }
 
+// What the partition leaves behind (kept per context: `yacht run` probes many samples against one partitioned reference)
+struct MsdPartState {
+    MsdPlan p;
+    int sbits = 0, rest_bits = 0;
+    const uint64_t* final_ent = nullptr;
+    const uint32_t* final_base = nullptr;
+    uint32_t nbuckets = 0;
+    uint64_t largest = 0;
+};
+
 int bitlen(uint64_t v) {
     int b = 0;
     while (b < 64 && (v >> b) != 0) b++;
@@ -1224,8 +1234,9 @@ int bitlen(uint64_t v) {
 // part / nparts: this call covers the `part`-th share of the hash space (level-1 digits split by hash count);
 // stream: leave the groups as a compact stream (d_post = genome ids, d_st_rem = members that follow) instead of
 // building work lists.  *used = 0 when the input does not qualify for this path.
-int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint32_t nparts, bool stream) {
+int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint32_t nparts, bool stream, bool partition_only = false) {
     *used = 0;
+    ctx->part_valid = false;
     const uint64_t T = ctx->T;
     const uint32_t n = ctx->n;
     if (T < 2 || n < 2) return 0;
@@ -1257,7 +1268,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     const int key_bits = p.kb1 - d2;                       // hash bits that still vary inside a final bucket
     const int sbits = std::max(0, std::min(GK_SUBBITS, key_bits));
     const int rest_bits = key_bits - sbits;                // compared inside a sub-bucket (32 low bits + the rest beside the genome id)
-    if (rest_bits > 32 && rest_bits - 32 + p.gb > 32) return 0;     // does not fit the candidate arrays: general path
+    if (!partition_only && rest_bits > 32 && rest_bits - 32 + p.gb > 32) return 0;     // does not fit the candidate arrays: general path
 
     // ---- buffers ----------------------------------------------------------------------------------
     YG_CHECK(dev_alloc(ctx, &ctx->d_ent1, T));
@@ -1376,6 +1387,18 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];   // (level-1 maximum: over all digits, a safe bound)
     const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
+    if (nparts == 1) {
+        if (!ctx->part_state) ctx->part_state = new MsdPartState();
+        MsdPartState* ps = (MsdPartState*)ctx->part_state;
+        ps->p = p; ps->sbits = sbits; ps->rest_bits = rest_bits; ps->final_ent = final_ent; ps->final_base = final_base;
+        ps->nbuckets = nbuckets; ps->largest = largest;
+        ctx->part_valid = true;
+    }
+    if (partition_only) {
+        ctx->tm.ms_sort += elapsed(ctx, 0, 1);
+        *used = 1;
+        return 0;
+    }
     uint32_t n_big = 0;
     uint64_t N_big = 0;
     std::vector<uint32_t> big_list;
@@ -1545,7 +1568,132 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     return 0;
 }
 
+#include "run_buckets.cuh"
+
+struct RunPartScratch {
+    uint32_t* d_aux = nullptr;      // sample histogram | bases | cursors: 3 x (nb + 2)
+    uint64_t aux_cap = 0;
+    uint64_t* d_skeys = nullptr;
+    uint64_t skeys_cap = 0;
+    uint32_t* d_ntbits = nullptr;
+    uint64_t nt_cap = 0;
+};
+
 }  // namespace
+
+void ygpu_part_release(ygpu_ctx* ctx) {
+    if (ctx->part_state) delete (MsdPartState*)ctx->part_state;
+    ctx->part_state = nullptr;
+    ctx->part_valid = false;
+    RunPartScratch* r = (RunPartScratch*)ctx->run_part_scratch;
+    if (r) {
+        if (r->d_aux) cudaFree(r->d_aux);
+        if (r->d_skeys) cudaFree(r->d_skeys);
+        if (r->d_ntbits) cudaFree(r->d_ntbits);
+        delete r;
+    }
+    ctx->run_part_scratch = nullptr;
+}
+
+// K5 on the partitioned reference (run_buckets.cuh).  d_sample: the sample hashes on the device (any order); d_mask: NULL or
+// the caller's nontrivial genomes; d_counts: zeroed by the caller.  *used = 0: this database / sample takes the general path.
+int ygpu_run_counts_buckets(ygpu_ctx* ctx, const uint64_t* d_sample, uint64_t n_sample, const uint8_t* d_mask, ygpu_genome_counts* d_counts,
+                            int* used) {
+    *used = 0;
+    if (ctx->run_path == 0 || ctx->sharded || ctx->T < 2 || ctx->n < 2) return 0;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->part_valid) {
+        ygpu_index_stats S{};
+        int u = 0;
+        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
+        YG_CHECK(msd_build(ctx, &S, &u, 0, 1, false, /*partition_only=*/true));
+        if (!u || !ctx->part_valid) return 0;
+        ctx->indexed = false;           // the partition buffers are shared with the train index build: that index is gone
+    }
+    const MsdPartState& ps = *(const MsdPartState*)ctx->part_state;
+    if (ps.largest > G2_MAXM) return 0;                     // skewed database: general path
+    const MsdPlan& p = ps.p;
+    const uint32_t nb = ps.nbuckets;
+    const int key_bits = ps.sbits + ps.rest_bits;
+    if (p.gb + ps.rest_bits > 63) return 0;
+    if (!ctx->run_part_scratch) ctx->run_part_scratch = new RunPartScratch();
+    RunPartScratch* r = (RunPartScratch*)ctx->run_part_scratch;
+    const uint64_t aux = 3ull * ((uint64_t)nb + 2);
+    if (aux > r->aux_cap) {
+        if (r->d_aux) cudaFree(r->d_aux);
+        r->d_aux = nullptr; r->aux_cap = 0;
+        YG_CUDA(ctx, cudaMalloc(&r->d_aux, aux * sizeof(uint32_t)));
+        r->aux_cap = aux;
+    }
+    if (n_sample + 1 > r->skeys_cap) {
+        if (r->d_skeys) cudaFree(r->d_skeys);
+        r->d_skeys = nullptr; r->skeys_cap = 0;
+        YG_CUDA(ctx, cudaMalloc(&r->d_skeys, (n_sample + 1) * sizeof(uint64_t)));
+        r->skeys_cap = n_sample + 1;
+    }
+    const uint64_t ntw = ((uint64_t)ctx->n + 31) / 32 + 1;
+    if (ntw > r->nt_cap) {
+        if (r->d_ntbits) cudaFree(r->d_ntbits);
+        r->d_ntbits = nullptr; r->nt_cap = 0;
+        YG_CUDA(ctx, cudaMalloc(&r->d_ntbits, ntw * sizeof(uint32_t)));
+        r->nt_cap = ntw;
+    }
+    uint32_t* shist = r->d_aux;
+    uint32_t* sbase = shist + ((uint64_t)nb + 2);
+    uint32_t* scur = sbase + ((uint64_t)nb + 2);
+    const uint64_t key_mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+    // ---- the sample, bucketed like the reference ----
+    YG_CUDA(ctx, cudaMemsetAsync(r->d_aux, 0, aux * sizeof(uint32_t), st));
+    if (n_sample) {
+        k5s_hist<<<grid_for(ctx, n_sample, 256), 256, 0, st>>>(d_sample, n_sample, p, shist);
+        YG_CUDA(ctx, cudaGetLastError());
+    }
+    uint32_t* d_smax = (uint32_t*)&ctx->d_scalars[SCM_ICUR];
+    size_t tb = 0, tb2 = 0;
+    YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, shist, sbase, (int64_t)nb + 1, st));
+    YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb2, shist, d_smax, (int64_t)nb, st));
+    YG_CHECK(ygpu_temp_reserve(ctx, std::max(tb, tb2)));
+    tb = ctx->temp_bytes;
+    YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, shist, sbase, (int64_t)nb + 1, st));
+    tb = ctx->temp_bytes;
+    YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, shist, d_smax, (int64_t)nb, st));
+    ctx->tm.n_library_launches += 4;
+    uint32_t smax = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(&smax, d_smax, sizeof smax, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (smax > RB_SCAP) return 0;                           // a bucket's sample does not fit shared memory: general path
+    YG_CUDA(ctx, cudaMemcpyAsync(scur, sbase, ((uint64_t)nb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (n_sample) {
+        k5s_scatter<<<grid_for(ctx, n_sample, 256), 256, 0, st>>>(d_sample, n_sample, p, key_mask, scur, r->d_skeys);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches += 2;
+    }
+    RunBucketArgs a{};
+    a.ent = ps.final_ent; a.base = ps.final_base; a.nb = nb; a.gb = p.gb;
+    a.sub_shift = p.gb + ps.rest_bits; a.sub_mask = (1u << ps.sbits) - 1u; a.rest_bits = ps.rest_bits;
+    a.key_mask = key_mask; a.skeys = r->d_skeys; a.sbase = sbase; a.ntbits = r->d_ntbits; a.counts = d_counts;
+    const size_t smem = sizeof(RunSmem);
+    YG_CUDA(ctx, cudaFuncSetAttribute(k5_bucket<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YG_CUDA(ctx, cudaFuncSetAttribute(k5_bucket<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5_bucket<1>, G2_THREADS, smem));
+    const int grid = (int)std::min<uint64_t>(nb, (uint64_t)ctx->num_sms * std::max(occ, 1));
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[0], st));
+    if (n_sample) {
+        k5_bucket<0><<<grid, G2_THREADS, smem, st>>>(a);
+        YG_CUDA(ctx, cudaGetLastError());
+        ctx->tm.n_kernel_launches++;
+    }
+    k5_nontrivial_bits<<<grid_for(ctx, ntw, 256), 256, 0, st>>>(d_counts, d_mask, ctx->n, r->d_ntbits);
+    YG_CUDA(ctx, cudaGetLastError());
+    k5_bucket<1><<<grid, G2_THREADS, smem, st>>>(a);
+    YG_CUDA(ctx, cudaGetLastError());
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[1], st));
+    ctx->tm.n_kernel_launches += 2;
+    ctx->last_run_path = 1;
+    *used = 1;
+    return 0;
+}
 
 int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     const uint64_t T = ctx->T;
@@ -1734,7 +1882,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     const int N = C->nranks, rank = C->rank;
     const uint64_t T = ctx->T, Tg = ctx->T_global;
     const uint32_t n = ctx->n;
-    ctx->indexed = false; ctx->row_work_valid = false; ctx->n_pairs = 0;
+    ctx->indexed = false; ctx->row_work_valid = false; ctx->n_pairs = 0; ctx->part_valid = false;
     ygpu_index_stats S{};
     S.n_hashes = Tg;
     S.max_sketch = ctx->max_sketch_global;

@@ -135,9 +135,7 @@ extern "C" int ygpu_exclusive_hashes(ygpu_ctx* ctx, const uint64_t* sample, uint
     const uint32_t n = ctx->n;
     const uint64_t T = ctx->T;
     if (n == 0) return 0;
-    YG_CHECK(ygpu_sort_sketches(ctx));
     RunScratch* r = scratch(ctx);
-
     if (n_sample + 1 > r->cap) {
         if (r->d_sample) cudaFree(r->d_sample);
         if (r->d_sample_in) cudaFree(r->d_sample_in);
@@ -164,6 +162,28 @@ extern "C" int ygpu_exclusive_hashes(ygpu_ctx* ctx, const uint64_t* sample, uint
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     YG_CUDA(ctx, cudaMemsetAsync(r->d_counts, 0, (size_t)n * sizeof(ygpu_genome_counts), st));
     if (mask) YG_CUDA(ctx, cudaMemcpyAsync(r->d_mask, mask, n, cudaMemcpyHostToDevice, st));
+    ctx->last_run_path = 0;
+    // ---- preferred: probe the MSD-partitioned reference bucket by bucket (run_buckets.cuh): no sort of the reference or the sample
+    if (T && ctx->run_path != 0) {
+        if (n_sample) YG_CUDA(ctx, cudaMemcpyAsync(r->d_sample_in, sample, n_sample * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+        int used = 0;
+        YG_CHECK(ygpu_run_counts_buckets(ctx, r->d_sample_in, n_sample, mask ? r->d_mask : nullptr, r->d_counts, &used));
+        if (used) {
+            YG_CUDA(ctx, cudaMemcpyAsync(counts, r->d_counts, (size_t)n * sizeof(ygpu_genome_counts), cudaMemcpyDeviceToHost, st));
+            YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+            YG_CUDA(ctx, cudaStreamSynchronize(st));
+            float ms = 0.f, msk = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&msk, ctx->evp[0], ctx->evp[1]);
+            ctx->tm.ms_sample += ms;
+            ctx->tm.ms_sample_kernels += msk;
+            return 0;
+        }
+        // not applicable: start over on the general path (counters may hold partial credits)
+        YG_CUDA(ctx, cudaMemsetAsync(r->d_counts, 0, (size_t)n * sizeof(ygpu_genome_counts), st));
+    }
+    YG_CHECK(ygpu_sort_sketches(ctx));
 
     int shift = 0;
     uint32_t nb = 0;

@@ -112,6 +112,7 @@ static void release_sketches(ygpu_ctx* ctx) {
     release_index(ctx);
     ctx->loaded = false;
     ctx->sharded = false;
+    ctx->part_valid = false;
     ctx->maxkey_valid = false;
     ctx->n = 0; ctx->T = 0;
 }
@@ -136,6 +137,7 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     release_sketches(ctx);
     free_all(ctx);
     ygpu_run_release(ctx);
+    ygpu_part_release(ctx);
     ygpu_upload_release(ctx);
     ygpu_comm_destroy(ctx);
     if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);
@@ -1341,6 +1343,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "count_kernel")) { ctx->count_kernel = (int)value; return 0; }
     if (!strcmp(name, "big_buckets")) { ctx->big_buckets = (int)value; return 0; }
     if (!strcmp(name, "group_kernel")) { ctx->group_kernel = (int)value; return 0; }
+    if (!strcmp(name, "run_path")) { ctx->run_path = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

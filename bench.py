@@ -497,7 +497,8 @@ def run_b200_arm(args):
                             regions="resident + e2e timed regions pooled") if clock_samples else clocks),
             "roofline": dominant, "rooflines": rooflines, "index_path": "msd-partition" if msd else "general-sort",
             "index_mode": mode["index"],
-            "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort")},
+            "phases_ms": {k: tm_res[k] / steps for k in ("ms_sort", "ms_index", "ms_count", "ms_pairsort", "ms_hist1", "ms_scatter1", "ms_hist2",
+                                                           "ms_scatter2", "ms_group", "ms_items", "ms_sync", "ms_gather")},
             "workload_counts": dict(counts, F=F, genomes=n), "wall_ms_per_step": wall_res * 1e3, "gen_seconds": gen_s,
         }
         # ---- parity at the benchmarked size: the gathered pair list of the last e2e step against the reference digest ----

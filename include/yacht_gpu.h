@@ -92,6 +92,9 @@ typedef struct {
     double ms_hist1, ms_scatter1, ms_hist2, ms_scatter2;
     double ms_group;        /* k2_group alone (ms_index additionally holds k2_items when sharded)  */
     double ms_sample_kernels; /* K5: the two probe passes over the partitioned reference alone (inside ms_sample) */
+    /* sharded step: work-list build from the complete stream (k2_items_regions), the control collectives + cross-rank
+     * waits between the phases, and the gather of the pair lists (inside ms_index / ms_pairsort)            */
+    double ms_items, ms_sync, ms_gather;
 } ygpu_timings;
 
 /* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */
@@ -146,7 +149,9 @@ int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
  * "count_kernel" = 1 forces the dense-row count kernel, 2 the warp-per-row one (0 = automatic);
  * "big_buckets" = 0 sends a database with ANY oversized final bucket to the general path (default 1:
  * only those buckets leave the partition path); "group_kernel" = 1 forces the general grouping kernel;
- * "run_path" = 0 forces the general sort-based run path (default 1: probe the partitioned reference).  */
+ * "run_path" = 0 forces the general sort-based run path (default 1: probe the partitioned reference);
+ * "count_thresholds" = 0 evaluates the containment expression per pair in fp64 inside the count kernel (default 1: the
+ * smallest passing count per genome is found with that expression once, the kernel compares integers).  */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

@@ -49,6 +49,12 @@ def _check(ctx, db, thr, expect_path=None, ref=None):
             got = ctx.pairwise_flag(thr)
             assert _pairs_tuple(got) == _pairs_tuple(ref.pairs), (path, count_kernel)
         ctx.set_option("count_kernel", 0)
+        # the containment test as per-genome integer thresholds (default) and as the fp64 expression per pair
+        ctx.set_option("count_thresholds", 0)
+        try:
+            assert _pairs_tuple(ctx.pairwise_flag(thr)) == _pairs_tuple(ref.pairs), (path, "fp64 per pair")
+        finally:
+            ctx.set_option("count_thresholds", 1)
         if path == 1:
             out = (st, got)
             if expect_path is not None:

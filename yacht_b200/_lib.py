@@ -48,7 +48,8 @@ class Timings(ctypes.Structure):
                 ("ms_stats", ctypes.c_double), ("n_count_launches", ctypes.c_uint64),
                 ("n_kernel_launches", ctypes.c_uint64), ("n_library_launches", ctypes.c_uint64),
                 ("ms_hist1", ctypes.c_double), ("ms_scatter1", ctypes.c_double), ("ms_hist2", ctypes.c_double),
-                ("ms_scatter2", ctypes.c_double), ("ms_group", ctypes.c_double), ("ms_sample_kernels", ctypes.c_double)]
+                ("ms_scatter2", ctypes.c_double), ("ms_group", ctypes.c_double), ("ms_sample_kernels", ctypes.c_double),
+                ("ms_items", ctypes.c_double), ("ms_sync", ctypes.c_double), ("ms_gather", ctypes.c_double)]
 
     def as_dict(self) -> dict:
         return {k: (float(getattr(self, k)) if t is ctypes.c_double else int(getattr(self, k))) for k, t in self._fields_}

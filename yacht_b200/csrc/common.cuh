@@ -16,7 +16,7 @@ struct ygpu_ctx {
     int smem_optin = 0;          // max dynamic shared memory per CTA (opt-in), bytes
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t evp[10] = {};     // per-kernel events of the partition path
+    cudaEvent_t evp[16] = {};     // per-kernel events of the partition path / the sharded step
     std::string err;
 
     // ---- sketches (flat, device resident) ---------------------------------------------------
@@ -70,6 +70,8 @@ struct ygpu_ctx {
     int last_count_kernel = 0;
     unsigned long long last_count_overflow_rows = 0;
     uint32_t* d_ovf_rows = nullptr; // rows the warp kernel deferred to the dense kernel
+    uint32_t* d_tc = nullptr;       // [n] smallest shared-hash count that passes the containment test of genome g
+    int count_thresholds = 1;       // test hook: 0 = evaluate the fp64 expression per pair inside the count kernel
     ygpu_index_stats stats = {};
 
     // ---- scratch ------------------------------------------------------------------------------

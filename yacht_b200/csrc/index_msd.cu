@@ -1901,7 +1901,9 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     auto used_buckets = [&](int D) -> uint64_t { return D == 0 ? 1ull : (maxkey >> (p.hb - D)) + 1ull; };
     int D = 0;
     while (D < p.hb && D < 22 && Tg / used_buckets(D) > A_TARGET) D++;
-    int d1 = D <= 8 ? D : (D + 1) / 2;
+    // level 1 is the exchange: its runs per (tile, digit) are what crosses NVLink, so it gets as FEW digits as the two levels
+    // allow (level 2 takes up to 11 bits) -- 16-word runs are 128-byte packets, 4-word runs are 32-byte ones
+    int d1 = D <= 8 ? D : std::max(D - 11, std::min(8, D / 2));
     const int need = p.hb + p.gb - 64;
     if (need > d1) d1 = need;
     int d2 = std::max(0, D - d1);
@@ -1995,6 +1997,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     // every rank's words have landed once every rank has passed this point (the collective also orders the peer stores)
     unsigned long long* d_sync = &ctx->d_sh_info[41];
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_sync, d_sync, 1, true));
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[9], st));
     ctx->tm.n_kernel_launches += 4;
 
     // ---- 2. level 2 + grouping on this rank's share of the hash space; groups stored into every rank's stream ---------
@@ -2059,12 +2062,14 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     // stream lengths of all ranks (the all-gather is also the barrier behind the stream stores)
     unsigned long long* d_lens = &ctx->d_sh_info[SHI_LENS];
     YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_scalars[SCM_STREAM], d_lens, sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
 
     // ---- 3. work lists of this rank's rows from the complete stream; statistics over all ranks ---------------------------
     k2_items_regions<<<grid_for(ctx, std::max<uint64_t>(Tg / 4, 1), 256, 16), 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end,
                                                                                       p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_row_begin_local,
                                                                                       ctx->d_row_cnt, ctx->d_row_items);
     YG_CUDA(ctx, cudaGetLastError());
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[11], st));
     ctx->tm.n_kernel_launches += 1;
     // scalars 0..3 (heads, singles, dups, W) summed over the ranks; slot SCM_MAXB(+1) = largest bucket (max)
     unsigned long long* d_tot = &ctx->d_sh_info[24];
@@ -2083,6 +2088,8 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         ctx->tm.ms_scatter1 += el(2, 3);
         if (d2) { ctx->tm.ms_hist2 += el(3, 4); ctx->tm.ms_scatter2 += el(5, 6); }
         ctx->tm.ms_group += el(7, 8);
+        ctx->tm.ms_items += el(10, 11);
+        ctx->tm.ms_sync += el(3, 9) + el(8, 10);       // waiting for the peers behind the two exchanges (+ the collectives themselves)
     }
     if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d owns %llu words, exchange buffer holds %llu", rank, info[SHI_TMINE], (unsigned long long)cap);
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
@@ -2134,6 +2141,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
             if (counts[q]) YG_CUDA(ctx, cudaMemcpyAsync(out + pos, pad + (uint64_t)q * mxc, counts[q] * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
             pos += counts[q];
         }
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[12], st));
         if (N > 1) YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
         if (total > ctx->pairs_cap) {
             if (ctx->d_pairs) cudaFree(ctx->d_pairs);
@@ -2146,6 +2154,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->tm.ms_pairsort += elapsed(ctx, 2, 3);
+    if (total) { float g = 0.f; cudaEventElapsedTime(&g, ctx->ev[2], ctx->evp[12]); ctx->tm.ms_gather += g; }
     ctx->n_pairs = total;
     *n_pairs_total = total;
     return 0;

@@ -127,6 +127,7 @@ static void free_all(ygpu_ctx* ctx) {
     dev_free(ctx, &ctx->d_hashes); dev_free(ctx, &ctx->d_offsets); dev_free(ctx, &ctx->d_sizes); dev_free(ctx, &ctx->d_gid);
     dev_free(ctx, &ctx->d_offsets_local); dev_free(ctx, &ctx->d_row_begin_local); dev_free(ctx, &ctx->d_sh_hist_all);
     dev_free(ctx, &ctx->d_sh_owner); dev_free(ctx, &ctx->d_sh_info);
+    dev_free(ctx, &ctx->d_tc);
     dev_free(ctx, &ctx->d_out_key); dev_free(ctx, &ctx->d_out_cnt); dev_free(ctx, &ctx->d_out_key2); dev_free(ctx, &ctx->d_out_cnt2);
 }
 
@@ -764,6 +765,7 @@ struct K3Params {
     const uint32_t* row_list;  // dense kernel: explicit rows (the warp kernel's overflow list) instead of [row_begin, row_end)
     uint32_t n_list;
     uint32_t* ovf_rows;        // warp kernel: rows whose distinct columns overflow a warp's hash table
+    const uint32_t* tc;        // [n] smallest count that passes the containment test for genome g (k4_thresholds), or NULL
 };
 
 // warp-aggregated append: one atomic per warp-instruction instead of one per lane
@@ -783,7 +785,28 @@ __device__ __forceinline__ void emit_pair(const K3Params& p, uint32_t i, uint32_
 
 // the reference's test for one unordered pair {i<j} with `cnt` shared hashes, both directions
 // (main.cpp:277-303).  The "union" is evaluated modulo 2^64 exactly as size_t + size_t - int is.
+// The reference's comparison `1.0 * cnt / size < thr` (main.cpp:297-301) is monotone in cnt, so for every genome there is a
+// smallest passing count; k4_thresholds finds it with that very fp64 expression, and the kernel compares integers.  Only
+// valid without in-sketch duplicates (the reference's zero-union skip can then never fire: cnt <= min(ni, nj)).
+__global__ void __launch_bounds__(256) k4_thresholds(const uint32_t* __restrict__ sizes, uint32_t n, double thr, uint32_t* __restrict__ tc) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t ni = sizes[g];
+        if (ni == 0) { tc[g] = 0xFFFFFFFFu; continue; }
+        const double dn = (double)ni;
+        long long c = (long long)ceil(thr * dn);
+        if (c < 1) c = 1;
+        while (c > 1 && !(1.0 * (double)(int32_t)(c - 1) / dn < thr)) c--;
+        while (c < 0x7FFFFFFFll && (1.0 * (double)(int32_t)c / dn < thr)) c++;
+        tc[g] = (uint32_t)c;
+    }
+}
+
 __device__ __forceinline__ void test_pair(const K3Params& p, uint32_t i, uint32_t j, uint32_t cnt) {
+    if (p.tc) {
+        if (cnt >= p.tc[i]) emit_pair(p, i, j, cnt);
+        if (cnt >= p.tc[j]) emit_pair(p, j, i, cnt);
+        return;
+    }
     const uint32_t ni = p.sizes[i], nj = p.sizes[j];
     if (ni == 0 || nj == 0) return;
     const uint64_t uni = (uint64_t)ni + (uint64_t)nj - (uint64_t)(int64_t)(int32_t)cnt;
@@ -1214,6 +1237,14 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
             p.n = n; p.row_begin = row_begin; p.row_end = row_end; p.tile_w = tile_w; p.n_tiles = n_tiles;
             p.thr = threshold; p.out_key = ctx->d_out_key; p.out_cnt = ctx->d_out_cnt; p.out_cap = ctx->out_cap;
             p.scal = ctx->d_scalars; p.row_list = nullptr; p.n_list = 0; p.ovf_rows = ctx->d_ovf_rows;
+            p.tc = nullptr;
+            if (!ctx->stats.has_duplicates && ctx->count_thresholds != 0) {
+                YG_CHECK(dev_alloc(ctx, &ctx->d_tc, n));
+                k4_thresholds<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->d_sizes, n, threshold, ctx->d_tc);
+                YG_CUDA(ctx, cudaGetLastError());
+                ctx->tm.n_kernel_launches++;
+                p.tc = ctx->d_tc;
+            }
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_OUT], 0, 2 * sizeof(unsigned long long), st));
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SC_OVF], 0, sizeof(unsigned long long), st));
             YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
@@ -1344,6 +1375,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "big_buckets")) { ctx->big_buckets = (int)value; return 0; }
     if (!strcmp(name, "group_kernel")) { ctx->group_kernel = (int)value; return 0; }
     if (!strcmp(name, "run_path")) { ctx->run_path = (int)value; return 0; }
+    if (!strcmp(name, "count_thresholds")) { ctx->count_thresholds = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);
 }
 

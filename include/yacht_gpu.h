@@ -17,8 +17,9 @@
  *                           counts (:252-262) fused with threshold/emit (:274-308)
  *   ygpu_greedy_select      do_yacht_train(): greedy near-duplicate removal    main.cpp:371-420
  *   ygpu_row_partition      the contiguous row chunks per thread / per pass    main.cpp:338-349
- *   ygpu_index_partial / _stream_copy / _finish   compute_index_from_sketches() split by hash range across GPUs   main.cpp:215-246
- *                           (here: work-balanced row ranges per GPU)
+ *   ygpu_comm_init / ygpu_load_sketches_sharded / ygpu_train_step_sharded
+ *                           the same three steps (:215-366) with one rank per GPU: index build split by hash
+ *                           range, count by query rows (the reference's row chunks per thread / pass, :338-349)
  *   ygpu_exclusive_hashes   `sourmash scripts multisearch ... -t 0`            hypothesis_recovery_src.py:93-113
  *                           (which reference genomes share >= 1 hash with the
  *                           sample: counts[g].n_overlap > 0), followed by
@@ -201,26 +202,6 @@ int ygpu_greedy_select(const uint64_t* offsets, uint32_t n_genomes, const ygpu_p
                        int32_t* selected, uint32_t* n_selected);
 /* bounds[0..nparts] : contiguous row ranges of (nearly) equal pairwise-count work.               */
 int ygpu_row_partition(ygpu_ctx* ctx, uint32_t nparts, uint32_t* bounds);
-
-/* ---- hash-range sharded index build (one process per GPU) -----------------------------------------
- * compute_index_from_sketches() (main.cpp:215-246) is one hash map filled by one thread.  Across GPUs the
- * hash SPACE is split instead: every rank holds all sketches, rank `part` of `nparts` partitions and groups
- * only the hashes whose leading bits fall in its share, and leaves a compact "group stream" on its device:
- * for every hash held by >= 2 genome slots the genome ids in ascending order (what main.cpp:228-236 keeps
- * per hash), plus per entry the number of entries of the same hash that follow.  The ranks exchange their
- * streams (the caller's NCCL all-gather; this library does not link NCCL) and each rank turns the complete
- * stream into the work lists of ITS query rows (main.cpp:338-349's row chunks) with ygpu_index_finish.
- * Fails with YGPU_ERR_STATE when the database does not qualify for the partition path (callers then use
- * the replicated ygpu_build_index).  `stats` holds this share's counts: sum them over the ranks.          */
-int ygpu_index_partial(ygpu_ctx* ctx, uint32_t part, uint32_t nparts, ygpu_index_stats* stats, uint64_t* n_entries);
-/* Copy this rank's stream (n_entries genome ids / follow counts) to DEVICE buffers of the caller.          */
-int ygpu_index_stream_copy(ygpu_ctx* ctx, uint32_t* d_gid_dst, uint16_t* d_rem_dst);
-/* d_gid / d_rem: DEVICE pointers to the complete stream (all ranks' slices, any order of the slices; entries
- * with d_rem = 0 that no other entry points to -- e.g. padding -- are ignored).  Builds the work lists of rows
- * [row_begin, row_end); ygpu_pairwise_flag[_device] is then valid for row ranges inside it.  `total` = the
- * sum of the ranks' partial statistics.                                                                     */
-int ygpu_index_finish(ygpu_ctx* ctx, const uint32_t* d_gid, const uint16_t* d_rem, uint64_t n_entries,
-                      uint32_t row_begin, uint32_t row_end, const ygpu_index_stats* total);
 
 /* ---- sharded train step: one rank per GPU (threads of one process or one process per GPU, one node) ---------
  * The reference's only parallelism is its contiguous row chunks per thread / pass over ONE shared index

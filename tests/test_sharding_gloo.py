@@ -72,7 +72,7 @@ def test_split_rows_by_work_properties():
 
 def test_slice_bounds_and_size_split():
     b = sharding.slice_bounds(10, 4)
-    assert b.tolist() == [0, 3, 6, 9, 10]                      # equal slices, the last one short
+    assert b.tolist() == [0, 3, 6, 9, 10]
     assert sharding.slice_bounds(0, 3).tolist() == [0, 0, 0, 0]
     assert sharding.slice_bounds(8, 1).tolist() == [0, 8]
     off = np.array([0, 10, 10, 30, 60, 100], dtype=np.uint64)   # sizes 10, 0, 20, 30, 40
@@ -82,140 +82,105 @@ def test_slice_bounds_and_size_split():
     assert abs(int(sizes[:r[1]].sum()) - int(sizes[r[1]:].sum())) <= int(sizes.max()) + 2 * int(sharding.ROW_CONSTANT)
 
 
-# ---- the sharded build's host orchestration (yacht_b200/sharding.py) with a stand-in for the library ---------------
-class _FakeCtx:
-    """Implements the three C-ABI calls of the hash-range sharded build in numpy (hash space split by hash % world),
-    writing / reading the caller's buffers through raw pointers exactly like libyachtgpu does."""
-
-    def __init__(self, db, fail=False):
-        self.db, self.fail = db, fail
-        self.finished = None
-
-    @staticmethod
-    def groups_of(db, keep):
-        gid = np.repeat(np.arange(db.n, dtype=np.int64), np.diff(db.offsets.astype(np.int64)))
-        order = np.lexsort((gid, db.hashes))
-        h, g = db.hashes[order], gid[order]
-        out = []
-        start = 0
-        for end in list(np.flatnonzero(h[1:] != h[:-1]) + 1) + [len(h)]:
-            if end - start >= 2 and keep(int(h[start])):
-                out.append(tuple(int(x) for x in g[start:end]))
-            start = end
-        return out
-
-    def index_partial(self, part, nparts):
-        from yacht_b200._lib import YgpuError
-        if self.fail:
-            raise YgpuError("does not qualify")
-        groups = self.groups_of(self.db, lambda hv: hv % nparts == part)
-        self.gid = np.array([x for grp in groups for x in grp], dtype=np.int32)
-        self.rem = np.array([len(grp) - 1 - k for grp in groups for k in range(len(grp))], dtype=np.int16)
-        st = dict(n_hashes=int(sum(1 for hv in self.db.hashes if int(hv) % nparts == part)), n_distinct=0, n_singleton=0, n_index=len(groups),
-                  n_postings=len(self.gid), n_increments=sum(len(grp) ** 2 for grp in groups),
-                  n_row_items=len(self.gid) - len(groups), has_duplicates=0)
-        return st, len(self.gid)
-
-    def index_stream_copy(self, gptr, rptr):
-        import ctypes
-        ctypes.memmove(gptr, self.gid.ctypes.data, self.gid.nbytes)
-        ctypes.memmove(rptr, self.rem.ctypes.data, self.rem.nbytes)
-
-    def index_finish(self, gptr, rptr, n_entries, rb, re, total):
-        import ctypes
-        gid = np.frombuffer(ctypes.string_at(gptr, 4 * n_entries), dtype=np.int32)
-        rem = np.frombuffer(ctypes.string_at(rptr, 2 * n_entries), dtype=np.int16)
-        groups, x = [], 0
-        while x < n_entries:
-            if rem[x] == 0:          # padding (or the tail of a group, consumed below)
-                x += 1
-                continue
-            L = int(rem[x]) + 1
-            assert list(rem[x:x + L]) == list(range(L - 1, -1, -1))
-            groups.append(tuple(int(v) for v in gid[x:x + L]))
-            x += L
-        self.finished = dict(groups=sorted(groups), rows=(rb, re), total=dict(total))
+# ---- the sharded index build's exchange plan (host mirror of csrc/index_msd.cu: k2s_prep) -------------------------------
+D1 = 7          # leading hash bits of the toy exchange
 
 
-def _sharded_worker(rank, world, port, q, fail_rank):
+def _digits(h):
+    return (np.asarray(h, dtype=np.uint64) >> np.uint64(55 - D1)).astype(np.int64)
+
+
+def _check_plan(db, world, hists, plan):
+    nb = hists.shape[1]
+    owner, start, count = plan["owner"], plan["start"], plan["count"]
+    assert np.all(np.diff(owner) >= 0) and owner.min() >= 0 and owner.max() < world          # contiguous digit ranges, rank order
+    assert count.sum() == int(db.offsets[-1])
+    cap = sharding.exchange_capacity(int(db.offsets[-1]), world, nb)
+    assert count.max() <= cap                                                                # the buffer bound the library allocates
+    # the (source, digit) ranges tile every owner's buffer exactly once, digit-major and source-minor
+    for o in range(world):
+        segs = sorted((int(start[r, d]), int(hists[r, d])) for d in np.flatnonzero(owner == o) for r in range(world) if hists[r, d])
+        pos = 0
+        for st, ln in segs:
+            assert st == pos
+            pos += ln
+        assert pos == count[o]
+
+
+def _plan_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        db = synth.make_reference_db(120, 4, mean_size=80, sd_size=20)
-        ctx = _FakeCtx(db, fail=(rank == fail_rank))
-        res = sharding.build_index_sharded(ctx, db.offsets, rank, world, torch.device("cpu"))
-        if res is None:
-            q.put((rank, "fallback", None))
-            return
-        rb, re, total = res
-        want = sorted(_FakeCtx.groups_of(db, lambda hv: True))
-        ok = ctx.finished["groups"] == want and ctx.finished["rows"] == (rb, re)
-        ok = ok and total["n_postings"] == sum(len(g) for g in want) and total["n_hashes"] == int(db.offsets[-1])
-        q.put((rank, "ok" if ok else "mismatch", (rb, re)))
+        db = synth.make_reference_db(400, 23, mean_size=300, sd_size=90)
+        bounds = sharding.split_rows_by_size(db.offsets, world)
+        lo, hi = int(db.offsets[bounds[rank]]), int(db.offsets[bounds[rank + 1]])
+        mine = db.hashes[lo:hi]
+        nb = int(_digits([synth.MAX_HASH - 1])[0]) + 1
+        h = torch.from_numpy(np.bincount(_digits(mine), minlength=nb).astype(np.int64))
+        allh = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)                                   # the library: ncclAllGather of the level-1 histograms
+        hists = torch.stack(allh).numpy()
+        plan = sharding.exchange_plan(hists)
+        _check_plan(db, world, hists, plan)
+        # carry the exchange out: every rank "stores" its words at plan positions; the owners end up with exactly the words
+        # of their digits, grouped by digit
+        sizes = [int(c) for c in plan["count"]]
+        send = [np.zeros(0, dtype=np.uint64)] * world
+        cursor = plan["start"][rank].copy()
+        bufs_pos = [[] for _ in range(world)]
+        bufs_val = [[] for _ in range(world)]
+        for v, d in zip(mine.tolist(), _digits(mine).tolist()):
+            o = int(plan["owner"][d])
+            bufs_pos[o].append(int(cursor[d]))
+            bufs_val[o].append(v)
+            cursor[d] += 1
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (bufs_pos, bufs_val))
+        buf = np.zeros(sizes[rank], dtype=np.uint64)
+        seen = np.zeros(sizes[rank], dtype=bool)
+        for pos_r, val_r in gathered:
+            p, v = np.array(pos_r[rank], dtype=np.int64), np.array(val_r[rank], dtype=np.uint64)
+            assert not seen[p].any()
+            buf[p] = v
+            seen[p] = True
+        ok = bool(seen.all()) and bool(np.all(np.diff(_digits(buf)) >= 0)) and bool(np.all(plan["owner"][_digits(buf)] == rank))
+        want = np.sort(db.hashes[plan["owner"][_digits(db.hashes)] == rank])
+        ok = ok and np.array_equal(np.sort(buf), want)
+        q.put((rank, ok, sizes[rank]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fail_rank", [-1, 1])
-def test_sharded_build_orchestration_two_ranks(fail_rank):
-    """Every rank ends up with the complete group stream (own slice + the peer's, padding ignored), the summed
-    statistics and its own row range; when one rank's share does not qualify, BOTH ranks take the fallback."""
+def test_exchange_plan_two_ranks():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, fail_rank)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=180) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-    if fail_rank >= 0:
-        assert [r[1] for r in res] == ["fallback", "fallback"], res
-    else:
-        assert [r[1] for r in res] == ["ok", "ok"], res
-        assert res[0][2][0] == 0 and res[0][2][1] == res[1][2][0] and res[1][2][1] == 120      # the row ranges partition [0, n)
-
-
-def _ingest_worker(rank, world, port, q):
-    import ctypes
-    import torch
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        db = synth.make_reference_db(50, 8, mean_size=61, sd_size=9)          # T not a multiple of the world size
-        T = int(db.offsets[-1])
-        sb = sharding.slice_bounds(T, world)
-        mine = torch.from_numpy(db.hashes[int(sb[rank]):int(sb[rank + 1])].view(np.int64).copy())
-
-        class Ctx:
-            def load_sketches_device(self, hptr, optr, n):
-                self.h = np.frombuffer(ctypes.string_at(hptr, 8 * T), dtype=np.uint64).copy()
-                self.o = np.frombuffer(ctypes.string_at(optr, 8 * (n + 1)), dtype=np.uint64).copy()
-
-        ctx = Ctx()
-        sharding.load_sketches_sharded(ctx, mine, db.offsets, T, rank, world, torch.device("cpu"))
-        q.put((rank, bool(np.array_equal(ctx.h, db.hashes) and np.array_equal(ctx.o, db.offsets.astype(np.uint64)))))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_sharded_ingest_two_ranks():
-    """Each rank contributes only its slice of the flat hash array; after the all-gather every rank hands the library
-    the complete array (the short last slice's padding stays beyond T)."""
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_ingest_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert all(ok for _, ok in res), res
+    assert all(r[1] for r in res), res
+    assert sum(r[2] for r in res) > 0
+
+
+def test_exchange_plan_properties():
+    rng = np.random.default_rng(9)
+    for world in (1, 2, 3, 8):
+        for nb in (1, 5, 64, 525):
+            hists = rng.integers(0, 50, size=(world, nb))
+            hists[:, rng.integers(0, nb)] += 400                      # one heavy digit
+            if nb > 3:
+                hists[:, 2] = 0                                       # an empty digit
+            plan = sharding.exchange_plan(hists)
+
+            class _Db:
+                offsets = np.array([0, int(hists.sum())])
+            _check_plan(_Db, world, hists, plan)
+    z = sharding.exchange_plan(np.zeros((2, 4), dtype=np.int64))
+    assert z["count"].tolist() == [0, 0] and z["total"] == 0

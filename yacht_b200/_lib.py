@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketch_blocks", "ygpu_load_sketches_device",
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
-    "ygpu_hyp_test", "ygpu_index_partial", "ygpu_index_stream_copy", "ygpu_index_finish",
+    "ygpu_hyp_test",
     "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
     "ygpu_comm_get_unique_id", "ygpu_comm_init", "ygpu_comm_destroy", "ygpu_load_sketches_sharded", "ygpu_load_sketches_sharded_device",
     "ygpu_train_step_sharded", "ygpu_upload_finish_sharded",
@@ -112,9 +112,6 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_upload_begin.argtypes = [vp]
     lib.ygpu_upload_block.argtypes = [vp, u32, vp, u64]
     lib.ygpu_upload_finish.argtypes = [vp, vp, u32, vp, u32]
-    lib.ygpu_index_partial.argtypes = [vp, u32, u32, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
-    lib.ygpu_index_stream_copy.argtypes = [vp, vp, vp]
-    lib.ygpu_index_finish.argtypes = [vp, vp, vp, u64, u32, u32, ctypes.POINTER(IndexStats)]
     lib.ygpu_pairwise_flag_device.argtypes = [vp, ctypes.c_double, u32, u32, ctypes.POINTER(u64)]
     lib.ygpu_pairs_copy.argtypes = [vp, vp, ctypes.c_int]
     lib.ygpu_mark.argtypes = [vp, ctypes.c_int]
@@ -219,23 +216,6 @@ class GpuContext:
         return st.as_dict()
 
     # -- hash-range sharded build (multi-GPU; the exchange between the calls is the caller's) ------------
-    def index_partial(self, part: int, nparts: int) -> Tuple[dict, int]:
-        """This rank's share of the hash space -> (partial statistics, entries of its group stream)."""
-        st = IndexStats()
-        n = ctypes.c_uint64(0)
-        self._check(self.lib.ygpu_index_partial(self.h, int(part), int(nparts), ctypes.byref(st), ctypes.byref(n)), "ygpu_index_partial")
-        return st.as_dict(), int(n.value)
-
-    def index_stream_copy(self, d_gid_ptr: int, d_rem_ptr: int) -> None:
-        self._check(self.lib.ygpu_index_stream_copy(self.h, d_gid_ptr, d_rem_ptr), "ygpu_index_stream_copy")
-
-    def index_finish(self, d_gid_ptr: int, d_rem_ptr: int, n_entries: int, row_begin: int, row_end: int, total: dict) -> None:
-        st = IndexStats()
-        for k, _ in IndexStats._fields_:
-            setattr(st, k, int(total.get(k, 0)))
-        self._check(self.lib.ygpu_index_finish(self.h, d_gid_ptr, d_rem_ptr, int(n_entries), int(row_begin), int(row_end), ctypes.byref(st)),
-                    "ygpu_index_finish")
-
     def pairwise_flag(self, threshold: float, row_begin: int = 0, row_end: Optional[int] = None) -> np.ndarray:
         """Flagged ordered pairs (structured array i, j, count), sorted by (i, j)."""
         if row_end is None:

@@ -62,7 +62,6 @@ struct ygpu_ctx {
     int big_buckets = 1;            // option: 0 = any oversized bucket sends the whole database to the general path
     uint32_t msd_big_buckets = 0;   // oversized buckets of the last build
     uint16_t* d_st_rem = nullptr;   // [T] group stream of a hash-range sharded build: members of the same group that follow
-    uint64_t stream_entries = 0;    //     entries of the stream of the last ygpu_index_partial (genome ids are in d_post)
     int index_path = 1;             // 1: MSD partition when the input qualifies, 0: always the general sort path
     int msd_fallbacks = 0;
     int last_index_path = 0;        // which path built the current index

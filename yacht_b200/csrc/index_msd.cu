@@ -7,22 +7,28 @@
 // (ascending), and for every genome the list of "postings that follow me".  So instead of sorting
 // T (hash, genome) pairs by all 55 significant bits (7 radix passes over 12-byte pairs), this path
 //   1. packs (hash low bits, genome id) into ONE 64-bit word -- the leading d1 hash bits are implied
-//      by the level-1 bucket, so 55 - d1 + ceil(log2 N) bits fit --
-//   2. partitions the words by the leading d1 and then the next d2 hash bits into ~T/1500 final
-//      buckets (two coalesced scatter passes of 8 bytes per element, tile-staged in shared memory),
-//   3. groups equal hashes inside each bucket in shared memory (k2_group: a counting filter over the next 11
-//      hash bits drops the ~70 % of words that are alone in their sub-bucket, the rest are scanned densely; no
-//      ordering of singleton hashes is ever computed), orders only the members of shared groups by genome id, and
-//      emits compact postings + per-genome work items -- or, when the build is sharded by hash range across GPUs,
-//      a compact group stream that the ranks exchange (ygpu_index_partial / _finish).
-// Algorithmic HBM traffic: 8T (histogram) + 12T + 8T (scatter 1) + 8T (histogram 2) + 16T (scatter 2)
-// + 8T (bucket read) + O(P) outputs ~= 60 bytes per hash, against ~176 for the 7-pass pair sort.
+//      by the level-1 bucket, so 55 - d1 + ceil(log2 N) bits fit; the genome id of a hash slot is derived from
+//      the CSR offsets (a few genome boundaries per tile), not read from a per-slot array --
+//   2. partitions the words by the leading d1 and then the next d2 hash bits into ~T/800 final
+//      buckets (two scatter passes of 8 bytes per element; tiles arrive through the copy engine --
+//      cp.async.bulk + mbarrier, double-buffered -- and are reordered in the buffer they arrived in),
+//   3. groups equal hashes inside each bucket in shared memory (k2_group2; k2_group for buckets or key widths it does
+//      not take: a counting filter over the next 11 hash bits drops the words that are alone in their sub-bucket,
+//      the rest are scanned densely; no ordering of singleton hashes is ever computed), orders only the members of
+//      shared groups by genome id, and emits compact postings + per-genome work items.
+// Algorithmic HBM traffic: 8T (histogram) + 8T + 8T (scatter 1) + 8T (histogram 2) + 16T (scatter 2)
+// + 8T (bucket read) + O(P) outputs ~= 56 bytes per hash, against ~176 for the 7-pass pair sort.
 //
 // Skew: a final bucket that does not fit shared memory (a hash held by thousands of genomes) leaves this path
-// alone -- its words are sorted device-wide and grouped by neighbour comparison (k2_big_*).  The general path
-// (yacht_gpu.cu, CUB radix sort of all pairs) remains for inputs that do not pack (hash width + genome-id width),
-// for more than 4096 oversized buckets and for sharded builds that meet one.  The choice is made per database
-// from the measured bucket histogram -- "chosen by measured posting-list skew".
+// alone -- its words are sorted device-wide (in chunks of buckets) and grouped by neighbour comparison (k2_big_*).
+// The general path (yacht_gpu.cu, library radix sort of all pairs) remains only for inputs that do not pack (hash width +
+// genome-id width).  The choice is made per database from the measured bucket histogram -- "chosen by measured
+// posting-list skew".
+//
+// Across GPUs (ygpu_train_step_sharded, end of this file) every rank partitions only its own sketches and the level-1
+// scatter stores each word straight into the buffer of the rank that owns its hash range (NVLink), the grouping kernel
+// stores each bucket's groups into every rank's stream buffer: the exchanges are part of the kernels.
+// The run path (`yacht run`) probes the same partition bucket by bucket (run_buckets.cuh).
 #include "common.cuh"
 
 #include <cub/cub.cuh>
@@ -447,8 +453,8 @@ constexpr int BK_CAP = 3072;        // max words of a final bucket (shared-memor
 //      the member's work item, appended to the member's per-genome list.  The returning atomicAdd on the
 //      per-genome counter is consumed one bucket later (software pipelining), so its latency never sits
 //      between two barriers.
-//   F' (stream mode, hash-range sharded build across GPUs) instead writes the staged groups to a compact stream
-//      (genome id, members that follow); ranks all-gather their streams and k2_items builds the work lists.
+// This is the GENERAL grouping kernel: buckets of up to BK_CAP words and remaining-key widths beyond 32 bits.  The common
+// case runs in k2_group2 (below), which is leaner; GroupArgs::m_lo tells this kernel which buckets that one already took.
 constexpr int GK_THREADS = 256;
 constexpr int GK_SUBBITS = 11;
 constexpr int GK_NSUB = 1 << GK_SUBBITS;            // 2048 = 8 counters per thread
@@ -469,7 +475,7 @@ struct GroupArgs {
     const uint64_t* row_off;     // [n] start of genome g's work list (= sketch offsets)
     unsigned long long* row_cnt; // [n] items appended so far
     uint64_t* row_items;         // [T]
-    // stream mode (hash-range sharded build): the groups leave as a compact stream instead of work items
+    // sharded build (k2_group2<STREAM>): the groups leave as a compact stream instead of work items
     uint32_t* st_gid;            // genome ids, group by group, ascending inside a group
     unsigned short* st_rem;      // members of the same group that follow
     unsigned long long* scal;
@@ -497,7 +503,7 @@ struct GroupSmem {
 
 // `staged`: this bucket's words were prefetched into shared memory (cp.async issued during the previous bucket's
 // phase E, into the start2|SUB2 region, dead by then); bb_next / m_next: the bucket to prefetch during this one.
-template <int ITEMS, bool STREAM>
+template <int ITEMS>
 __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t bb, const uint32_t m, const GroupSmem& sm,
                                              uint32_t* s_pcur, uint32_t* s_gpos, GroupStats& st, GroupPending& pd,
                                              const bool staged, const uint32_t bb_next, const uint32_t m_next) {
@@ -620,10 +626,6 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + k * GK_THREADS * 8), "l"(nsrc + k * GK_THREADS) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (STREAM && tid == 0) {        // claim this bucket's slice of the stream (the cursor is final: barrier above)
-        const uint32_t np0 = *s_pcur;
-        *s_gpos = np0 ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np0) : 0u;
-    }
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         if (lr[k]) {
@@ -636,14 +638,6 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     __syncthreads();
     // ---- F: postings + work items -------------------------------------------------------------------------------
     const uint32_t np = *s_pcur;
-    if (STREAM) {
-        const uint32_t gpos = *s_gpos;
-        for (uint32_t x = tid; x < np; x += GK_THREADS) {
-            a.st_gid[(uint64_t)gpos + x] = stg_g[x];
-            a.st_rem[(uint64_t)gpos + x] = (unsigned short)(stg_rem[x] & 0x7fffu);
-        }
-        return;
-    }
     for (uint32_t x = tid; x < np; x += GK_THREADS) {
         const uint32_t g = stg_g[x];
         const uint32_t rr = stg_rem[x];
@@ -666,7 +660,6 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
     }
 }
 
-template <bool STREAM>
 __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GroupSmem sm;
@@ -695,8 +688,8 @@ __global__ void __launch_bounds__(GK_THREADS, 4) k2_group(const GroupArgs a) {
         uint32_t bbn = 0, mn = 0;
         if (bn < a.b_hi) { bbn = a.base[bn]; mn = a.base[bn + 1] - bbn; }
         if (m > a.m_lo && m <= BK_CAP) {    // uniform per CTA (larger buckets: k2_big_*, below)
-            if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, staged, bbn, mn);
-            else group_bucket<GK_SLOW, STREAM>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, false, bbn, mn);
+            if (m <= GK_FAST * GK_THREADS) group_bucket<GK_FAST>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, staged, bbn, mn);
+            else group_bucket<GK_SLOW>(a, bb, m, sm, &s_pcur[par], &s_gpos[par], st, pd, false, bbn, mn);
             par ^= 1;
             staged = mn > a.m_lo && mn <= GK_FAST * GK_THREADS;
         } else {
@@ -1067,29 +1060,6 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
     }
 }
 
-// group stream -> work items of the rows [row_begin, row_end): one thread per stream entry (the fused phase F of
-// k2_group does this per bucket when the build is not sharded)
-__global__ void __launch_bounds__(256) k2_items(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem, uint64_t n_entries,
-                                                uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_off,
-                                                unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items) {
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_entries; x += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = rem[x];
-        if (!r) continue;
-        const uint32_t g = gid[x];
-        if (g < row_begin || g >= row_end) continue;
-        uint64_t item;
-        if (can_inline && r <= 3) {
-            item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
-            if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
-            if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
-        } else {
-            item = ((x + 1) << 32) | ((uint64_t)r << 2);
-        }
-        const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-        row_items[row_off[g] + slot] = item;
-    }
-}
-
 // sharded build: the stream is N regions (one per producing rank) of `cap` slots each, region q holding lens[q] entries
 __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem,
                                                         const unsigned long long* __restrict__ lens, int n_regions, uint64_t cap,
@@ -1231,10 +1201,9 @@ int bitlen(uint64_t v) {
     return b;
 }
 
-// part / nparts: this call covers the `part`-th share of the hash space (level-1 digits split by hash count);
-// stream: leave the groups as a compact stream (d_post = genome ids, d_st_rem = members that follow) instead of
-// building work lists.  *used = 0 when the input does not qualify for this path.
-int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint32_t nparts, bool stream, bool partition_only = false) {
+// Partition + grouping of the resident sketches on one GPU.  partition_only: stop after the partition (the run path probes
+// it, run_buckets.cuh).  *used = 0 when the input does not qualify for this path.
+int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, bool partition_only = false) {
     *used = 0;
     ctx->part_valid = false;
     const uint64_t T = ctx->T;
@@ -1292,32 +1261,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[1], st));
     k2_prep1<<<1, 1024, 0, st>>>(hist1, p.nb1, base1, tile_start, cursor, ctx->d_scalars);
     YG_CUDA(ctx, cudaGetLastError());
-    uint64_t T_mine = T;
-    if (nparts > 1) {
-        // this rank's share of the hash space: level-1 digits [dlo, dhi), split by hash count
-        std::vector<uint32_t> h(p.nb1);
-        YG_CUDA(ctx, cudaMemcpyAsync(h.data(), hist1, (size_t)p.nb1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        YG_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<uint32_t> cut(nparts + 1, p.nb1);
-        cut[0] = 0;
-        uint64_t acc = 0;
-        uint32_t k = 1;
-        for (uint32_t d = 0; d < p.nb1 && k < nparts; d++) {
-            acc += h[d];
-            while (k < nparts && acc * nparts >= (uint64_t)k * T) cut[k++] = d + 1;
-        }
-        p.dlo = cut[part]; p.dhi = cut[part + 1];
-        uint64_t tiles = 0;
-        T_mine = 0;
-        p.unit_lo = 0; p.unit_hi = 0;
-        for (uint32_t d = 0; d < p.nb1; d++) {
-            if (d == p.dlo) p.unit_lo = (uint32_t)tiles;
-            tiles += ((uint64_t)h[d] + SC_TILE - 1) / SC_TILE;
-            if (d >= p.dlo && d < p.dhi) T_mine += h[d];
-            if (d + 1 == p.dhi) p.unit_hi = (uint32_t)tiles;
-        }
-        if (p.dlo >= p.dhi) { p.unit_lo = 0; p.unit_hi = 0; }
-    }
+    const uint64_t T_mine = T;
     ScatterArgs a{};
     a.hashes = ctx->d_hashes; a.offsets = ctx->d_offsets; a.n = n; a.out_ent = ctx->d_ent1; a.cursor = cursor;
     a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2;
@@ -1387,7 +1331,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)maxb[1] : (uint64_t)maxb[0];   // (level-1 maximum: over all digits, a safe bound)
     const uint32_t nbuckets = d2 ? p.nfb : p.nb1;
-    if (nparts == 1) {
+    {
         if (!ctx->part_state) ctx->part_state = new MsdPartState();
         MsdPartState* ps = (MsdPartState*)ctx->part_state;
         ps->p = p; ps->sbits = sbits; ps->rest_bits = rest_bits; ps->final_ent = final_ent; ps->final_base = final_base;
@@ -1407,7 +1351,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
     if (largest > BK_CAP) {
         // some final buckets do not fit shared memory.  Sharded builds and option big_buckets = 0 leave the whole
         // database to the general (sort) path; otherwise only those buckets take the k2_big_* route.
-        bool ok = !stream && ctx->big_buckets != 0;
+        bool ok = ctx->big_buckets != 0;
         if (ok) {
             YG_CHECK(dev_alloc(ctx, &ctx->d_big_list, (uint64_t)nbuckets));
             YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_scalars[SCM_STREAM], 0, sizeof(unsigned long long), st));
@@ -1439,13 +1383,9 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
 
     // ---- buckets -> postings + per-genome work lists (or the group stream) ------------------------------
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, T + N_big));
-    if (stream) {
-        YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, T));
-    } else {
-        YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
-        YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
-        YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-    }
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
     {
         GroupArgs g{};
         g.ent = final_ent; g.base = final_base; g.gb = p.gb;
@@ -1461,7 +1401,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         const uint64_t nbk = g.b_hi > g.b_lo ? g.b_hi - g.b_lo : 0;
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[7], st));
         // the common case (remaining hash bits fit 32, bucket <= G2_MAXM words) goes to k2_group2; k2_group takes the rest
-        const bool fast2 = !stream && rest_bits <= 32 && ctx->group_kernel != 1;
+        const bool fast2 = rest_bits <= 32 && ctx->group_kernel != 1;
         g.m_lo = 0;
         if (fast2 && nbk) {
             const size_t smem2 = sizeof(G2Smem);
@@ -1476,7 +1416,7 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         }
         if (nbk && (!fast2 || largest > G2_MAXM)) {
             const size_t smem = (size_t)GK_NSUB * 4 + (size_t)BK_CAP * 8 + (size_t)(GK_NSUB + 8) * 2 + (size_t)BK_CAP * 4;
-            auto kern = stream ? k2_group<true> : k2_group<false>;
+            auto kern = k2_group;
             YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;
             YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GK_THREADS, smem));
@@ -1548,14 +1488,9 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, uint32_t part, uint
         if (d2) { ctx->tm.ms_hist2 += el(3, 4); ctx->tm.ms_scatter2 += el(5, 6); }
         ctx->tm.ms_group += el(7, 8);
     }
-    if (stream) {
-        if (sc[SCM_STREAM] != P) return ygpu_fail(ctx, YGPU_ERR_CUDA, "group stream holds %llu entries, expected %llu", sc[SCM_STREAM], (unsigned long long)P);
-        ctx->stream_entries = P;
-    } else {
-        ctx->P = P;
-        ctx->n_items = I;
-        ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])
-    }
+    ctx->P = P;
+    ctx->n_items = I;
+    ctx->d_row_begin = ctx->d_offsets;          // work list of row g: row_items[offsets[g] .. + row_cnt[g])
     S->n_hashes = T_mine;
     S->n_distinct = sc[SC_HEADS];
     S->n_singleton = sc[SC_SINGLE];
@@ -1606,7 +1541,7 @@ int ygpu_run_counts_buckets(ygpu_ctx* ctx, const uint64_t* d_sample, uint64_t n_
         ygpu_index_stats S{};
         int u = 0;
         YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
-        YG_CHECK(msd_build(ctx, &S, &u, 0, 1, false, /*partition_only=*/true));
+        YG_CHECK(msd_build(ctx, &S, &u, /*partition_only=*/true));
         if (!u || !ctx->part_valid) return 0;
         ctx->indexed = false;           // the partition buffers are shared with the train index build: that index is gone
     }
@@ -1697,87 +1632,11 @@ int ygpu_run_counts_buckets(ygpu_ctx* ctx, const uint64_t* d_sample, uint64_t n_
 
 int ygpu_build_index_msd(ygpu_ctx* ctx, ygpu_index_stats* S, int* used) {
     const uint64_t T = ctx->T;
-    const int rc = msd_build(ctx, S, used, 0, 1, false);
+    const int rc = msd_build(ctx, S, used);
     S->n_hashes = T;
     return rc;
 }
 
-static uint32_t max_sketch_of(ygpu_ctx* ctx) {
-    std::vector<uint32_t> sz(ctx->n);
-    if (ctx->n) cudaMemcpy(sz.data(), ctx->d_sizes, (size_t)ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    uint32_t mx = 0;
-    for (uint32_t v : sz) mx = std::max(mx, v);
-    return mx;
-}
-
-// ---- hash-range sharded build (one rank per GPU; the exchange itself is the caller's: NCCL all-gather) -------
-extern "C" int ygpu_index_partial(ygpu_ctx* ctx, uint32_t part, uint32_t nparts, ygpu_index_stats* stats, uint64_t* n_entries) {
-    if (!ctx || !stats || !n_entries || nparts == 0 || part >= nparts) return YGPU_ERR_ARG;
-    if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_partial: no sketches loaded");
-    YG_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->indexed = false; ctx->row_work_valid = false; ctx->P = 0; ctx->n_items = 0; ctx->stream_entries = 0;
-    *n_entries = 0;
-    ygpu_index_stats S{};
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), ctx->stream));
-    int used = 0;
-    YG_CHECK(msd_build(ctx, &S, &used, part, nparts, true));
-    if (!used) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_partial: this database does not qualify for the partition path (use ygpu_build_index)");
-    S.index_path = 1;
-    *stats = S;
-    *n_entries = ctx->stream_entries;
-    return 0;
-}
-
-extern "C" int ygpu_index_stream_copy(ygpu_ctx* ctx, uint32_t* d_gid_dst, uint16_t* d_rem_dst) {
-    if (!ctx || ((!d_gid_dst || !d_rem_dst) && ctx->stream_entries)) return YGPU_ERR_ARG;
-    if (!ctx->stream_entries) return 0;
-    YG_CUDA(ctx, cudaSetDevice(ctx->device));
-    YG_CUDA(ctx, cudaMemcpyAsync(d_gid_dst, ctx->d_post, ctx->stream_entries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    YG_CUDA(ctx, cudaMemcpyAsync(d_rem_dst, ctx->d_st_rem, ctx->stream_entries * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    YG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return 0;
-}
-
-extern "C" int ygpu_index_finish(ygpu_ctx* ctx, const uint32_t* d_gid, const uint16_t* d_rem, uint64_t n_entries, uint32_t row_begin,
-                                 uint32_t row_end, const ygpu_index_stats* total) {
-    if (!ctx || !total || (n_entries && (!d_gid || !d_rem))) return YGPU_ERR_ARG;
-    if (!ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "index_finish: no sketches loaded");
-    if (row_begin > row_end || row_end > ctx->n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad row range [%u,%u) of %u", row_begin, row_end, ctx->n);
-    if (n_entries >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "group stream of %llu entries >= 2^32 not supported", (unsigned long long)n_entries);
-    YG_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const uint64_t T = ctx->T;
-    const uint32_t n = ctx->n;
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_post, std::max<uint64_t>(T, n_entries + 4)));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, T));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-    if (n_entries) {
-        if (d_gid != ctx->d_post)
-            YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_post, d_gid, n_entries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        const int gb = bitlen(n > 0 ? (uint64_t)n - 1 : 0);
-        k2_items<<<grid_for(ctx, n_entries, 256, 16), 256, 0, st>>>(ctx->d_post, d_rem, n_entries, row_begin, row_end,
-                                                                     gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_offsets, ctx->d_row_cnt, ctx->d_row_items);
-        YG_CUDA(ctx, cudaGetLastError());
-        ctx->tm.n_kernel_launches += 1;
-    }
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->tm.ms_index += elapsed(ctx, 0, 1);
-    ygpu_index_stats S = *total;
-    S.n_hashes = T;
-    S.max_sketch = max_sketch_of(ctx);
-    S.index_path = 1;
-    ctx->stats = S;
-    ctx->P = n_entries;
-    ctx->n_items = S.n_row_items;
-    ctx->d_row_begin = ctx->d_offsets;
-    ctx->row_work_valid = false;
-    ctx->last_index_path = 1;
-    ctx->indexed = true;
-    return 0;
-}
 
 // ============================================================================================================
 // Sharded train step: one rank per GPU, every rank resident with the sketches of ITS genome range only.

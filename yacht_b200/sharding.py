@@ -75,104 +75,42 @@ def all_gather_pairs(local, n_local: int, world: int, device=None, group=None) -
 
 
 def slice_bounds(total: int, world: int) -> np.ndarray:
-    """Equal contiguous slices of the flat hash array (the last one may be short): slice r = [b[r], b[r+1])."""
+    """Equal contiguous slices of a flat array (the last one may be short): slice r = [b[r], b[r+1])."""
     per = (int(total) + world - 1) // world if world else 0
     return np.minimum(np.arange(world + 1, dtype=np.int64) * per, int(total))
 
 
-def load_sketches_sharded(ctx, pinned_slice, offsets: np.ndarray, total: int, rank: int, world: int, device, group=None):
-    """Sharded ingest: every rank copies only ITS slice of the flat hash array from (pinned) host
-    memory over its own PCIe link, the slices are all-gathered over NVLink (NCCL), and the assembled array is
-    handed to the library device-to-device.  `pinned_slice` is a pinned int64 torch tensor holding
-    hashes[b[rank]:b[rank+1]] with b = slice_bounds(total, world).  Returns the assembled device tensor."""
-    import torch
-    import torch.distributed as dist
-
-    per = (int(total) + world - 1) // world
-    full = torch.empty(max(per, 1) * world, dtype=torch.int64, device=device)
-    mine = full[rank * per: (rank + 1) * per]
-    n_mine = int(pinned_slice.numel())
-    if n_mine:
-        mine[:n_mine].copy_(pinned_slice, non_blocking=True)
-    if world > 1:
-        dist.all_gather_into_tensor(full, mine, group=group)
-    d_off = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.uint64).view(np.int64)).to(device, non_blocking=True)
-    _sync(device)                                        # the library works on its own stream
-    ctx.load_sketches_device(full.data_ptr(), d_off.data_ptr(), int(offsets.shape[0]) - 1)
-    return full
-
-
-SUMMED_STATS = ("n_hashes", "n_distinct", "n_singleton", "n_index", "n_postings", "n_increments", "n_row_items", "has_duplicates")
-
-
 def split_rows_by_size(offsets: np.ndarray, nparts: int) -> np.ndarray:
-    """Contiguous row ranges holding nearly equal numbers of sketch hashes (known before any index exists)."""
+    """Contiguous genome ranges holding nearly equal numbers of sketch hashes: the residency of the sharded train step
+    (rank r holds the sketches of genomes [b[r], b[r+1]) and counts / flags those query rows)."""
     sizes = np.diff(np.asarray(offsets).astype(np.int64)).astype(np.float64)
     return split_rows_by_work(sizes, nparts)
 
 
-def _sync(device) -> None:
-    """Order torch's stream against the library's (CUDA devices only; the gloo tests run the same code on CPU tensors)."""
-    import torch
-    if torch.device(device).type == "cuda":
-        torch.cuda.current_stream(device).synchronize()
+# ---- host mirror of the sharded index build's exchange plan (csrc/index_msd.cu: k2s_prep) -------------------------------
+# Every rank histograms the leading hash bits of ITS sketches; the histograms are all-gathered and every rank derives the
+# same plan: which rank owns which level-1 digit, and where in the owner's buffer the words of (source rank, digit) lie.
+# The level-1 scatter then stores every word straight into its owner's buffer.  The device computes this in one CTA; this
+# numpy version documents the rule and is what the CPU tests (gloo, world size 2) check.
+def exchange_plan(hist_all: np.ndarray) -> dict:
+    """hist_all[r, d] = hashes of rank r's sketches with leading digit d.  Returns
+    owner[d]; start[r_src, d] = first slot, in owner[d]'s buffer, of the words (r_src, d); count[o] = words rank o owns."""
+    hist_all = np.asarray(hist_all, dtype=np.int64)
+    nranks, nb = hist_all.shape
+    g = hist_all.sum(axis=0)
+    total = int(g.sum())
+    ex = np.concatenate([[0], np.cumsum(g)[:-1]])                      # hashes before digit d
+    owner = np.minimum(nranks - 1, (ex * nranks) // max(total, 1)) if total else np.zeros(nb, dtype=np.int64)
+    own_start = np.zeros(nranks, dtype=np.int64)
+    for d in range(nb):
+        if d == 0 or owner[d] != owner[d - 1]:
+            own_start[owner[d]] = ex[d]
+    pre = np.concatenate([np.zeros((1, nb), dtype=np.int64), np.cumsum(hist_all, axis=0)[:-1]], axis=0)   # words of lower ranks
+    start = (ex - own_start[owner])[None, :] + pre
+    count = np.array([int(g[owner == o].sum()) for o in range(nranks)], dtype=np.int64)
+    return dict(owner=owner.astype(np.int64), start=start, count=count, total=total)
 
 
-_stream_buffers = {}     # (device index, world) -> (gid, rem) device tensors reused across builds
-
-
-def _stream_buffer(device, world: int, m: int):
-    import torch
-    key = (str(device), world)
-    buf = _stream_buffers.get(key)
-    if buf is None or buf[0].numel() < world * m:
-        cap = world * (m + m // 16 + 1024)
-        buf = (torch.zeros(cap, dtype=torch.int32, device=device), torch.zeros(cap, dtype=torch.int16, device=device))
-        _stream_buffers[key] = buf
-    return buf[0][: world * m], buf[1][: world * m]
-
-
-def build_index_sharded(ctx, offsets: np.ndarray, rank: int, world: int, device, group=None, bounds: Optional[np.ndarray] = None):
-    """Index build split by hash range across the ranks (include/yacht_gpu.h: ygpu_index_partial / _finish).
-
-    Every rank holds all sketches.  Rank r partitions and groups only its share of the hash space, the ranks
-    all-gather their group streams over NCCL (padded to the longest; padding entries carry follow-count 0 and
-    are ignored), and each rank builds the work lists of its own query rows (`bounds`: row ranges per rank,
-    default split_rows_by_size(offsets, world)).  Returns (row_begin, row_end, total statistics), or None when
-    the database does not qualify (the caller then runs ctx.build_index())."""
-    import torch
-    import torch.distributed as dist
-    from ._lib import YgpuError
-
-    try:
-        st, n_r = ctx.index_partial(rank, world)
-        ok = 1
-    except YgpuError:
-        st, n_r, ok = {k: 0 for k in SUMMED_STATS}, 0, 0
-    head = torch.tensor([ok, n_r] + [int(st[k]) for k in SUMMED_STATS], dtype=torch.int64, device=device)
-    if world > 1:
-        allh = torch.empty(world * head.numel(), dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(allh, head, group=group)
-        allh = allh.view(world, -1).cpu()
-    else:
-        allh = head.view(1, -1).cpu()
-    if int(allh[:, 0].min()) == 0:
-        return None
-    m = max(int(allh[:, 1].max()), 1)
-    total = {k: int(allh[:, 2 + i].sum()) for i, k in enumerate(SUMMED_STATS)}
-    total["has_duplicates"] = 1 if total["has_duplicates"] else 0
-    gid, rem = _stream_buffer(device, world, m)
-    mine_g, mine_r = gid[rank * m: (rank + 1) * m], rem[rank * m: (rank + 1) * m]
-    if n_r < m:                                            # padding of this rank's slice: follow-count 0 = ignored
-        mine_r[n_r:].zero_()
-    _sync(device)                                          # the library writes on its own stream
-    ctx.index_stream_copy(mine_g.data_ptr(), mine_r.data_ptr())
-    if world > 1:
-        dist.all_gather_into_tensor(gid, mine_g, group=group)
-        dist.all_gather_into_tensor(rem.view(torch.uint8), mine_r.view(torch.uint8), group=group)   # NCCL has no int16
-        _sync(device)
-    if bounds is None:
-        bounds = split_rows_by_size(offsets, world)
-    rb, re = int(bounds[rank]), int(bounds[rank + 1])
-    ctx.index_finish(gid.data_ptr(), rem.data_ptr(), world * m, rb, re, total)
-    return rb, re, total
+def exchange_capacity(total: int, nranks: int, nb: int) -> int:
+    """Words a rank's exchange buffer holds (ygpu_train_step_sharded): its share plus the digit granularity of the split."""
+    return total // nranks + 2 * (total // max(nb, 1)) + 3 * 4096

@@ -66,6 +66,26 @@ def test_sharded_step_matches_oracle(nranks):
     _check(db, nranks, THR)
 
 
+@pytest.mark.parametrize("nranks", [1, 2, 8])
+def test_sharded_step_larger_groups(nranks):
+    """Hashes held by 5 .. 60 genomes: groups of up to 16 members travel as self-contained work items to the owners of
+    the query rows, larger ones through the posting stream every rank receives."""
+    if _lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    rng = np.random.default_rng(77)
+    base = synth.make_reference_db(5000, 31, mean_size=3000, sd_size=600)
+    parts = [base.sketch(g) for g in range(base.n)]
+    for size in (5, 9, 16, 17, 33, 60):
+        for rep in range(6):
+            members = rng.choice(base.n, size=size, replace=False)
+            common = rng.integers(0, synth.MAX_HASH, size=int(rng.integers(20, 200)), dtype=np.uint64)
+            for m in members:
+                parts[m] = np.unique(np.concatenate([parts[m], common]))
+    db = synth.from_sketches(parts)
+    _check(db, nranks, 0.01)
+    _check(db, nranks, THR)
+
+
 @pytest.mark.parametrize("nranks", [1, 2])
 def test_sharded_step_edge_rows(nranks):
     if _lib.device_count() < nranks:

@@ -70,6 +70,7 @@ struct ygpu_ctx {
     unsigned long long last_count_overflow_rows = 0;
     uint32_t* d_ovf_rows = nullptr; // rows the warp kernel deferred to the dense kernel
     uint32_t* d_tc = nullptr;       // [n] smallest shared-hash count that passes the containment test of genome g
+    bool skip_pair_sort = false;    // sharded step: the pair lists of all ranks are ordered once, after the gather
     int count_thresholds = 1;       // test hook: 0 = evaluate the fp64 expression per pair inside the count kernel
     ygpu_index_stats stats = {};
 
@@ -104,6 +105,14 @@ struct ygpu_ctx {
     void* sh_peer_ent1[YG_MAX_RANKS] = {};  // peers' level-1 exchange buffers (d_ent1)
     void* sh_peer_gid[YG_MAX_RANKS] = {};   // peers' group-stream buffers (d_post / d_st_rem)
     void* sh_peer_rem[YG_MAX_RANKS] = {};
+    void* sh_peer_item[YG_MAX_RANKS] = {};  // peers' item inboxes (d_inbox_item / d_inbox_row)
+    void* sh_peer_row[YG_MAX_RANKS] = {};
+    uint64_t* d_inbox_item = nullptr;       // [nranks][sh_cap] ready-made work items for this rank's rows, one region per sending rank
+    uint32_t* d_inbox_row = nullptr;        // ... and their query rows
+    void* sh_shared_item = nullptr;
+    void* sh_shared_row = nullptr;
+    uint32_t sh_row_bounds[YG_MAX_RANKS + 1] = {};   // rank q holds / counts the genomes [sh_row_bounds[q], sh_row_bounds[q + 1])
+    uint64_t row_items_cap = 0;
     void* sh_shared_ent1 = nullptr;         // which allocations the peer pointers above refer to (re-shared when they move)
     void* sh_shared_gid = nullptr;
     void* sh_shared_rem = nullptr;

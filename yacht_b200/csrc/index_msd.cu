@@ -486,6 +486,14 @@ struct GroupArgs {
     uint64_t region_base;              // first stream entry of this rank's region in every rank's buffer
     uint32_t* peer_gid[YG_MAX_RANKS];
     unsigned short* peer_rem[YG_MAX_RANKS];
+    // ... except that the work items of small groups (<= IG_MAXL members: every database without extreme skew) travel alone,
+    // self-contained (the following genome ids are inside the item), and only to the rank that owns the query row
+    uint32_t row_bounds[YG_MAX_RANKS + 1];   // rank q owns query rows [row_bounds[q], row_bounds[q + 1])
+    uint64_t* peer_item[YG_MAX_RANKS];       // rank q's item inbox; this rank writes region [rank * icap, (rank + 1) * icap)
+    uint32_t* peer_row[YG_MAX_RANKS];        // ... the query row of every item
+    uint64_t icap;
+    uint64_t item_region;                    // rank * icap
+    unsigned long long* icursor;             // [n_peers] items this rank has sent to every rank so far (local memory)
 };
 
 struct GroupStats { uint32_t heads, single, dups; unsigned long long w; };   // postings = T - singles, items = postings - shared groups
@@ -726,6 +734,7 @@ constexpr int G2_THREADS = 256;
 constexpr int G2_WIN = 1024;                      // words of the 16-byte aligned window copied per bucket
 constexpr uint32_t G2_MAXM = G2_WIN - 2;          // largest bucket this kernel takes
 constexpr int G2_NSUB = 1 << GK_SUBBITS;          // 2048 sub-bucket counters = 8 per thread
+constexpr uint32_t IG_MAXL = 16;                  // sharded build: groups up to this size travel as self-contained items
 
 struct __align__(16) G2Smem {
     uint64_t stage[G2_WIN];                       // the bucket's words (bulk copy target)
@@ -737,6 +746,8 @@ struct __align__(16) G2Smem {
     unsigned short stg_r[G2_WIN];                 // ordered groups: members that follow | 0x8000 posting wanted | 0x4000 hole
     uint32_t wsum[G2_THREADS / 32];
     uint32_t next[2][2];                          // [parity]{first word, words} of the bucket after this one (words = 0: none)
+    uint32_t dcnt[YG_MAX_RANKS];                  // STREAM: items of this bucket per destination rank
+    uint32_t dbase[YG_MAX_RANKS];                 // STREAM: ... and where they start in that rank's inbox
     uint64_t mbar;
 };
 
@@ -890,7 +901,7 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             }
             const uint32_t pos = lo + rall;
             sm.stg_g[pos] = (uint32_t)wq;
-            sm.stg_r[pos] = L >= 2 ? (unsigned short)((L - 1 - rank) | ((!can_inline || L > 4) ? 0x8000u : 0u)) : (unsigned short)0x4000u;
+            sm.stg_r[pos] = L >= 2 ? (unsigned short)((L - 1 - rank) | ((!can_inline || L > (STREAM ? IG_MAXL : 4u)) ? 0x8000u : 0u)) : (unsigned short)0x4000u;
             n_heads += rank == 0;
             n_single += L == 1;
             n_dups += dup;
@@ -898,42 +909,85 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
         }
         __syncthreads();
         if (STREAM) {
-            // ---- F': the groups, holes squeezed out, go to every rank's stream buffer (NVLink stores for the peers) -----
-            uint32_t* cg = reinterpret_cast<uint32_t*>(sm.cand);                     // the candidate array is dead: compact copy
-            unsigned short* cr = reinterpret_cast<unsigned short*>(cg + G2_WIN);
-            uint32_t np = 0;
-            for (uint32_t x0 = 0; x0 < ncand; x0 += G2_THREADS) {
-                const uint32_t x = x0 + tid;
-                const uint32_t rr = x < ncand ? sm.stg_r[x] : 0x4000u;
-                const bool member = !(rr & 0x4000u);
-                const uint32_t bal = __ballot_sync(0xffffffffu, member);
-                if (lane == 0) sm.wsum[warp] = __popc(bal);
-                __syncthreads();
-                uint32_t off = np, tot = 0;
-#pragma unroll
-                for (int w = 0; w < G2_THREADS / 32; w++) {
-                    const uint32_t c = sm.wsum[w];
-                    off += (w < (int)warp) ? c : 0u;
-                    tot += c;
-                }
-                if (member) {
-                    const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
-                    cg[pos] = sm.stg_g[x];
-                    cr[pos] = (unsigned short)(rr & 0x3fffu);
-                }
-                np += tot;
-                __syncthreads();
-            }
-            if (tid == 0) sm.wsum[0] = np ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np) : 0u;
+            // ---- F' (sharded build): the groups leave this rank --------------------------------------------------------------
+            // (1) small groups: every non-last member becomes ceil(followers / 3) self-contained items, stored straight into
+            //     the inbox of the rank that owns the member's query row (NVLink for peers); slots are claimed once per
+            //     (bucket, destination) from this rank's cursors
+            if (tid < (uint32_t)a.n_peers) sm.dcnt[tid] = 0;
             __syncthreads();
-            const uint64_t gpos = a.region_base + sm.wsum[0];
-            for (int q = 0; q < a.n_peers; q++) {
-                uint32_t* dg = a.peer_gid[q] + gpos;
-                unsigned short* dr = a.peer_rem[q] + gpos;
-                for (uint32_t i = tid; i < np; i += G2_THREADS) { dg[i] = cg[i]; dr[i] = cr[i]; }
+            bool any_big = false;
+            for (uint32_t x = tid; x < ncand; x += G2_THREADS) {
+                const uint32_t rr = sm.stg_r[x];
+                sm.ext[x] = 0xFFFFFFFFu;
+                if (rr & 0x4000u) continue;
+                if (rr & 0x8000u) { any_big = true; continue; }
+                const uint32_t rem = rr & 0x3fffu;
+                if (!rem) continue;
+                const uint32_t g = sm.stg_g[x];
+                uint32_t dest = 0;
+                for (int q = 1; q < a.n_peers; q++) dest += g >= a.row_bounds[q] ? 1u : 0u;
+                sm.ext[x] = atomicAdd(&sm.dcnt[dest], (rem + 2u) / 3u) | (dest << 24);
+            }
+            any_big = __syncthreads_or(any_big);
+            if (tid < (uint32_t)a.n_peers) {
+                const uint32_t c = sm.dcnt[tid];
+                sm.dbase[tid] = c ? (uint32_t)atomicAdd(&a.icursor[tid], (unsigned long long)c) : 0u;
+            }
+            __syncthreads();
+            for (uint32_t x = tid; x < ncand; x += G2_THREADS) {
+                const uint32_t ex = sm.ext[x];
+                if (ex == 0xFFFFFFFFu) continue;
+                const uint32_t dest = ex >> 24, rem = sm.stg_r[x] & 0x3fffu, g = sm.stg_g[x];
+                uint64_t pos = (uint64_t)sm.dbase[dest] + (ex & 0xFFFFFFu);
+                uint64_t* di = a.peer_item[dest] + a.item_region;
+                uint32_t* dr = a.peer_row[dest] + a.item_region;
+                for (uint32_t k = 0; k < rem; k += 3, pos++) {
+                    const uint32_t c = min(3u, rem - k);
+                    uint64_t item = (uint64_t)c | ((uint64_t)sm.stg_g[x + 1 + k] << 2);
+                    if (c >= 2) item |= (uint64_t)sm.stg_g[x + 2 + k] << 22;
+                    if (c >= 3) item |= (uint64_t)sm.stg_g[x + 3 + k] << 42;
+                    if (pos < a.icap) { di[pos] = item; dr[pos] = g; }       // (an overflow shows in the cursor; the host checks it)
+                }
+            }
+            // (2) larger groups (rare): their genome ids go, holes squeezed out, to EVERY rank's posting stream; the owners of
+            //     the query rows derive indirect items from it (k2_items_regions)
+            if (any_big) {
+                uint32_t* cg = reinterpret_cast<uint32_t*>(sm.cand);                     // the candidate array is dead: compact copy
+                unsigned short* cr = reinterpret_cast<unsigned short*>(cg + G2_WIN);
+                uint32_t np = 0;
+                for (uint32_t x0 = 0; x0 < ncand; x0 += G2_THREADS) {
+                    const uint32_t x = x0 + tid;
+                    const uint32_t rr = x < ncand ? sm.stg_r[x] : 0x4000u;
+                    const bool member = !(rr & 0x4000u) && (rr & 0x8000u);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, member);
+                    if (lane == 0) sm.wsum[warp] = __popc(bal);
+                    __syncthreads();
+                    uint32_t off = np, tot = 0;
+#pragma unroll
+                    for (int w = 0; w < G2_THREADS / 32; w++) {
+                        const uint32_t c = sm.wsum[w];
+                        off += (w < (int)warp) ? c : 0u;
+                        tot += c;
+                    }
+                    if (member) {
+                        const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
+                        cg[pos] = sm.stg_g[x];
+                        cr[pos] = (unsigned short)(rr & 0x3fffu);
+                    }
+                    np += tot;
+                    __syncthreads();
+                }
+                if (tid == 0) sm.wsum[0] = np ? (uint32_t)atomicAdd(&a.scal[SCM_STREAM], (unsigned long long)np) : 0u;
+                __syncthreads();
+                const uint64_t gpos = a.region_base + sm.wsum[0];
+                for (int q = 0; q < a.n_peers; q++) {
+                    uint32_t* dg = a.peer_gid[q] + gpos;
+                    unsigned short* dr = a.peer_rem[q] + gpos;
+                    for (uint32_t i = tid; i < np; i += G2_THREADS) { dg[i] = cg[i]; dr[i] = cr[i]; }
+                }
             }
             par ^= 1u;
-            continue;          // (wsum[0] is rewritten in the next bucket's phase B, two barriers from here)
+            continue;          // (the next bucket's first barrier separates its phases from this one)
         }
         // ---- F: postings + work items, one thread per ordered slot ------------------------------------------------------
         for (uint32_t x = tid; x < ncand; x += G2_THREADS) {
@@ -1060,11 +1114,35 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
     }
 }
 
-// sharded build: the stream is N regions (one per producing rank) of `cap` slots each, region q holding lens[q] entries
+// sharded build, receiving side.  Work items arrive (a) ready-made in the item inbox: region q holds ilens[q * n_regions + me]
+// items of rank q for rows of this rank; (b) as the posting stream of the larger groups: N regions of `cap` slots, region q holding
+// lens[q] entries, every rank holds all of it and derives the (indirect) items of its own rows.  A row's list has no size
+// bound here (a member of a group of 16 is worth five items), so the lists are laid out by counting first: PLACE = false
+// counts per row, the host scans, PLACE = true fills.
+template <bool PLACE>
+__global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ items, const uint32_t* __restrict__ rows,
+                                                const unsigned long long* __restrict__ ilens, int n_regions, int me, uint64_t icap,
+                                                const uint64_t* __restrict__ row_ptr, unsigned long long* __restrict__ row_cnt,
+                                                uint64_t* __restrict__ row_items, uint64_t items_cap) {
+    for (int q = 0; q < n_regions; q++) {
+        const uint64_t base = (uint64_t)q * icap;
+        const uint64_t len = min((uint64_t)ilens[(size_t)q * n_regions + me], icap);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t g = rows[base + i];
+            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            if (PLACE) {
+                const uint64_t dst = row_ptr[g] + slot;
+                if (dst < items_cap) row_items[dst] = items[base + i];
+            }
+        }
+    }
+}
+
+template <bool PLACE>
 __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem,
                                                         const unsigned long long* __restrict__ lens, int n_regions, uint64_t cap,
-                                                        uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_off,
-                                                        unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items) {
+                                                        uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_ptr,
+                                                        unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items, uint64_t items_cap) {
     for (int q = 0; q < n_regions; q++) {
         const uint64_t base = (uint64_t)q * cap, len = lens[q];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1073,16 +1151,19 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
             if (!r) continue;
             const uint32_t g = gid[x];
             if (g < row_begin || g >= row_end) continue;
-            uint64_t item;
-            if (can_inline && r <= 3) {
-                item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
-                if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
-                if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
-            } else {
-                item = ((x + 1) << 32) | ((uint64_t)r << 2);
-            }
             const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            row_items[row_off[g] + slot] = item;
+            if (PLACE) {
+                uint64_t item;
+                if (can_inline && r <= 3) {
+                    item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
+                    if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
+                    if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
+                } else {
+                    item = ((x + 1) << 32) | ((uint64_t)r << 2);
+                }
+                const uint64_t dst = row_ptr[g] + slot;
+                if (dst < items_cap) row_items[dst] = item;
+            }
         }
     }
 }
@@ -1093,7 +1174,8 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
 // owner's earlier digits) + (words of digit d from lower ranks), so every source rank knows exactly where its words go and
 // the level-1 scatter can store them there directly.  For the digits this rank owns it also lays out level 2 (bucket
 // bases and tile prefix in the GLOBAL digit numbering: foreign digits are simply empty).
-enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_LENS = 8 };   // slots of ctx->d_sh_info (LENS: [nranks])
+// slots of ctx->d_sh_info (LENS: [nranks] posting-stream lengths; ICUR: [nranks] items sent to every rank; ILENS: [nranks][nranks] all-gathered)
+enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_LENS = 8, SHI_ICUR = 64, SHI_ILENS = 96, SHI_WORDS = 512 };
 
 __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hist_all, uint32_t nb, int nranks, int rank, int d2,
                                                  uint32_t* __restrict__ owner, uint32_t* __restrict__ cursor, uint32_t* __restrict__ base,
@@ -1696,7 +1778,20 @@ int ygpu_sharded_finish(ygpu_ctx* ctx, const uint64_t* offsets, uint32_t n, uint
     }
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_max, d_max, 1, true));
     YG_CUDA(ctx, cudaMemcpyAsync(&ctx->maxkey, d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    // every rank's genome range (the query rows it counts): contiguous, in rank order, covering [0, n)
+    const int N = ctx->comm->nranks;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)SHI_WORDS));
+    unsigned long long gb0 = g_begin, all[YG_MAX_RANKS];
+    YG_CUDA(ctx, cudaMemcpyAsync(&ctx->d_sh_info[SHI_ICUR], &gb0, sizeof gb0, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_sh_info[SHI_ICUR], &ctx->d_sh_info[SHI_ILENS], sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaMemcpyAsync(all, &ctx->d_sh_info[SHI_ILENS], (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int q = 0; q < N; q++) ctx->sh_row_bounds[q] = (uint32_t)all[q];
+    ctx->sh_row_bounds[N] = n;
+    if (ctx->sh_row_bounds[0] != 0 || ctx->sh_row_bounds[ctx->comm->rank + 1] != g_end)
+        return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_sharded: the ranks' genome ranges must be contiguous, in rank order, and cover [0, n)");
+    for (int q = 0; q < N; q++)
+        if (ctx->sh_row_bounds[q] > ctx->sh_row_bounds[q + 1]) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_sharded: genome ranges out of order at rank %d", q);
     ctx->maxkey_valid = true;
     ctx->loaded = true;
     return 0;
@@ -1787,11 +1882,15 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     if (d2) YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, cap + 2));
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, (uint64_t)N * cap + 8));
     YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, (uint64_t)N * cap + 8));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, std::max<uint64_t>(T, 1)));
+    ctx->row_items_cap = 2 * T + (1ull << 20);
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, ctx->row_items_cap));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_ptr, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_inbox_item, (uint64_t)N * cap + 8));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_inbox_row, (uint64_t)N * cap + 8));
     YG_CHECK(dev_alloc(ctx, &ctx->d_sh_hist_all, (uint64_t)(N + 1) * NB_MAX));
     YG_CHECK(dev_alloc(ctx, &ctx->d_sh_owner, (uint64_t)NB_MAX));
-    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)64));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)SHI_WORDS));
     const uint64_t aux_words = 3ull * (NB_MAX + 2) + 3ull * ((uint64_t)p.nfb + 2);
     YG_CHECK(dev_alloc(ctx, &ctx->d_msd_aux, aux_words));
     const uint32_t units1 = (uint32_t)((T + SC_TILE - 1) / SC_TILE);
@@ -1801,7 +1900,8 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     {
         // collective: every rank evaluates the same conditions in the same order (allocations move together or a rank re-shares alone
         // harmlessly -- the exchange is an all-gather every rank takes part in, so the decision must be global)
-        unsigned long long moved = (ctx->sh_shared_ent1 != ctx->d_ent1) || (ctx->sh_shared_gid != ctx->d_post) || (ctx->sh_shared_rem != ctx->d_st_rem);
+        unsigned long long moved = (ctx->sh_shared_ent1 != ctx->d_ent1) || (ctx->sh_shared_gid != ctx->d_post) || (ctx->sh_shared_rem != ctx->d_st_rem) ||
+                                   (ctx->sh_shared_item != ctx->d_inbox_item) || (ctx->sh_shared_row != ctx->d_inbox_row);
         unsigned long long* d_flag = &ctx->d_sh_info[40];
         YG_CUDA(ctx, cudaMemcpyAsync(d_flag, &moved, sizeof moved, cudaMemcpyHostToDevice, st));
         YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_flag, d_flag, 1, true));
@@ -1811,7 +1911,10 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
             YG_CHECK(ygpu_comm_share(ctx, ctx->d_ent1, ctx->sh_peer_ent1));
             YG_CHECK(ygpu_comm_share(ctx, ctx->d_post, ctx->sh_peer_gid));
             YG_CHECK(ygpu_comm_share(ctx, ctx->d_st_rem, ctx->sh_peer_rem));
+            YG_CHECK(ygpu_comm_share(ctx, ctx->d_inbox_item, ctx->sh_peer_item));
+            YG_CHECK(ygpu_comm_share(ctx, ctx->d_inbox_row, ctx->sh_peer_row));
             ctx->sh_shared_ent1 = ctx->d_ent1; ctx->sh_shared_gid = ctx->d_post; ctx->sh_shared_rem = ctx->d_st_rem;
+            ctx->sh_shared_item = ctx->d_inbox_item; ctx->sh_shared_row = ctx->d_inbox_row;
         }
     }
     uint32_t* hist1 = ctx->d_msd_aux;
@@ -1824,6 +1927,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_sh_info[SHI_ICUR], 0, (size_t)YG_MAX_RANKS * sizeof(unsigned long long), st));
 
     // ---- 1. level 1 on the resident slice, words stored into their owners' buffers ---------------------------------------
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[0], st));
@@ -1907,7 +2011,12 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         g.scal = ctx->d_scalars;
         g.n_peers = N;
         g.region_base = (uint64_t)rank * cap;
-        for (int q = 0; q < N; q++) { g.peer_gid[q] = (uint32_t*)ctx->sh_peer_gid[q]; g.peer_rem[q] = (unsigned short*)ctx->sh_peer_rem[q]; }
+        for (int q = 0; q < N; q++) {
+            g.peer_gid[q] = (uint32_t*)ctx->sh_peer_gid[q]; g.peer_rem[q] = (unsigned short*)ctx->sh_peer_rem[q];
+            g.peer_item[q] = (uint64_t*)ctx->sh_peer_item[q]; g.peer_row[q] = (uint32_t*)ctx->sh_peer_row[q];
+        }
+        for (int q = 0; q <= N; q++) g.row_bounds[q] = ctx->sh_row_bounds[q];
+        g.icap = cap; g.item_region = (uint64_t)rank * cap; g.icursor = &ctx->d_sh_info[SHI_ICUR];
         const size_t smem2 = sizeof(G2Smem);
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int occ2 = 1;
@@ -1921,22 +2030,45 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     // stream lengths of all ranks (the all-gather is also the barrier behind the stream stores)
     unsigned long long* d_lens = &ctx->d_sh_info[SHI_LENS];
     YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_scalars[SCM_STREAM], d_lens, sizeof(unsigned long long)));
-    YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
 
-    // ---- 3. work lists of this rank's rows from the complete stream; statistics over all ranks ---------------------------
-    k2_items_regions<<<grid_for(ctx, std::max<uint64_t>(Tg / 4, 1), 256, 16), 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end,
-                                                                                      p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0, ctx->d_row_begin_local,
-                                                                                      ctx->d_row_cnt, ctx->d_row_items);
+    // ---- 3. work lists of this rank's rows: the items the ranks sent (+ those derived from the posting stream of the larger
+    //         groups), laid out by count -> scan -> fill; statistics over all ranks ------------------------------------------------
+    unsigned long long* d_ilens = &ctx->d_sh_info[SHI_ILENS];
+    YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_sh_info[SHI_ICUR], d_ilens, (size_t)N * sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
+    const int can_inl = p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0;
+    const int grid_in = grid_for(ctx, std::max<uint64_t>(Tg / (4ull * N), 1), 256, 16);
+    unsigned long long* d_rp = (unsigned long long*)ctx->d_row_ptr;
+    k2_inbox<false><<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_ptr, ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
+    YG_CUDA(ctx, cudaGetLastError());
+    k2_items_regions<false><<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_ptr,
+                                                    ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
+    YG_CUDA(ctx, cudaGetLastError());
+    {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_row_cnt, d_rp, (int64_t)n + 1, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_row_cnt, d_rp, (int64_t)n + 1, st));
+        ctx->tm.n_library_launches += 2;
+    }
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
+    k2_inbox<true><<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_ptr, ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
+    YG_CUDA(ctx, cudaGetLastError());
+    k2_items_regions<true><<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_ptr,
+                                                   ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
     YG_CUDA(ctx, cudaGetLastError());
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[11], st));
-    ctx->tm.n_kernel_launches += 1;
+    ctx->tm.n_kernel_launches += 4;
     // scalars 0..3 (heads, singles, dups, W) summed over the ranks; slot SCM_MAXB(+1) = largest bucket (max)
     unsigned long long* d_tot = &ctx->d_sh_info[24];
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, ctx->d_scalars, d_tot, 4, false));
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, &ctx->d_scalars[SCM_MAXB], d_tot + 4, 2, true));
-    unsigned long long tot[6], info[8];
+    unsigned long long tot[6], info[8], ilens[YG_MAX_RANKS * YG_MAX_RANKS], my_items = 0;
     YG_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_sh_info, sizeof info, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(ilens, d_ilens, (size_t)N * N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(&my_items, d_rp + n, sizeof my_items, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
@@ -1950,6 +2082,9 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         ctx->tm.ms_items += el(10, 11);
         ctx->tm.ms_sync += el(3, 9) + el(8, 10);       // waiting for the peers behind the two exchanges (+ the collectives themselves)
     }
+    for (int q = 0; q < N * N; q++)
+        if (ilens[q] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d sent %llu work items to rank %d, the inbox region holds %llu", q / N, ilens[q], q % N, (unsigned long long)cap);
+    if (my_items > ctx->row_items_cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: %llu work items for this rank's rows, buffer holds %llu", my_items, (unsigned long long)ctx->row_items_cap);
     if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d owns %llu words, exchange buffer holds %llu", rank, info[SHI_TMINE], (unsigned long long)cap);
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
     if (largest > G2_MAXM)
@@ -1965,14 +2100,17 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     ctx->stats = S;
     ctx->P = (uint64_t)N * cap;
     ctx->n_items = S.n_row_items;
-    ctx->d_row_begin = ctx->d_row_begin_local;
+    ctx->d_row_begin = ctx->d_row_ptr;
     ctx->last_index_path = 1;
     ctx->indexed = true;
     if (stats) *stats = S;
 
     // ---- 4. K3 + K4 on this rank's rows, then the pair lists of all ranks on every rank, ordered by (i, j) ---------------
     uint64_t n_r = 0;
-    YG_CHECK(ygpu_pairwise_flag_device(ctx, threshold, ctx->g_begin, ctx->g_end, &n_r));
+    ctx->skip_pair_sort = true;
+    const int rc_pw = ygpu_pairwise_flag_device(ctx, threshold, ctx->g_begin, ctx->g_end, &n_r);
+    ctx->skip_pair_sort = false;
+    YG_CHECK(rc_pw);
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     unsigned long long mine = n_r, counts[YG_MAX_RANKS];
     unsigned long long* d_cnt = &ctx->d_sh_info[44];
@@ -2001,7 +2139,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
             pos += counts[q];
         }
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[12], st));
-        if (N > 1) YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
+        YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
         if (total > ctx->pairs_cap) {
             if (ctx->d_pairs) cudaFree(ctx->d_pairs);
             ctx->d_pairs = nullptr; ctx->pairs_cap = 0;

@@ -758,7 +758,8 @@ struct K3Params {
     uint32_t tile_w;       // columns per tile
     uint32_t n_tiles;
     double thr;
-    uint64_t* out_key;     // (i << 32) | j
+    uint64_t* out_key;     // (i << key_shift) | j   (key_shift = bits of a genome id: the later sort only walks 2 * key_shift bits)
+    int key_shift;
     uint32_t* out_cnt;
     uint64_t out_cap;
     unsigned long long* scal;  // SC_OUT = pairs emitted, SC_UNIT = work-unit ticket, SC_OVF = rows deferred to the dense kernel
@@ -778,7 +779,7 @@ __device__ __forceinline__ void emit_pair(const K3Params& p, uint32_t i, uint32_
     base = __shfl_sync(m, base, leader);
     const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
     if (slot < p.out_cap) {
-        p.out_key[slot] = ((uint64_t)i << 32) | (uint64_t)j;
+        p.out_key[slot] = ((uint64_t)i << p.key_shift) | (uint64_t)j;
         p.out_cnt[slot] = cnt;
     }
 }
@@ -1127,44 +1128,52 @@ __global__ void __launch_bounds__(K3W_THREADS) k3w_count_flag(const K3Params p) 
 }
 
 __global__ void __launch_bounds__(256) k_pack_pairs(const uint64_t* __restrict__ key, const uint32_t* __restrict__ cnt,
-                                                     uint64_t n, ygpu_pair* __restrict__ out) {
+                                                     uint64_t n, int shift, ygpu_pair* __restrict__ out) {
+    const uint64_t jmask = (1ull << shift) - 1ull;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t kk = key[k];
         ygpu_pair pr;
-        pr.i = (int32_t)(kk >> 32);
-        pr.j = (int32_t)(kk & 0xffffffffu);
+        pr.i = (int32_t)(kk >> shift);
+        pr.j = (int32_t)(kk & jmask);
         pr.count = (int32_t)cnt[k];
         out[k] = pr;
     }
 }
 
-__global__ void __launch_bounds__(256) k_unpack_pairs(const ygpu_pair* __restrict__ in, uint64_t n, uint64_t* __restrict__ key,
+__global__ void __launch_bounds__(256) k_unpack_pairs(const ygpu_pair* __restrict__ in, uint64_t n, int shift, uint64_t* __restrict__ key,
                                                        uint32_t* __restrict__ cnt) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
         const ygpu_pair pr = in[k];
-        key[k] = ((uint64_t)(uint32_t)pr.i << 32) | (uint64_t)(uint32_t)pr.j;
+        key[k] = ((uint64_t)(uint32_t)pr.i << shift) | (uint64_t)(uint32_t)pr.j;
         cnt[k] = (uint32_t)pr.count;
     }
 }
 
 static int ensure_out(ygpu_ctx* ctx, uint64_t cap);
 
+static int pair_key_shift(const ygpu_ctx* ctx) {     // bits of a genome id (at least 1)
+    int b = 1;
+    while (b < 32 && ((uint64_t)ctx->n >> b) != 0) b++;
+    return b;
+}
+
 // order a device-resident pair list by (i, j) in place (the gathered lists of several ranks interleave)
 int ygpu_sort_pairs_device(ygpu_ctx* ctx, ygpu_pair* d_pairs, uint64_t n) {
     if (n < 2) return 0;
     cudaStream_t st = ctx->stream;
     YG_CHECK(ensure_out(ctx, std::max<uint64_t>(ctx->out_cap, n)));
-    k_unpack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(d_pairs, n, ctx->d_out_key, ctx->d_out_cnt);
+    const int shift = pair_key_shift(ctx);
+    k_unpack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(d_pairs, n, shift, ctx->d_out_key, ctx->d_out_cnt);
     YG_CUDA(ctx, cudaGetLastError());
     size_t tb = 0;
-    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 64, st));
+    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 2 * shift, st));
     YG_CHECK(ygpu_temp_reserve(ctx, tb));
     tb = ctx->temp_bytes;
-    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 64, st));
-    k_pack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, n, d_pairs);
+    YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt, ctx->d_out_cnt2, (int64_t)n, 0, 2 * shift, st));
+    k_pack_pairs<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, n, shift, d_pairs);
     YG_CUDA(ctx, cudaGetLastError());
     ctx->tm.n_kernel_launches += 2;
-    ctx->tm.n_library_launches += 10;
+    ctx->tm.n_library_launches += 2 + (2 * shift + 7) / 8;
     return 0;
 }
 
@@ -1237,6 +1246,7 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
             p.n = n; p.row_begin = row_begin; p.row_end = row_end; p.tile_w = tile_w; p.n_tiles = n_tiles;
             p.thr = threshold; p.out_key = ctx->d_out_key; p.out_cnt = ctx->d_out_cnt; p.out_cap = ctx->out_cap;
             p.scal = ctx->d_scalars; p.row_list = nullptr; p.n_list = 0; p.ovf_rows = ctx->d_ovf_rows;
+            p.key_shift = pair_key_shift(ctx);
             p.tc = nullptr;
             if (!ctx->stats.has_duplicates && ctx->count_thresholds != 0) {
                 YG_CHECK(dev_alloc(ctx, &ctx->d_tc, n));
@@ -1287,23 +1297,31 @@ static int pairwise_device(ygpu_ctx* ctx, double threshold, uint32_t row_begin, 
         }
     }
     if (npairs) {
-        // order by (i, j): the reference emits row-major (main.cpp:274-275)
+        // order by (i, j): the reference emits row-major (main.cpp:274-275).  The sharded step orders the gathered lists of
+        // all ranks once instead (ctx->skip_pair_sort): here the records are only packed.
         YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
-                                                     ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
-                                                     ctx->d_out_cnt2, (int64_t)npairs, 0, 64, st));
-        ctx->tm.n_library_launches += 10;
+        const int shift = pair_key_shift(ctx);
+        const uint64_t* keys = ctx->d_out_key;
+        const uint32_t* cnts = ctx->d_out_cnt;
+        if (!ctx->skip_pair_sort) {
+            size_t tb = 0;
+            YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
+                                                         ctx->d_out_cnt2, (int64_t)npairs, 0, 2 * shift, st));
+            YG_CHECK(ygpu_temp_reserve(ctx, tb));
+            tb = ctx->temp_bytes;
+            YG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_temp, tb, ctx->d_out_key, ctx->d_out_key2, ctx->d_out_cnt,
+                                                         ctx->d_out_cnt2, (int64_t)npairs, 0, 2 * shift, st));
+            ctx->tm.n_library_launches += 2 + (2 * shift + 7) / 8;
+            keys = ctx->d_out_key2;
+            cnts = ctx->d_out_cnt2;
+        }
         if (npairs > ctx->pairs_cap) {
             if (ctx->d_pairs) cudaFree(ctx->d_pairs);
             ctx->d_pairs = nullptr; ctx->pairs_cap = 0;
             YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs, (npairs + 1024) * sizeof(ygpu_pair)));
             ctx->pairs_cap = npairs + 1024;
         }
-        k_pack_pairs<<<grid_for(ctx, npairs, 256), 256, 0, st>>>(ctx->d_out_key2, ctx->d_out_cnt2, npairs, ctx->d_pairs);
+        k_pack_pairs<<<grid_for(ctx, npairs, 256), 256, 0, st>>>(keys, cnts, npairs, shift, ctx->d_pairs);
         YG_CUDA(ctx, cudaGetLastError());
         ctx->tm.n_kernel_launches++;
         YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));

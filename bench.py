@@ -275,8 +275,8 @@ def workload_config(args, db):
                         f"all-vs-all train hot path, k={KSIZE}, ani_thresh={ANI}",
             "genomes": db.n, "hashes": T, "seed": args.seed, "containment_threshold": THR,
             "parallelism": "1 GPU" if args.gpus == 1 else
-                           f"{args.gpus} GPUs: sketches resident by genome range, index build sharded by hash range (words and group streams "
-                           f"stored into peer buffers over NVLink by the kernels), pairwise count sharded by query rows, pair lists all-gathered (NCCL)",
+                           f"{args.gpus} GPUs, residency by {args.residency}: index build sharded by hash range, pairwise count sharded by query rows "
+                           f"(work items stored into the row owners' buffers over NVLink by the grouping kernel), pair lists all-gathered (NCCL)",
             "l2": f"inputs {8 * T / 1e9:.2f} GB > L2 {L2_BYTES / 1e6:.0f} MB: no flush needed" if 8 * T > L2_BYTES
                   else "inputs fit L2: an L2 flush (write of 256 MB) runs before every timed step"}
 
@@ -337,18 +337,38 @@ def run_b200_arm(args):
     g0, g1 = int(row_bounds[rank]), int(row_bounds[rank + 1])
     lo, hi = int(offsets[g0]), int(offsets[g1])
     pinned_slice = d_slice = None
+    part_off = None
+    sizes32 = db.sizes.astype(np.uint32)
     if world > 1:
-        # N > 1: the library's own sharded step (C++ host layer + NCCL + stores into peer buffers over NVLink): every rank is
-        # resident with the sketches of ITS genome range only; torch.distributed is used for the unique-id hand-over, the
-        # barrier around the timed region and the max over ranks, nothing on the data path
+        # N > 1: the library's own sharded step (C++ host layer + NCCL + stores into peer buffers over NVLink).
+        #   residency "hashes" (default): every rank holds, of EVERY sketch, the hashes of its hash range -- the host cuts the sorted
+        #     sketches at the same N - 1 values; equal hashes meet on one rank, so only work items ever cross NVLink;
+        #   residency "genomes": every rank holds the sketches of its genome range; the level-1 scatter stores every packed word
+        #     into the buffer of the rank that owns its hash range (an all-to-all over NVLink inside the kernel).
+        # torch.distributed is used for the unique-id hand-over, the barrier around the timed region and the max over ranks,
+        # nothing on the data path.
         uid = [_lib.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-        pinned_slice = torch.empty(max(hi - lo, 1), dtype=torch.int64, pin_memory=True)
-        pinned_slice.numpy()[: hi - lo] = db.hashes[lo:hi].view(np.int64)
-        d_slice = torch.from_numpy(db.hashes[lo:hi].view(np.int64)).to(dev)
-        mode["index"] = ("sharded residency (each rank holds its genome range); level-1 words and group streams stored into the owners' "
-                         "buffers over NVLink by the partition / grouping kernels; NCCL for histograms, lengths, statistics, pair lists")
+        if args.residency == "hashes":
+            cuts = sharding.hash_cuts(int(db.hashes.max()), world)
+            mine, part_off = sharding.hashrange_share(db.hashes, offsets, int(cuts[rank]), int(cuts[rank + 1]), last=rank == world - 1)
+            mode["index"] = ("hash-range residency (each rank holds its hash range of every sketch): partition and grouping are local, work items "
+                             "go to the owners of the query rows over NVLink (stores from the grouping kernel); NCCL for lengths, statistics, pair lists")
+        else:
+            mine = db.hashes[lo:hi]
+            mode["index"] = ("genome-range residency (each rank holds the sketches of its genomes): level-1 words and work items stored into the "
+                             "owners' buffers over NVLink by the partition / grouping kernels; NCCL for histograms, lengths, statistics, pair lists")
+        pinned_slice = torch.empty(max(len(mine), 1), dtype=torch.int64, pin_memory=True)
+        pinned_slice.numpy()[: len(mine)] = mine.view(np.int64)
+        d_slice = torch.from_numpy(np.ascontiguousarray(mine).view(np.int64)).to(dev)
+        h2d_mine = 8 * len(mine)
+
+    def load_sharded(ptr, on_device):
+        if args.residency == "hashes":
+            ctx.load_sketches_hashrange(ptr, part_off, sizes32, g0, g1, on_device=on_device)
+        else:
+            ctx.load_sketches_sharded_ptr(ptr, on_device, offsets, g0, g1)
 
     def step_resident():
         if world > 1:
@@ -360,7 +380,7 @@ def run_b200_arm(args):
 
     def step_e2e():
         if world > 1:
-            ctx.load_sketches_sharded_ptr(pinned_slice.data_ptr(), False, offsets, g0, g1)
+            load_sharded(pinned_slice.data_ptr(), False)
             st, F = ctx.train_step_sharded(THR)
             index_stats.update(st)
             return ctx.pairs_host(F)                       # every rank reads the complete, ordered pair list back
@@ -374,7 +394,7 @@ def run_b200_arm(args):
     def timed(fn, reload_first: bool):
         if reload_first:
             if world > 1:
-                ctx.load_sketches_sharded_ptr(d_slice.data_ptr(), True, offsets, g0, g1)
+                load_sharded(d_slice.data_ptr(), True)
             else:
                 ctx.load_sketches_device(d_hashes.data_ptr(), d_offsets.data_ptr(), n)
         for _ in range(args.warmup):
@@ -549,6 +569,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="genomes in the CPU sample (cpu_baseline: 0 = size for ~15 s; --impl reference: 0 = the FULL configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--residency", default="hashes", choices=["hashes", "genomes"],
+                    help="N > 1: what a rank holds -- its hash range of every sketch (default) or the sketches of its genome range")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -228,6 +228,16 @@ int ygpu_load_sketches_sharded_device(ygpu_ctx* ctx, const uint64_t* d_hashes_sl
  * were uploaded to this rank; block_dst[id] is relative to the first hash of genome g_begin                       */
 int ygpu_upload_finish_sharded(ygpu_ctx* ctx, const uint64_t* block_dst, uint32_t nblocks, const uint64_t* offsets, uint32_t n_genomes,
                                uint32_t g_begin, uint32_t g_end);
+/* Hash-range residency (the faster of the two): this rank holds, of EVERY sketch, the hashes inside its hash range -- the
+ * host cuts every (sorted) sketch at the same nranks - 1 hash values, so a rank's share of a sketch is one contiguous
+ * piece of it.  part_offsets[n + 1]: CSR over this rank's share; sizes[n]: the FULL sketch sizes (the containment
+ * denominators); [row_begin, row_end): the query rows this rank counts (contiguous, in rank order, covering [0, n)).
+ * Equal hashes meet on one rank by construction, so ygpu_train_step_sharded exchanges nothing but work items.
+ * The caller guarantees that the ranks' hash ranges are disjoint.                                                     */
+int ygpu_load_sketches_hashrange(ygpu_ctx* ctx, const uint64_t* part_hashes, const uint64_t* part_offsets, const uint32_t* sizes,
+                                 uint32_t n_genomes, uint32_t row_begin, uint32_t row_end);
+int ygpu_load_sketches_hashrange_device(ygpu_ctx* ctx, const uint64_t* d_part_hashes, const uint64_t* part_offsets, const uint32_t* sizes,
+                                        uint32_t n_genomes, uint32_t row_begin, uint32_t row_end);
 int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats /* may be NULL */, uint64_t* n_pairs_total);
 
 /* ---- run path ------------------------------------------------------------------------------ */

@@ -15,9 +15,13 @@ pytestmark = pytest.mark.gpu
 THR = 0.95 ** 31
 
 
-def _run_ranks(db, nranks, thr):
+def _run_ranks(db, nranks, thr, residency):
+    """residency "genomes": rank r holds the sketches of its genome range (words cross NVLink in the level-1 scatter);
+    "hashes": rank r holds, of every sketch, the hashes of its hash range (only work items cross NVLink)."""
     offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
     bounds = sharding.split_rows_by_size(offsets, nranks)
+    cuts = sharding.hash_cuts(int(db.hashes.max()) if len(db.hashes) else 0, nranks)
+    sizes = db.sizes.astype(np.uint32)
     uid = _lib.comm_unique_id()
     out = [None] * nranks
     err = [None] * nranks
@@ -28,8 +32,12 @@ def _run_ranks(db, nranks, thr):
                 ctx.comm_init(r, nranks, uid)
                 g0, g1 = int(bounds[r]), int(bounds[r + 1])
                 sl = db.hashes[int(offsets[g0]):int(offsets[g1])]
+                ph, po = sharding.hashrange_share(db.hashes, offsets, int(cuts[r]), int(cuts[r + 1]), last=r == nranks - 1)
                 for rep in range(2):            # the second step reuses the shared exchange buffers
-                    ctx.load_sketches_sharded(sl, offsets, g0, g1)
+                    if residency == "genomes":
+                        ctx.load_sketches_sharded(sl, offsets, g0, g1)
+                    else:
+                        ctx.load_sketches_hashrange(ph, po, sizes, g0, g1)
                     st, F = ctx.train_step_sharded(thr)
                 out[r] = (st, ctx.pairs_host(F))
         except Exception as e:  # noqa: BLE001
@@ -48,7 +56,12 @@ def _run_ranks(db, nranks, thr):
 
 def _check(db, nranks, thr):
     ref = to.oracle_train(db.hashes, db.offsets, thr)
-    res = _run_ranks(db, nranks, thr)
+    for residency in ("hashes", "genomes"):
+        _check_one(db, nranks, thr, residency, ref)
+
+
+def _check_one(db, nranks, thr, residency, ref):
+    res = _run_ranks(db, nranks, thr, residency)
     for st, pairs in res:
         assert (st["n_distinct"], st["n_singleton"], st["n_index"]) == (ref.n_distinct, ref.n_singleton, ref.n_index)
         assert (st["n_postings"], st["n_increments"]) == (ref.n_postings, ref.n_increments)

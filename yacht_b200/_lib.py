@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "ygpu_hyp_test",
     "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
     "ygpu_comm_get_unique_id", "ygpu_comm_init", "ygpu_comm_destroy", "ygpu_load_sketches_sharded", "ygpu_load_sketches_sharded_device",
-    "ygpu_train_step_sharded", "ygpu_upload_finish_sharded",
+    "ygpu_train_step_sharded", "ygpu_upload_finish_sharded", "ygpu_load_sketches_hashrange", "ygpu_load_sketches_hashrange_device",
 ]
 COMM_ID_BYTES = 128
 
@@ -125,6 +125,8 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_comm_destroy.argtypes = [vp]
     lib.ygpu_load_sketches_sharded.argtypes = [vp, vp, vp, u32, u32, u32]
     lib.ygpu_load_sketches_sharded_device.argtypes = [vp, vp, vp, u32, u32, u32]
+    lib.ygpu_load_sketches_hashrange.argtypes = [vp, vp, vp, vp, u32, u32, u32]
+    lib.ygpu_load_sketches_hashrange_device.argtypes = [vp, vp, vp, vp, u32, u32, u32]
     lib.ygpu_upload_finish_sharded.argtypes = [vp, vp, u32, vp, u32, u32, u32]
     lib.ygpu_train_step_sharded.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     for name in ABI_SYMBOLS:
@@ -259,6 +261,21 @@ class GpuContext:
         fn = self.lib.ygpu_load_sketches_sharded_device if on_device else self.lib.ygpu_load_sketches_sharded
         self._check(fn(self.h, ctypes.c_void_p(slice_ptr), offsets.ctypes.data, int(offsets.shape[0]) - 1, int(g_begin), int(g_end)),
                     "ygpu_load_sketches_sharded")
+
+    def load_sketches_hashrange(self, part_hashes, part_offsets: np.ndarray, sizes: np.ndarray, row_begin: int, row_end: int,
+                                on_device: bool = False) -> None:
+        """Hash-range residency: part_hashes (numpy array, or a raw pointer when on_device) = of every sketch the hashes inside
+        this rank's hash range; part_offsets = CSR over that share; sizes = the full sketch sizes."""
+        part_offsets = np.ascontiguousarray(part_offsets, dtype=np.uint64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        n = int(sizes.shape[0])
+        if isinstance(part_hashes, np.ndarray):
+            part_hashes = np.ascontiguousarray(part_hashes, dtype=np.uint64)
+            ptr = part_hashes.ctypes.data if part_hashes.size else None
+        else:
+            ptr = ctypes.c_void_p(int(part_hashes))
+        fn = self.lib.ygpu_load_sketches_hashrange_device if on_device else self.lib.ygpu_load_sketches_hashrange
+        self._check(fn(self.h, ptr, part_offsets.ctypes.data, sizes.ctypes.data, n, int(row_begin), int(row_end)), "ygpu_load_sketches_hashrange")
 
     def train_step_sharded(self, threshold: float) -> Tuple[dict, int]:
         """Index build + pairwise count/flag over all ranks; afterwards pairs_copy()/pairs_host() give the COMPLETE sorted pair list."""

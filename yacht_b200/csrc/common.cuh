@@ -92,7 +92,10 @@ struct ygpu_ctx {
 
     // ---- sharded residency + multi-GPU train step (comm.cu, index_msd.cu: ygpu_train_step_sharded) ----------------
     ygpu_comm* comm = nullptr;
-    bool sharded = false;           // this context holds only the sketches of genomes [g_begin, g_end)
+    bool sharded = false;           // this context holds only a share of the sketches (rank of a communicator)
+    int shard_mode = 0;             // 0: the sketches of genomes [g_begin, g_end); 1: of EVERY sketch the hashes of this rank's hash range
+    uint64_t sh_cap_req = 0;        // mode 1: largest share over the ranks (sizes the exchange buffers)
+    unsigned long long* d_sh_flags = nullptr;
     uint32_t g_begin = 0, g_end = 0;
     uint64_t T_global = 0;
     uint32_t max_sketch_global = 0;
@@ -112,7 +115,7 @@ struct ygpu_ctx {
     void* sh_shared_item = nullptr;
     void* sh_shared_row = nullptr;
     uint32_t sh_row_bounds[YG_MAX_RANKS + 1] = {};   // rank q holds / counts the genomes [sh_row_bounds[q], sh_row_bounds[q + 1])
-    uint64_t row_items_cap = 0;
+    uint64_t row_items_cap = 0, row_items_need = 0;
     void* sh_shared_ent1 = nullptr;         // which allocations the peer pointers above refer to (re-shared when they move)
     void* sh_shared_gid = nullptr;
     void* sh_shared_rem = nullptr;

@@ -1116,33 +1116,32 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
 
 // sharded build, receiving side.  Work items arrive (a) ready-made in the item inbox: region q holds ilens[q * n_regions + me]
 // items of rank q for rows of this rank; (b) as the posting stream of the larger groups: N regions of `cap` slots, region q holding
-// lens[q] entries, every rank holds all of it and derives the (indirect) items of its own rows.  A row's list has no size
-// bound here (a member of a group of 16 is worth five items), so the lists are laid out by counting first: PLACE = false
-// counts per row, the host scans, PLACE = true fills.
-template <bool PLACE>
+// lens[q] entries, every rank holds all of it and derives the (indirect) items of its own rows.  Row g's list lives at
+// row_ptr[g] with room for 2 * |S_g| + 8 items (k2s_sizes); a row that would need more (nearly all of its hashes in groups of
+// 9..16 genomes) raises *overflow and the step is refused -- callers then run the database on one GPU.
 __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ items, const uint32_t* __restrict__ rows,
                                                 const unsigned long long* __restrict__ ilens, int n_regions, int me, uint64_t icap,
-                                                const uint64_t* __restrict__ row_ptr, unsigned long long* __restrict__ row_cnt,
-                                                uint64_t* __restrict__ row_items, uint64_t items_cap) {
+                                                const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ sizes,
+                                                unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items,
+                                                unsigned long long* __restrict__ overflow) {
     for (int q = 0; q < n_regions; q++) {
         const uint64_t base = (uint64_t)q * icap;
         const uint64_t len = min((uint64_t)ilens[(size_t)q * n_regions + me], icap);
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
             const uint32_t g = rows[base + i];
+            const uint64_t item = items[base + i];
             const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            if (PLACE) {
-                const uint64_t dst = row_ptr[g] + slot;
-                if (dst < items_cap) row_items[dst] = items[base + i];
-            }
+            if (slot < 2ull * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
+            else *overflow = 1ull;
         }
     }
 }
 
-template <bool PLACE>
 __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem,
                                                         const unsigned long long* __restrict__ lens, int n_regions, uint64_t cap,
                                                         uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_ptr,
-                                                        unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items, uint64_t items_cap) {
+                                                        const uint32_t* __restrict__ sizes, unsigned long long* __restrict__ row_cnt,
+                                                        uint64_t* __restrict__ row_items, unsigned long long* __restrict__ overflow) {
     for (int q = 0; q < n_regions; q++) {
         const uint64_t base = (uint64_t)q * cap, len = lens[q];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1151,19 +1150,17 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
             if (!r) continue;
             const uint32_t g = gid[x];
             if (g < row_begin || g >= row_end) continue;
-            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            if (PLACE) {
-                uint64_t item;
-                if (can_inline && r <= 3) {
-                    item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
-                    if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
-                    if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
-                } else {
-                    item = ((x + 1) << 32) | ((uint64_t)r << 2);
-                }
-                const uint64_t dst = row_ptr[g] + slot;
-                if (dst < items_cap) row_items[dst] = item;
+            uint64_t item;
+            if (can_inline && r <= 3) {
+                item = (uint64_t)r | ((uint64_t)gid[x + 1] << 2);
+                if (r >= 2) item |= (uint64_t)gid[x + 2] << 22;
+                if (r >= 3) item |= (uint64_t)gid[x + 3] << 42;
+            } else {
+                item = ((x + 1) << 32) | ((uint64_t)r << 2);
             }
+            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            if (slot < 2ull * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
+            else *overflow = 1ull;
         }
     }
 }
@@ -1175,7 +1172,7 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
 // the level-1 scatter can store them there directly.  For the digits this rank owns it also lays out level 2 (bucket
 // bases and tile prefix in the GLOBAL digit numbering: foreign digits are simply empty).
 // slots of ctx->d_sh_info (LENS: [nranks] posting-stream lengths; ICUR: [nranks] items sent to every rank; ILENS: [nranks][nranks] all-gathered)
-enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_LENS = 8, SHI_ICUR = 64, SHI_ILENS = 96, SHI_WORDS = 512 };
+enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_TMAX = 5, SHI_LENS = 8, SHI_ICUR = 64, SHI_ILENS = 96, SHI_WORDS = 512 };
 
 __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hist_all, uint32_t nb, int nranks, int rank, int d2,
                                                  uint32_t* __restrict__ owner, uint32_t* __restrict__ cursor, uint32_t* __restrict__ base,
@@ -1186,7 +1183,7 @@ __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hi
     __shared__ typename Scan64::TempStorage ts0;
     __shared__ typename Scan32::TempStorage ts1, ts2;
     __shared__ unsigned char s_own[NB_MAX];
-    __shared__ unsigned long long s_start[YG_MAX_RANKS];
+    __shared__ unsigned long long s_start[YG_MAX_RANKS], s_owned[YG_MAX_RANKS];
     __shared__ uint32_t s_lo, s_hi;
     constexpr int per = (NB_MAX + 1023) / 1024;
     unsigned long long g[per], pre[per], gs = 0;
@@ -1204,6 +1201,7 @@ __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hi
     unsigned long long acc, total;
     Scan64(ts0).ExclusiveSum(gs, acc, total);
     if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0; }
+    if (threadIdx.x < YG_MAX_RANKS) s_owned[threadIdx.x] = 0;
     unsigned long long ex[per];
     uint32_t own[per];
     for (int k = 0; k < per; k++) {
@@ -1217,6 +1215,7 @@ __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hi
     for (int k = 0; k < per; k++) {
         const uint32_t d = threadIdx.x * per + k;
         if (d < nb && (d == 0 || s_own[d - 1] != own[k])) s_start[own[k]] = ex[k];
+        if (d < nb && g[k]) atomicAdd(&s_owned[own[k]], g[k]);
     }
     __syncthreads();
     uint32_t hm[per], tl[per], hs = 0, tsum = 0, mx = 0;
@@ -1249,11 +1248,16 @@ __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hi
         const uint32_t lo = s_lo == 0xFFFFFFFFu ? 0u : s_lo, hi = s_lo == 0xFFFFFFFFu ? 0u : s_hi;
         info[SHI_DLO] = lo; info[SHI_DHI] = hi; info[SHI_TMINE] = htot;
         info[SHI_BLO] = (unsigned long long)lo << d2; info[SHI_BHI] = (unsigned long long)hi << d2;
+        unsigned long long tmax = 0;
+        for (int q = 0; q < nranks; q++) tmax = max(tmax, s_owned[q]);
+        info[SHI_TMAX] = tmax;          // the most words any rank owns: every rank knows whether the exchange buffers suffice
     }
     if (mx) atomicMax(&scal[SCM_MAXB], (unsigned long long)mx);
 }
 
-// sketch sizes of ALL genomes and the work-list starts of the resident rows (sharded residency)
+// sketch sizes of ALL genomes, the slice-relative offsets (genome-range residency) and the work-list starts of this rank's
+// query rows [g_begin, g_end): row g may receive up to 2 * |S_g| + 8 items (one per shared hash for pairs and groups up to 4,
+// ceil(followers / 3) for a member of a group of up to 16; more is refused, see k2_inbox)
 __global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ offsets, uint32_t n, uint32_t g_begin, uint32_t g_end,
                                                  uint32_t* __restrict__ sizes, uint64_t* __restrict__ row_begin_local,
                                                  uint64_t* __restrict__ offsets_local) {
@@ -1261,9 +1265,25 @@ __global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ of
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g <= n; g += gridDim.x * blockDim.x) {
         if (g < n) {
             sizes[g] = (uint32_t)(offsets[g + 1] - offsets[g]);
-            row_begin_local[g] = (g >= g_begin && g < g_end) ? offsets[g] - o0 : 0ull;
+            row_begin_local[g] = (g >= g_begin && g < g_end) ? 2ull * (offsets[g] - o0) + 8ull * (g - g_begin) : 0ull;
         }
-        if (g >= g_begin && g <= g_end) offsets_local[g - g_begin] = offsets[g] - o0;
+        if (offsets_local && g >= g_begin && g <= g_end) offsets_local[g - g_begin] = offsets[g] - o0;
+    }
+}
+
+// first / last level-1 digit this rank holds words of (hash-range residency: its hash range), as bucket range for the grouping
+__global__ void __launch_bounds__(1024) k2s_range(const uint32_t* __restrict__ hist, uint32_t nb, int d2, unsigned long long T_mine,
+                                                  unsigned long long* __restrict__ info) {
+    __shared__ uint32_t s_lo, s_hi;
+    if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0; }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < nb; d += blockDim.x)
+        if (hist[d]) { atomicMin(&s_lo, d); atomicMax(&s_hi, d + 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t lo = s_lo == 0xFFFFFFFFu ? 0u : s_lo, hi = s_lo == 0xFFFFFFFFu ? 0u : s_hi;
+        info[SHI_DLO] = lo; info[SHI_DHI] = hi; info[SHI_TMINE] = T_mine;
+        info[SHI_BLO] = (unsigned long long)lo << d2; info[SHI_BHI] = (unsigned long long)hi << d2;
     }
 }
 
@@ -1756,7 +1776,9 @@ int ygpu_sharded_finish(ygpu_ctx* ctx, const uint64_t* offsets, uint32_t n, uint
     if (Tg >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)Tg);
     const uint64_t T = offsets[g_end] - offsets[g_begin];
     ctx->n = n; ctx->T = T; ctx->T_global = Tg; ctx->g_begin = g_begin; ctx->g_end = g_end; ctx->sharded = true;
+    ctx->shard_mode = 0;
     ctx->max_sketch_global = mx;
+    ctx->row_items_need = 2 * T + 8ull * (g_end - g_begin) + 16;
     YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
     YG_CHECK(dev_alloc(ctx, &ctx->d_sizes, n));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_begin_local, (uint64_t)n + 1));
@@ -1826,6 +1848,91 @@ extern "C" int ygpu_load_sketches_sharded_device(ygpu_ctx* ctx, const uint64_t* 
     return sharded_load(ctx, d_hashes_slice, offsets, n_genomes, g_begin, g_end, true);
 }
 
+// ---- hash-range residency: this rank holds, of EVERY sketch, the hashes that fall into its hash range ------------------------
+// (a sketch is sorted, so that share is one contiguous piece of it: the host cuts every sketch at the same N - 1 hash values).
+// Equal hashes then meet on one rank by construction: the index build needs no exchange at all before the grouping, and the
+// only data that ever crosses NVLink are the work items the grouping kernel sends to the owners of the query rows.
+static int hashrange_load(ygpu_ctx* ctx, const uint64_t* part_hashes, const uint64_t* part_offsets, const uint32_t* sizes, uint32_t n,
+                          uint32_t row_begin, uint32_t row_end, bool from_device) {
+    if (!ctx || !part_offsets || (n && !sizes)) return YGPU_ERR_ARG;
+    if (!ctx->comm) return ygpu_fail(ctx, YGPU_ERR_STATE, "load_sketches_hashrange: ygpu_comm_init first");
+    if (row_begin > row_end || row_end > n) return ygpu_fail(ctx, YGPU_ERR_ARG, "bad row range [%u,%u) of %u", row_begin, row_end, n);
+    YG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->loaded = false; ctx->indexed = false; ctx->sorted = false; ctx->maxkey_valid = false; ctx->row_work_valid = false;
+    ctx->part_valid = false; ctx->P = 0; ctx->n_items = 0;
+    if (part_offsets[0] != 0) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets[0] must be 0");
+    uint64_t Tg = 0;
+    uint32_t mx = 0;
+    for (uint32_t g = 0; g < n; g++) {
+        if (part_offsets[g + 1] < part_offsets[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "offsets not monotone at genome %u", g);
+        if (part_offsets[g + 1] - part_offsets[g] > sizes[g]) return ygpu_fail(ctx, YGPU_ERR_ARG, "genome %u: the resident share exceeds the sketch size", g);
+        Tg += sizes[g];
+        mx = std::max(mx, sizes[g]);
+    }
+    const uint64_t T = part_offsets[n];
+    if (Tg >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)Tg);
+    if (T && !part_hashes) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_hashrange: NULL hashes");
+    // work-list starts of this rank's query rows: room for 2 * |S_g| + 8 items per row (k2s_sizes has the same rule)
+    std::vector<uint64_t> rb((size_t)n + 1, 0);
+    uint64_t acc = 0;
+    for (uint32_t g = row_begin; g < row_end; g++) { rb[g] = acc; acc += 2ull * sizes[g] + 8ull; }
+    ctx->n = n; ctx->T = T; ctx->T_global = Tg; ctx->g_begin = row_begin; ctx->g_end = row_end; ctx->sharded = true;
+    ctx->shard_mode = 1;
+    ctx->max_sketch_global = mx;
+    ctx->row_items_need = acc + 16;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_hashes, T + 2));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sizes, n));
+    YG_CHECK(dev_alloc(ctx, &ctx->d_row_begin_local, (uint64_t)n + 1));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (T) YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_hashes, part_hashes, T * sizeof(uint64_t), from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, part_offsets, ((uint64_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (n) YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, sizes, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_row_begin_local, rb.data(), ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    // over ALL ranks: the largest hash (decides the partition plan), the largest share (sizes the exchange buffers), the row ranges
+    const int N = ctx->comm->nranks;
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)SHI_WORDS));
+    unsigned long long* d_mx = &ctx->d_sh_info[SHI_ICUR];            // {largest hash, largest share}
+    YG_CUDA(ctx, cudaMemsetAsync(d_mx, 0, 2 * sizeof(unsigned long long), st));
+    if (T) {
+        size_t tb = 0;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tb, ctx->d_hashes, (uint64_t*)d_mx, (int64_t)T, st));
+        YG_CHECK(ygpu_temp_reserve(ctx, tb));
+        tb = ctx->temp_bytes;
+        YG_CUDA(ctx, cub::DeviceReduce::Max(ctx->d_temp, tb, ctx->d_hashes, (uint64_t*)d_mx, (int64_t)T, st));
+        ctx->tm.n_library_launches += 2;
+    }
+    unsigned long long share = T, back[2], rb0 = row_begin, all[YG_MAX_RANKS];
+    YG_CUDA(ctx, cudaMemcpyAsync(d_mx + 1, &share, sizeof share, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_mx, d_mx, 2, true));
+    YG_CUDA(ctx, cudaMemcpyAsync(back, d_mx, sizeof back, cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(d_mx + 2, &rb0, sizeof rb0, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allgather(ctx, d_mx + 2, &ctx->d_sh_info[SHI_ILENS], sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaMemcpyAsync(all, &ctx->d_sh_info[SHI_ILENS], (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->maxkey = back[0];
+    ctx->sh_cap_req = back[1];
+    for (int q = 0; q < N; q++) ctx->sh_row_bounds[q] = (uint32_t)all[q];
+    ctx->sh_row_bounds[N] = n;
+    if (ctx->sh_row_bounds[0] != 0 || ctx->sh_row_bounds[ctx->comm->rank + 1] != row_end)
+        return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_hashrange: the ranks' row ranges must be contiguous, in rank order, and cover [0, n)");
+    ctx->maxkey_valid = true;
+    ctx->loaded = true;
+    ctx->tm.ms_h2d += elapsed(ctx, 0, 1);
+    return 0;
+}
+
+extern "C" int ygpu_load_sketches_hashrange(ygpu_ctx* ctx, const uint64_t* part_hashes, const uint64_t* part_offsets, const uint32_t* sizes,
+                                            uint32_t n_genomes, uint32_t row_begin, uint32_t row_end) {
+    return hashrange_load(ctx, part_hashes, part_offsets, sizes, n_genomes, row_begin, row_end, false);
+}
+extern "C" int ygpu_load_sketches_hashrange_device(ygpu_ctx* ctx, const uint64_t* d_part_hashes, const uint64_t* part_offsets, const uint32_t* sizes,
+                                                   uint32_t n_genomes, uint32_t row_begin, uint32_t row_end) {
+    return hashrange_load(ctx, d_part_hashes, part_offsets, sizes, n_genomes, row_begin, row_end, true);
+}
+
 extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats, uint64_t* n_pairs_total) {
     if (!ctx || !n_pairs_total) return YGPU_ERR_ARG;
     *n_pairs_total = 0;
@@ -1857,7 +1964,8 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     while (D < p.hb && D < 22 && Tg / used_buckets(D) > A_TARGET) D++;
     // level 1 is the exchange: its runs per (tile, digit) are what crosses NVLink, so it gets as FEW digits as the two levels
     // allow (level 2 takes up to 11 bits) -- 16-word runs are 128-byte packets, 4-word runs are 32-byte ones
-    int d1 = D <= 8 ? D : std::max(D - 11, std::min(8, D / 2));
+    const bool hr = ctx->shard_mode == 1;     // hash-range residency: nothing is exchanged before the grouping
+    int d1 = D <= 8 ? D : (hr ? (D + 1) / 2 : std::max(D - 11, std::min(8, D / 2)));
     const int need = p.hb + p.gb - 64;
     if (need > d1) d1 = need;
     int d2 = std::max(0, D - d1);
@@ -1875,14 +1983,15 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     if (why) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: this database does not qualify for the sharded partition path: %s", why);
 
     // ---- buffers; the exchange targets are (re)shared with the peers when they move ------------------------------------
-    const uint64_t cap = Tg / N + 2 * (Tg / std::max<uint32_t>(p.nb1, 1)) + 3 * SC_TILE;        // words a rank can own: its share + digit granularity
+    // words a rank can own: its share + digit granularity (genome-range residency), the largest share (hash-range residency)
+    const uint64_t cap = hr ? ctx->sh_cap_req + 3 * SC_TILE : Tg / N + 2 * (Tg / std::max<uint32_t>(p.nb1, 1)) + 3 * SC_TILE;
     if ((uint64_t)N * cap + 8 >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "stream of %llu entries >= 2^32 not supported", (unsigned long long)N * cap);
     ctx->sh_cap = cap;
     YG_CHECK(dev_alloc(ctx, &ctx->d_ent1, cap + 2));
     if (d2) YG_CHECK(dev_alloc(ctx, &ctx->d_ent2, cap + 2));
     YG_CHECK(dev_alloc(ctx, &ctx->d_post, (uint64_t)N * cap + 8));
     YG_CHECK(dev_alloc(ctx, &ctx->d_st_rem, (uint64_t)N * cap + 8));
-    ctx->row_items_cap = 2 * T + (1ull << 20);
+    ctx->row_items_cap = ctx->row_items_need;
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_items, ctx->row_items_cap));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_cnt, (uint64_t)n + 1));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_ptr, (uint64_t)n + 1));
@@ -1929,37 +2038,56 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
     YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_sh_info[SHI_ICUR], 0, (size_t)YG_MAX_RANKS * sizeof(unsigned long long), st));
 
-    // ---- 1. level 1 on the resident slice, words stored into their owners' buffers ---------------------------------------
+    // ---- 1. level 1.  Genome-range residency: on the resident slice, every word stored into its owner's buffer (NVLink).
+    //         Hash-range residency: purely local -- this rank already holds exactly the hashes of its range. ---------------------
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[0], st));
     if (T) {
         k2_hist1<<<ctx->num_sms * 8, 256, p.nb1 * sizeof(uint32_t), st>>>(ctx->d_hashes, p, hist1);
         YG_CUDA(ctx, cudaGetLastError());
     }
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[1], st));
-    YG_CHECK(ygpu_comm_allgather(ctx, hist1, ctx->d_sh_hist_all, (size_t)NB_MAX * sizeof(uint32_t)));
-    k2s_prep<<<1, 1024, 0, st>>>(ctx->d_sh_hist_all, p.nb1, N, rank, d2, ctx->d_sh_owner, cursor, base1, tile_start, ctx->d_sh_info, ctx->d_scalars);
-    YG_CUDA(ctx, cudaGetLastError());
     ScatterArgs a{};
-    a.hashes = ctx->d_hashes; a.offsets = ctx->d_offsets_local; a.n = ctx->g_end - ctx->g_begin; a.gid_base = ctx->g_begin;
-    a.out_ent = ctx->d_ent1; a.cursor = cursor; a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2; a.owner = ctx->d_sh_owner;
-    for (int q = 0; q < N; q++) a.peer_ent[q] = (uint64_t*)ctx->sh_peer_ent1[q];
+    a.hashes = ctx->d_hashes; a.out_ent = ctx->d_ent1; a.cursor = cursor; a.base1 = base1; a.tile_start = tile_start; a.hist2 = hist2;
+    if (hr) {
+        k2_prep1<<<1, 1024, 0, st>>>(hist1, p.nb1, base1, tile_start, cursor, ctx->d_scalars);
+        YG_CUDA(ctx, cudaGetLastError());
+        k2s_range<<<1, 1024, 0, st>>>(hist1, p.nb1, d2, (unsigned long long)T, ctx->d_sh_info);
+        YG_CUDA(ctx, cudaGetLastError());
+        a.offsets = ctx->d_offsets; a.n = n; a.gid_base = 0;           // the resident CSR spans all genomes
+    } else {
+        YG_CHECK(ygpu_comm_allgather(ctx, hist1, ctx->d_sh_hist_all, (size_t)NB_MAX * sizeof(uint32_t)));
+        k2s_prep<<<1, 1024, 0, st>>>(ctx->d_sh_hist_all, p.nb1, N, rank, d2, ctx->d_sh_owner, cursor, base1, tile_start, ctx->d_sh_info, ctx->d_scalars);
+        YG_CUDA(ctx, cudaGetLastError());
+        // the plan is the same on every rank, so every rank sees whether some rank would own more words than the exchange
+        // buffers hold (a hash distribution far from uniform) and all of them stop here, before a single word is stored
+        unsigned long long tmax = 0;
+        YG_CUDA(ctx, cudaMemcpyAsync(&tmax, &ctx->d_sh_info[SHI_TMAX], sizeof tmax, cudaMemcpyDeviceToHost, st));
+        YG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (tmax > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a rank would own %llu words, the exchange buffers hold %llu", tmax, (unsigned long long)cap);
+        a.offsets = ctx->d_offsets_local; a.n = ctx->g_end - ctx->g_begin; a.gid_base = ctx->g_begin;
+        a.owner = ctx->d_sh_owner;
+        for (int q = 0; q < N; q++) a.peer_ent[q] = (uint64_t*)ctx->sh_peer_ent1[q];
+    }
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[2], st));
     if (T) {
-        k2_tile_g0<<<grid_for(ctx, (uint64_t)units1 + 1, 256, 8), 256, 0, st>>>(ctx->d_offsets_local, a.n, T, units1, ctx->d_tile_g0);
+        k2_tile_g0<<<grid_for(ctx, (uint64_t)units1 + 1, 256, 8), 256, 0, st>>>(a.offsets, a.n, T, units1, ctx->d_tile_g0);
         YG_CUDA(ctx, cudaGetLastError());
         a.tile_g0 = ctx->d_tile_g0;
-        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)p.nb1 * 20 + (size_t)SC_TILE * 2;
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_scatter<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)2 * SC_BUF * 8 + (size_t)p.nb1 * (hr ? 12 : 20) + (size_t)SC_TILE * 2;
+        auto kern = hr ? k2_scatter<1, false> : k2_scatter<1, true>;
+        YG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_scatter<1, true>, SC_THREADS, smem));
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC_THREADS, smem));
         const int grid = (int)std::min<uint64_t>(units1, (uint64_t)ctx->num_sms * std::max(occ, 1));
-        k2_scatter<1, true><<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
+        kern<<<grid, SC_THREADS, smem, st>>>(a, p, 0u, units1);
         YG_CUDA(ctx, cudaGetLastError());
     }
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[3], st));
-    // every rank's words have landed once every rank has passed this point (the collective also orders the peer stores)
-    unsigned long long* d_sync = &ctx->d_sh_info[41];
-    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_sync, d_sync, 1, true));
+    if (!hr) {
+        // every rank's words have landed once every rank has passed this point (the collective also orders the peer stores)
+        unsigned long long* d_sync = &ctx->d_sh_info[41];
+        YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_sync, d_sync, 1, true));
+    }
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[9], st));
     ctx->tm.n_kernel_launches += 4;
 
@@ -2038,37 +2166,30 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
     const int can_inl = p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0;
     const int grid_in = grid_for(ctx, std::max<uint64_t>(Tg / (4ull * N), 1), 256, 16);
-    unsigned long long* d_rp = (unsigned long long*)ctx->d_row_ptr;
-    k2_inbox<false><<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_ptr, ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
+    unsigned long long* d_ovf = &ctx->d_sh_info[42];
+    YG_CUDA(ctx, cudaMemsetAsync(d_ovf, 0, sizeof(unsigned long long), st));
+    k2_inbox<<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_begin_local, ctx->d_sizes, ctx->d_row_cnt,
+                                      ctx->d_row_items, d_ovf);
     YG_CUDA(ctx, cudaGetLastError());
-    k2_items_regions<false><<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_ptr,
-                                                    ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
-    YG_CUDA(ctx, cudaGetLastError());
-    {
-        size_t tb = 0;
-        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->d_row_cnt, d_rp, (int64_t)n + 1, st));
-        YG_CHECK(ygpu_temp_reserve(ctx, tb));
-        tb = ctx->temp_bytes;
-        YG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_temp, tb, ctx->d_row_cnt, d_rp, (int64_t)n + 1, st));
-        ctx->tm.n_library_launches += 2;
-    }
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-    k2_inbox<true><<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_ptr, ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
-    YG_CUDA(ctx, cudaGetLastError());
-    k2_items_regions<true><<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_ptr,
-                                                   ctx->d_row_cnt, ctx->d_row_items, ctx->row_items_cap);
+    k2_items_regions<<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_begin_local,
+                                              ctx->d_sizes, ctx->d_row_cnt, ctx->d_row_items, d_ovf);
     YG_CUDA(ctx, cudaGetLastError());
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[11], st));
-    ctx->tm.n_kernel_launches += 4;
+    ctx->tm.n_kernel_launches += 2;
     // scalars 0..3 (heads, singles, dups, W) summed over the ranks; slot SCM_MAXB(+1) = largest bucket (max)
     unsigned long long* d_tot = &ctx->d_sh_info[24];
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, ctx->d_scalars, d_tot, 4, false));
     YG_CHECK(ygpu_comm_allreduce_u64(ctx, &ctx->d_scalars[SCM_MAXB], d_tot + 4, 2, true));
+    // refusals must be unanimous (a rank that stopped here would leave the others waiting in the pair gather): the overflow flag
+    // and the largest number of words any rank owns, over all ranks
+    YG_CUDA(ctx, cudaMemcpyAsync(d_ovf + 1, &ctx->d_sh_info[SHI_TMINE], sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_ovf, d_ovf, 2, true));
     unsigned long long tot[6], info[8], ilens[YG_MAX_RANKS * YG_MAX_RANKS], my_items = 0;
     YG_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_sh_info, sizeof info, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaMemcpyAsync(ilens, d_ilens, (size_t)N * N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaMemcpyAsync(&my_items, d_rp + n, sizeof my_items, cudaMemcpyDeviceToHost, st));
+    unsigned long long ovf_tm[2] = {0, 0};
+    YG_CUDA(ctx, cudaMemcpyAsync(ovf_tm, d_ovf, sizeof ovf_tm, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
@@ -2084,8 +2205,10 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     }
     for (int q = 0; q < N * N; q++)
         if (ilens[q] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d sent %llu work items to rank %d, the inbox region holds %llu", q / N, ilens[q], q % N, (unsigned long long)cap);
-    if (my_items > ctx->row_items_cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: %llu work items for this rank's rows, buffer holds %llu", my_items, (unsigned long long)ctx->row_items_cap);
-    if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d owns %llu words, exchange buffer holds %llu", rank, info[SHI_TMINE], (unsigned long long)cap);
+    my_items = ovf_tm[0];
+    info[SHI_TMINE] = ovf_tm[1];
+    if (my_items) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row received more work items than 2 x its sketch size + 8 (dense groups of 9..16 genomes): run this database on one GPU");
+    if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a rank owns %llu words, the exchange buffers hold %llu", info[SHI_TMINE], (unsigned long long)cap);
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
     if (largest > G2_MAXM)
         return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a final bucket holds %llu words (> %u): skewed databases take the replicated build (ygpu_build_index)",
@@ -2100,7 +2223,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     ctx->stats = S;
     ctx->P = (uint64_t)N * cap;
     ctx->n_items = S.n_row_items;
-    ctx->d_row_begin = ctx->d_row_ptr;
+    ctx->d_row_begin = ctx->d_row_begin_local;
     ctx->last_index_path = 1;
     ctx->indexed = true;
     if (stats) *stats = S;

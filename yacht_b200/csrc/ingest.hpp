@@ -36,6 +36,8 @@ struct Ingest {
     std::vector<int> empty_ids;
     // when read_sketches(..., assemble_flat = false): the parsed blocks stay where the workers left them
     std::vector<std::vector<uint64_t>> blocks;     // block b = sketches of files [b * kFilesPerBlock, ...)
+    std::vector<uint64_t> block_max;               // largest hash of block b
+    std::vector<uint8_t> block_sorted;             // 1 if every sketch of block b is ascending (sourmash writes them so)
     // called by a parser thread as soon as block b is complete (blocks[b] is final from then on): lets the caller
     // ship blocks to the GPU while later files are still being parsed
     std::function<void(uint32_t)> on_block;
@@ -70,6 +72,8 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
     const uint32_t n = (uint32_t)in.names.size();
     const uint32_t nblocks = (n + kFilesPerBlock - 1) / kFilesPerBlock;
     in.blocks.assign(nblocks, std::vector<uint64_t>());
+    in.block_max.assign(nblocks, 0);
+    in.block_sorted.assign(nblocks, 1);
     std::vector<std::vector<uint64_t>>& block_hashes = in.blocks;
     std::vector<uint32_t> sizes(n, 0);
     std::atomic<uint32_t> next{0};
@@ -101,6 +105,16 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
                     out.resize(before);
                 }
                 sizes[f] = (uint32_t)(out.size() - before);
+                // (while the sketch is still in cache) its largest hash and whether it is ascending: the multi-GPU host layer
+                // cuts sorted sketches by hash range with two binary searches
+                uint64_t mx = in.block_max[b];
+                bool asc = true;
+                for (size_t k = before; k < out.size(); k++) {
+                    mx = std::max(mx, out[k]);
+                    asc &= k == before || out[k - 1] <= out[k];
+                }
+                in.block_max[b] = mx;
+                if (!asc) in.block_sorted[b] = 0;
             }
             block_hashes[b] = std::move(out);
             if (in.on_block) in.on_block(b);

@@ -14,9 +14,10 @@
 // program exits non-zero if no B200 is available.
 //
 // Multi-GPU: every visible device (or the first YACHT_NUM_GPUS of them) is one rank (a host thread) of the library's
-// sharded train step: it holds the sketches of a contiguous range of files only, the index build is split by hash
-// range and exchanged by the kernels over NVLink, the pairwise count by query rows, the pair lists are gathered over
-// NCCL (include/yacht_gpu.h: ygpu_comm_init / ygpu_upload_finish_sharded / ygpu_train_step_sharded).
+// sharded train step: it holds, of every sketch, the hashes of its hash range (cut out of the parsed, sorted sketches
+// on the host), builds the index of that range locally and sends the work items to the ranks that own the query rows
+// over NVLink; the pair lists are gathered over NCCL (include/yacht_gpu.h: ygpu_comm_init /
+// ygpu_load_sketches_hashrange / ygpu_train_step_sharded).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -195,12 +196,11 @@ int main(int argc, char** argv) {
     bool q_done = false;
     std::atomic<int> upload_rc{0};
     std::vector<std::thread> uploaders;
-    // Multi-GPU: rank d (one thread per GPU) holds the sketches of a contiguous range of file BLOCKS -- the split is by file
-    // count, fixed before any file is parsed, so parsed blocks can travel to their GPU while later files are still read.
+    // Multi-GPU: rank d (one thread per GPU) will hold, of every sketch, the hashes of its hash range (cut on the host once all
+    // files are parsed); a single GPU receives the parsed blocks while later files are still being read.
     const uint32_t nblocks_total = (n + yingest::kFilesPerBlock - 1) / yingest::kFilesPerBlock;
-    std::vector<uint32_t> blk_lo;        // first block of rank d (ndev + 1 entries)
-    auto owner_of_block = [&](uint32_t b) { return (int)(std::upper_bound(blk_lo.begin(), blk_lo.end(), b) - blk_lo.begin()) - 1; };
     uint8_t comm_id[YGPU_COMM_ID_BYTES];
+    std::atomic<bool> want_stream{false};
     if (stream_upload)
         in.on_block = [&](uint32_t b) {
             { std::lock_guard<std::mutex> lk(q_mu); q_blocks.push_back(b); }
@@ -213,8 +213,6 @@ int main(int argc, char** argv) {
         nd = std::max(1, std::min<int>(nd, (int)std::max<uint32_t>(nblocks_total, 1)));
         ctxs.assign(nd, nullptr);
         res.resize(nd);
-        blk_lo.resize(nd + 1);
-        for (int d = 0; d <= nd; d++) blk_lo[d] = (uint32_t)((uint64_t)nblocks_total * d / nd);
         if (nd > 1 && ygpu_comm_get_unique_id(comm_id)) {
             res[0].rc = -1; res[0].err = ygpu_last_error(nullptr);
             ndev = nd;
@@ -228,16 +226,16 @@ int main(int argc, char** argv) {
                 if (nd > 1) {
                     res[d].rc = ygpu_comm_init(ctxs[d], d, nd, comm_id);
                     if (res[d].rc) { res[d].err = ygpu_last_error(ctxs[d]); return; }
-                }
-                if (stream_upload) {
+                } else if (stream_upload) {
                     res[d].rc = ygpu_upload_begin(ctxs[d]);
                     if (res[d].rc) res[d].err = ygpu_last_error(ctxs[d]);
                 }
             });
         for (auto& t : th) t.join();
         ndev = nd;
-        if (!stream_upload) return;
-        for (int d = 0; d < nd; d++) if (res[d].rc) return;
+        if (!stream_upload || nd > 1) return;
+        if (res[0].rc) return;
+        want_stream = true;
         const int nu = std::max(2, std::min(4, args.number_of_threads / 4));
         for (int k = 0; k < nu; k++)
             uploaders.emplace_back([&, k, nu]() {
@@ -251,7 +249,7 @@ int main(int argc, char** argv) {
                         b = q_blocks.front();
                         q_blocks.pop_front();
                     }
-                    const int rc = ygpu_upload_block(ctxs[owner_of_block(b)], b, in.blocks[b].data(), in.blocks[b].size());
+                    const int rc = ygpu_upload_block(ctxs[0], b, in.blocks[b].data(), in.blocks[b].size());
                     if (rc) upload_rc = rc;
                 }
             });
@@ -289,13 +287,28 @@ int main(int argc, char** argv) {
             return 5;
         }
     const size_t nb = in.blocks.size();
-    std::vector<uint32_t> g_lo(ndev + 1);            // genome range of rank d
-    for (int d = 0; d <= ndev; d++) g_lo[d] = (uint32_t)std::min<uint64_t>((uint64_t)blk_lo[d] * yingest::kFilesPerBlock, n);
     std::vector<const uint64_t*> block_ptrs(nb);
     std::vector<uint64_t> block_lens(nb);
     for (size_t b = 0; b < nb; b++) { block_ptrs[b] = in.blocks[b].data(); block_lens[b] = in.blocks[b].size(); }
-    // One thread per GPU from here on.  With several GPUs each rank finishes its sharded load (collective), then runs the
-    // library's sharded train step; every rank ends up with the complete pair list and rank 0's is written out.
+    // query rows of rank d: contiguous genome ranges of nearly equal hash counts; hash range of rank d: equal-width pieces
+    // of [0, largest hash] (FracMinHash hashes are uniform below max_hash)
+    std::vector<uint32_t> g_lo(ndev + 1, n);
+    g_lo[0] = 0;
+    {
+        const uint64_t Tall = in.offsets[n];
+        int d = 1;
+        for (uint32_t g = 0; g < n && d < ndev; g++)
+            while (d < ndev && in.offsets[g + 1] * (uint64_t)ndev >= Tall * (uint64_t)d) g_lo[d++] = g + 1;
+    }
+    uint64_t max_hash = 0;
+    for (size_t b = 0; b < nb; b++) max_hash = std::max(max_hash, in.block_max[b]);
+    std::vector<uint64_t> cuts(ndev + 1, ~0ull);
+    for (int d = 0; d < ndev; d++) cuts[d] = (uint64_t)(((unsigned __int128)max_hash + 1) * (unsigned)d / (unsigned)ndev);
+    std::vector<uint32_t> sizes32(n);
+    for (uint32_t g = 0; g < n; g++) sizes32[g] = (uint32_t)(in.offsets[g + 1] - in.offsets[g]);
+    // One thread per GPU from here on.  With several GPUs each rank cuts its share out of the parsed sketches, loads it
+    // (collective) and runs the library's sharded train step; every rank ends up with the complete pair list and rank 0's is
+    // written out.
     std::vector<ygpu_pair> pairs;
     ygpu_index_stats S{};
     bool sharded_refused = false;
@@ -306,27 +319,36 @@ int main(int argc, char** argv) {
             th.emplace_back([&, d]() {
                 DeviceResult& r = res[d];
                 ygpu_ctx* c = ctxs[d];
-                std::vector<uint64_t> block_dst(nb, 0);
-                const uint64_t slice0 = in.offsets[g_lo[d]];
-                for (size_t b = blk_lo[d]; b < blk_lo[d + 1]; b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)] - slice0;
                 if (ndev == 1) {
-                    if (stream_upload)
+                    std::vector<uint64_t> block_dst(nb, 0);
+                    for (size_t b = 0; b < nb; b++) block_dst[b] = in.offsets[std::min<size_t>(b * yingest::kFilesPerBlock, n)];
+                    if (want_stream)
                         r.rc = upload_rc ? (int)upload_rc : ygpu_upload_finish(c, block_dst.data(), (uint32_t)nb, in.offsets.data(), n);
                     else
                         r.rc = ygpu_load_sketch_blocks(c, block_ptrs.data(), block_lens.data(), (uint32_t)nb, in.offsets.data(), n);
                     if (!r.rc) r.rc = ygpu_build_index(c, &r.stats);
                     if (!r.rc) r.rc = ygpu_pairwise_flag(c, args.containment_threshold, 0, n, &r.pairs, &r.n_pairs);
                 } else {
-                    if (stream_upload) {
-                        r.rc = upload_rc ? (int)upload_rc
-                                         : ygpu_upload_finish_sharded(c, block_dst.data(), (uint32_t)nb, in.offsets.data(), n, g_lo[d], g_lo[d + 1]);
-                    } else {
-                        // (debug path) assemble this rank's slice on the host
-                        std::vector<uint64_t> flat;
-                        flat.reserve(in.offsets[g_lo[d + 1]] - slice0);
-                        for (size_t b = blk_lo[d]; b < blk_lo[d + 1]; b++) flat.insert(flat.end(), in.blocks[b].begin(), in.blocks[b].end());
-                        r.rc = ygpu_load_sketches_sharded(c, flat.data(), in.offsets.data(), n, g_lo[d], g_lo[d + 1]);
+                    yingest::pin_worker(d * std::max(1, args.number_of_threads / ndev));
+                    const uint64_t lo = cuts[d], hi = cuts[d + 1];
+                    const bool last = d == ndev - 1;
+                    std::vector<uint64_t> part_off((size_t)n + 1, 0), part;
+                    part.reserve((size_t)(in.offsets[n] / ndev + in.offsets[n] / (16 * ndev) + 1024));
+                    for (uint32_t g = 0; g < n; g++) {
+                        const size_t b = g / yingest::kFilesPerBlock;
+                        const uint64_t* sk = in.blocks[b].data() + (in.offsets[g] - in.offsets[b * yingest::kFilesPerBlock]);
+                        const uint64_t* se = sk + sizes32[g];
+                        if (in.block_sorted[b]) {
+                            const uint64_t* a0 = std::lower_bound(sk, se, lo);
+                            const uint64_t* a1 = last ? se : std::lower_bound(a0, se, hi);
+                            part.insert(part.end(), a0, a1);
+                        } else {
+                            for (const uint64_t* x = sk; x < se; x++)
+                                if (*x >= lo && (last || *x < hi)) part.push_back(*x);
+                        }
+                        part_off[g + 1] = part.size();
                     }
+                    r.rc = ygpu_load_sketches_hashrange(c, part.data(), part_off.data(), sizes32.data(), n, g_lo[d], g_lo[d + 1]);
                     if (!r.rc) {
                         r.rc = ygpu_train_step_sharded(c, args.containment_threshold, &r.stats, &r.n_pairs);
                         if (!r.rc && d == 0 && r.n_pairs) {

@@ -114,3 +114,21 @@ def exchange_plan(hist_all: np.ndarray) -> dict:
 def exchange_capacity(total: int, nranks: int, nb: int) -> int:
     """Words a rank's exchange buffer holds (ygpu_train_step_sharded): its share plus the digit granularity of the split."""
     return total // nranks + 2 * (total // max(nb, 1)) + 3 * 4096
+
+
+# ---- hash-range residency (ygpu_load_sketches_hashrange): cut every sketch at the same hash values ----------------------------
+def hash_cuts(max_hash: int, nranks: int) -> np.ndarray:
+    """nranks + 1 cut values: rank r holds the hashes in [cuts[r], cuts[r + 1]).  FracMinHash hashes are uniform below max_hash
+    by construction, so equal-width ranges hold equal shares."""
+    top = int(max_hash) + 1
+    return np.array([top * r // nranks for r in range(nranks)] + [2 ** 64 - 1], dtype=np.uint64)
+
+
+def hashrange_share(hashes: np.ndarray, offsets: np.ndarray, lo: int, hi: int, last: bool = False):
+    """(part_hashes, part_offsets) of the hashes h with lo <= h < hi (<= when `last`), sketch by sketch, order preserved."""
+    hashes = np.asarray(hashes, dtype=np.uint64)
+    keep = hashes >= np.uint64(lo)
+    keep &= (hashes <= np.uint64(hi)) if last else (hashes < np.uint64(hi))
+    c = np.zeros(hashes.shape[0] + 1, dtype=np.uint64)
+    np.cumsum(keep, out=c[1:])
+    return hashes[keep], c[np.asarray(offsets).astype(np.int64)]

@@ -14,6 +14,7 @@
 #include "comm.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <unistd.h>
 #include <cstdio>
 #include <cstring>
@@ -91,6 +92,9 @@ extern "C" int ygpu_comm_init(ygpu_ctx* ctx, int rank, int nranks, const uint8_t
     if (!api.ok) return ygpu_fail(ctx, YGPU_ERR_STATE, "%s", api.err.c_str());
     YG_CUDA(ctx, cudaSetDevice(ctx->device));
     ygpu_comm_destroy(ctx);
+    // Only a few hundred bytes per collective ever go through NCCL here; its NVLink-SHARP (NVLS) set-up costs seconds of
+    // communicator start-up on NVSwitch systems and buys nothing for them (not overridden when the caller has set it).
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
     ygpu_comm* c = new (std::nothrow) ygpu_comm();
     if (!c) return ygpu_fail(ctx, YGPU_ERR_NOMEM, "out of host memory");
     c->rank = rank;

@@ -735,6 +735,7 @@ constexpr int G2_WIN = 1024;                      // words of the 16-byte aligne
 constexpr uint32_t G2_MAXM = G2_WIN - 2;          // largest bucket this kernel takes
 constexpr int G2_NSUB = 1 << GK_SUBBITS;          // 2048 sub-bucket counters = 8 per thread
 constexpr uint32_t IG_MAXL = 16;                  // sharded build: groups up to this size travel as self-contained items
+constexpr uint64_t IG_ROW_MUL = (IG_MAXL - 1 + 2) / 3;   // ... so one shared hash is worth at most this many items of a query row
 
 struct __align__(16) G2Smem {
     uint64_t stage[G2_WIN];                       // the bucket's words (bulk copy target)
@@ -1117,8 +1118,8 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
 // sharded build, receiving side.  Work items arrive (a) ready-made in the item inbox: region q holds ilens[q * n_regions + me]
 // items of rank q for rows of this rank; (b) as the posting stream of the larger groups: N regions of `cap` slots, region q holding
 // lens[q] entries, every rank holds all of it and derives the (indirect) items of its own rows.  Row g's list lives at
-// row_ptr[g] with room for 2 * |S_g| + 8 items (k2s_sizes); a row that would need more (nearly all of its hashes in groups of
-// 9..16 genomes) raises *overflow and the step is refused -- callers then run the database on one GPU.
+// row_ptr[g] with room for IG_ROW_MUL * |S_g| + 8 items (k2s_sizes), which cannot be exceeded without in-sketch duplicates; if it
+// is, *overflow is raised and the step is refused -- callers then run the database on one GPU.
 __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ items, const uint32_t* __restrict__ rows,
                                                 const unsigned long long* __restrict__ ilens, int n_regions, int me, uint64_t icap,
                                                 const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ sizes,
@@ -1131,7 +1132,7 @@ __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ ite
             const uint32_t g = rows[base + i];
             const uint64_t item = items[base + i];
             const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            if (slot < 2ull * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
+            if (slot < IG_ROW_MUL * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
             else *overflow = 1ull;
         }
     }
@@ -1159,7 +1160,7 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
                 item = ((x + 1) << 32) | ((uint64_t)r << 2);
             }
             const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
-            if (slot < 2ull * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
+            if (slot < IG_ROW_MUL * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
             else *overflow = 1ull;
         }
     }
@@ -1256,8 +1257,8 @@ __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hi
 }
 
 // sketch sizes of ALL genomes, the slice-relative offsets (genome-range residency) and the work-list starts of this rank's
-// query rows [g_begin, g_end): row g may receive up to 2 * |S_g| + 8 items (one per shared hash for pairs and groups up to 4,
-// ceil(followers / 3) for a member of a group of up to 16; more is refused, see k2_inbox)
+// query rows [g_begin, g_end): row g has room for IG_ROW_MUL * |S_g| + 8 items (a shared hash is worth ceil(followers / 3) items,
+// at most IG_ROW_MUL for a group of IG_MAXL; the indirect items of larger groups are one per hash)
 __global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ offsets, uint32_t n, uint32_t g_begin, uint32_t g_end,
                                                  uint32_t* __restrict__ sizes, uint64_t* __restrict__ row_begin_local,
                                                  uint64_t* __restrict__ offsets_local) {
@@ -1265,7 +1266,7 @@ __global__ void __launch_bounds__(256) k2s_sizes(const uint64_t* __restrict__ of
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g <= n; g += gridDim.x * blockDim.x) {
         if (g < n) {
             sizes[g] = (uint32_t)(offsets[g + 1] - offsets[g]);
-            row_begin_local[g] = (g >= g_begin && g < g_end) ? 2ull * (offsets[g] - o0) + 8ull * (g - g_begin) : 0ull;
+            row_begin_local[g] = (g >= g_begin && g < g_end) ? IG_ROW_MUL * (offsets[g] - o0) + 8ull * (g - g_begin) : 0ull;
         }
         if (offsets_local && g >= g_begin && g <= g_end) offsets_local[g - g_begin] = offsets[g] - o0;
     }
@@ -1778,7 +1779,7 @@ int ygpu_sharded_finish(ygpu_ctx* ctx, const uint64_t* offsets, uint32_t n, uint
     ctx->n = n; ctx->T = T; ctx->T_global = Tg; ctx->g_begin = g_begin; ctx->g_end = g_end; ctx->sharded = true;
     ctx->shard_mode = 0;
     ctx->max_sketch_global = mx;
-    ctx->row_items_need = 2 * T + 8ull * (g_end - g_begin) + 16;
+    ctx->row_items_need = IG_ROW_MUL * T + 8ull * (g_end - g_begin) + 16;
     YG_CHECK(dev_alloc(ctx, &ctx->d_offsets, (uint64_t)n + 1));
     YG_CHECK(dev_alloc(ctx, &ctx->d_sizes, n));
     YG_CHECK(dev_alloc(ctx, &ctx->d_row_begin_local, (uint64_t)n + 1));
@@ -1873,10 +1874,10 @@ static int hashrange_load(ygpu_ctx* ctx, const uint64_t* part_hashes, const uint
     const uint64_t T = part_offsets[n];
     if (Tg >= (1ull << 32)) return ygpu_fail(ctx, YGPU_ERR_ARG, "total hashes %llu >= 2^32 not supported", (unsigned long long)Tg);
     if (T && !part_hashes) return ygpu_fail(ctx, YGPU_ERR_ARG, "load_sketches_hashrange: NULL hashes");
-    // work-list starts of this rank's query rows: room for 2 * |S_g| + 8 items per row (k2s_sizes has the same rule)
+    // work-list starts of this rank's query rows: room for IG_ROW_MUL * |S_g| + 8 items per row (k2s_sizes has the same rule)
     std::vector<uint64_t> rb((size_t)n + 1, 0);
     uint64_t acc = 0;
-    for (uint32_t g = row_begin; g < row_end; g++) { rb[g] = acc; acc += 2ull * sizes[g] + 8ull; }
+    for (uint32_t g = row_begin; g < row_end; g++) { rb[g] = acc; acc += IG_ROW_MUL * sizes[g] + 8ull; }
     ctx->n = n; ctx->T = T; ctx->T_global = Tg; ctx->g_begin = row_begin; ctx->g_end = row_end; ctx->sharded = true;
     ctx->shard_mode = 1;
     ctx->max_sketch_global = mx;
@@ -2207,7 +2208,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         if (ilens[q] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d sent %llu work items to rank %d, the inbox region holds %llu", q / N, ilens[q], q % N, (unsigned long long)cap);
     my_items = ovf_tm[0];
     info[SHI_TMINE] = ovf_tm[1];
-    if (my_items) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row received more work items than 2 x its sketch size + 8 (dense groups of 9..16 genomes): run this database on one GPU");
+    if (my_items) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row received more work items than its list holds (sketches with repeated hashes): run this database on one GPU");
     if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a rank owns %llu words, the exchange buffers hold %llu", info[SHI_TMINE], (unsigned long long)cap);
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
     if (largest > G2_MAXM)

@@ -208,8 +208,12 @@ int main(int argc, char** argv) {
         };
     std::thread gpu_init([&]() {
         int nd = ygpu_device_count();
-        if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) nd = std::min(nd, v); }
         if (nd < 1) return;
+        // How many GPUs: YACHT_NUM_GPUS when set; otherwise one GPU up to 200 000 sketches -- an 85 205-genome database is
+        // indexed and compared in ~15 ms on one B200, while bringing up a communicator over several GPUs costs seconds --
+        // and every visible GPU beyond that.
+        if (const char* e = getenv("YACHT_NUM_GPUS")) { int v = atoi(e); if (v >= 1) nd = std::min(nd, v); }
+        else if (n <= 200000u) nd = 1;
         nd = std::max(1, std::min<int>(nd, (int)std::max<uint32_t>(nblocks_total, 1)));
         ctxs.assign(nd, nullptr);
         res.resize(nd);

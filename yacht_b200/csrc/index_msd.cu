@@ -660,7 +660,7 @@ __device__ __forceinline__ void group_bucket(const GroupArgs& a, const uint32_t 
             } else {
                 item = (((uint64_t)bb + x + 1) << 32) | ((uint64_t)rem << 2);
             }
-            const uint32_t slot = (uint32_t)atomicAdd(&a.row_cnt[g], 1ull);
+            const uint32_t slot = atomicAdd(reinterpret_cast<unsigned int*>(&a.row_cnt[g]), 1u);
             const uint32_t dst = (uint32_t)a.row_off[g];
             if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued one bucket ago
             pd.item = item; pd.dst = dst; pd.slot = slot; pd.has = true;
@@ -740,10 +740,9 @@ constexpr uint64_t IG_ROW_MUL = (IG_MAXL - 1 + 2) / 3;   // ... so one shared ha
 struct __align__(16) G2Smem {
     uint64_t stage[G2_WIN];                       // the bucket's words (bulk copy target)
     uint64_t cand[G2_WIN + 4];                    // candidates, sub-bucket by sub-bucket: remaining hash << 32 | genome id
-    uint32_t cnt[G2_NSUB];                        // sub-bucket sizes (zero between buckets)
-    uint32_t ext[G2_WIN];                         // per candidate: start of its sub-bucket | size << 16
+    uint32_t cnt[G2_NSUB];                        // sub-bucket sizes; after phase B: candidate-array start | size << 16 (zero between buckets)
+    uint32_t ext[G2_WIN];                         // per candidate of a sub-bucket of >= 3 words: start of its sub-bucket | size << 16
     uint32_t stg_g[G2_WIN + 4];                   // ordered groups: genome id
-    unsigned short start2[G2_NSUB + 8];           // candidate-array start of every sub-bucket
     unsigned short stg_r[G2_WIN];                 // ordered groups: members that follow | 0x8000 posting wanted | 0x4000 hole
     uint32_t wsum[G2_THREADS / 32];
     uint32_t next[2][2];                          // [parity]{first word, words} of the bucket after this one (words = 0: none)
@@ -752,8 +751,8 @@ struct __align__(16) G2Smem {
     uint64_t mbar;
 };
 
-template <bool STREAM>
-__global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
+template <bool STREAM, int MIN_CTAS>
+__global__ void __launch_bounds__(G2_THREADS, MIN_CTAS) k2_group2(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     G2Smem& sm = *reinterpret_cast<G2Smem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -828,15 +827,18 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
         }
         __syncthreads();                                             // stage is free: request the next bucket
         if (tid == 0) advance(par ^ 1u);
-        // ---- B: scan the sizes of sub-buckets with >= 2 words (and reset the counters for the next bucket) ----------
+        // ---- B: candidate-array starts of the sub-buckets with >= 2 words, in TWO regions: sub-buckets of exactly two words
+        //      (most of them: two genomes sharing a hash, or two hashes that merely share 11 bits) come first, as aligned
+        //      pairs; phase D settles those with one compare.  Larger sub-buckets follow.  One packed scan serves both
+        //      regions (16 bits each); the counter of a sub-bucket is replaced by start | size << 16 (0: no candidates).
+        uint32_t nx, ncand;
         {
             uint4* c4 = reinterpret_cast<uint4*>(&sm.cnt[8 * tid]);
-            uint4 c0 = c4[0], c1 = c4[1];
-            c4[0] = make_uint4(0u, 0u, 0u, 0u);
-            c4[1] = make_uint4(0u, 0u, 0u, 0u);
-            c0.x = c0.x >= 2 ? c0.x : 0u; c0.y = c0.y >= 2 ? c0.y : 0u; c0.z = c0.z >= 2 ? c0.z : 0u; c0.w = c0.w >= 2 ? c0.w : 0u;
-            c1.x = c1.x >= 2 ? c1.x : 0u; c1.y = c1.y >= 2 ? c1.y : 0u; c1.z = c1.z >= 2 ? c1.z : 0u; c1.w = c1.w >= 2 ? c1.w : 0u;
-            const uint32_t sum = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+            const uint4 c0 = c4[0], c1 = c4[1];
+            uint32_t c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            uint32_t sum = 0;                                        // words of pair sub-buckets | words of larger ones << 16
+#pragma unroll
+            for (int i = 0; i < 8; i++) sum += c[i] == 2 ? 2u : (c[i] >= 3 ? (c[i] << 16) : 0u);
             uint32_t inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -848,10 +850,20 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
             const uint4 wa = *reinterpret_cast<const uint4*>(&sm.wsum[0]), wb = *reinterpret_cast<const uint4*>(&sm.wsum[4]);
             const uint32_t wp = (warp > 0 ? wa.x : 0u) + (warp > 1 ? wa.y : 0u) + (warp > 2 ? wa.z : 0u) + (warp > 3 ? wa.w : 0u) +
                                 (warp > 4 ? wb.x : 0u) + (warp > 5 ? wb.y : 0u) + (warp > 6 ? wb.z : 0u);
-            const uint32_t p0 = wp + inc - sum;
-            const uint32_t p1 = p0 + c0.x, p2 = p1 + c0.y, p3 = p2 + c0.z, p4 = p3 + c0.w, p5 = p4 + c1.x, p6 = p5 + c1.y, p7 = p6 + c1.z;
-            *reinterpret_cast<uint4*>(&sm.start2[8 * tid]) = make_uint4(p0 | (p1 << 16), p2 | (p3 << 16), p4 | (p5 << 16), p6 | (p7 << 16));
-            if (tid == G2_THREADS - 1) sm.start2[G2_NSUB] = (unsigned short)(p7 + c1.w);
+            const uint32_t tot = wa.x + wa.y + wa.z + wa.w + wb.x + wb.y + wb.z + wb.w;
+            nx = tot & 0xffffu;
+            ncand = nx + (tot >> 16);
+            const uint32_t ex = wp + inc - sum;
+            uint32_t px = ex & 0xffffu, py = nx + (ex >> 16);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t v = 0;
+                if (c[i] == 2) { v = px | (2u << 16); px += 2; }
+                else if (c[i] >= 3) { v = py | (c[i] << 16); py += c[i]; }
+                c[i] = v;
+            }
+            c4[0] = make_uint4(c[0], c[1], c[2], c[3]);
+            c4[1] = make_uint4(c[4], c[5], c[6], c[7]);
         }
         __syncthreads();
         // ---- C: candidates -> dense array, sub-bucket by sub-bucket; a word alone in its sub-bucket is a singleton ----
@@ -859,14 +871,13 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (sr[k] != 0xFFFFFFFFu) {
-                const uint32_t s = sr[k] & 0xffffu;
-                const uint32_t lo = sm.start2[s], hi = sm.start2[s + 1];
-                if (hi > lo) {
-                    const uint32_t pos = lo + (sr[k] >> 16);
+                const uint32_t v = sm.cnt[sr[k] & 0xffffu];
+                if (v) {
+                    const uint32_t pos = (v & 0xffffu) + (sr[k] >> 16);
                     const uint32_t K = (uint32_t)(e[k] >> a.gb) & kmask;
                     const uint32_t G = (uint32_t)e[k] & gmask;
                     sm.cand[pos] = ((uint64_t)K << 32) | (uint64_t)G;
-                    sm.ext[pos] = lo | ((hi - lo) << 16);
+                    if (v >= (3u << 16)) sm.ext[pos] = v;
                 } else {
                     solo++;
                 }
@@ -875,9 +886,28 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
         n_heads += solo;
         n_single += solo;
         __syncthreads();
-        // ---- D: every candidate scans its sub-bucket once: group size, rank in the group, rank in the sub-bucket -----
-        const uint32_t ncand = sm.start2[G2_NSUB];
-        for (uint32_t q = tid; q < ncand; q += G2_THREADS) {
+        {   // the counters are free again: zero for the next bucket
+            uint4* c4 = reinterpret_cast<uint4*>(&sm.cnt[8 * tid]);
+            c4[0] = make_uint4(0u, 0u, 0u, 0u);
+            c4[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- D: group size, rank in the group (by genome id), slot in the (hash, genome) order of the sub-bucket ------------
+        // pairs: the partner is the other word of the aligned pair
+        for (uint32_t q = tid; q < nx; q += G2_THREADS) {
+            const uint64_t wq = sm.cand[q], wp = sm.cand[q ^ 1u];
+            const bool same = (uint32_t)(wp >> 32) == (uint32_t)(wq >> 32);
+            const bool tie = (wp == wq) & (q & 1u);                          // same genome too (in-sketch duplicate): the even slot goes first
+            const bool before = (wp < wq) | tie;
+            const uint32_t pos = (q & ~1u) + (before ? 1u : 0u);
+            sm.stg_g[pos] = (uint32_t)wq;
+            sm.stg_r[pos] = same ? (unsigned short)((before ? 0u : 1u) | (can_inline ? 0u : 0x8000u)) : (unsigned short)0x4000u;
+            n_heads += !(same & before);
+            n_single += !same;
+            n_dups += tie;
+            if (same & !before) n_w += 4ull;
+        }
+        // larger sub-buckets: every candidate scans its sub-bucket once
+        for (uint32_t q = nx + tid; q < ncand; q += G2_THREADS) {
             const uint64_t wq = sm.cand[q];
             const uint32_t x = sm.ext[q];
             const uint32_t lo = x & 0xffffu, c = x >> 16;
@@ -1006,7 +1036,7 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k2_group2(const GroupArgs a) {
                 } else {
                     item = (((uint64_t)bb + x + 1) << 32) | ((uint64_t)rem << 2);
                 }
-                const uint32_t slot = (uint32_t)atomicAdd(&a.row_cnt[g], 1ull);
+                const uint32_t slot = atomicAdd(reinterpret_cast<unsigned int*>(&a.row_cnt[g]), 1u);
                 const uint32_t dst = (uint32_t)a.row_off[g];
                 if (pd.has) a.row_items[(uint64_t)pd.dst + pd.slot] = pd.item;     // the append issued two items ago
                 pd = pd2;
@@ -1099,7 +1129,7 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
             } else {
                 item = ((post_base + i + 1) << 32) | (rem << 2);
             }
-            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned int*>(&row_cnt[g]), 1u);   // (32-bit: twice the L2 atomic rate; T < 2^32)
             row_items[row_off[g] + slot] = item;
         }
     }
@@ -1131,7 +1161,7 @@ __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ ite
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
             const uint32_t g = rows[base + i];
             const uint64_t item = items[base + i];
-            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned int*>(&row_cnt[g]), 1u);   // (32-bit: twice the L2 atomic rate; T < 2^32)
             if (slot < IG_ROW_MUL * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
             else *overflow = 1ull;
         }
@@ -1159,7 +1189,7 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
             } else {
                 item = ((x + 1) << 32) | ((uint64_t)r << 2);
             }
-            const unsigned long long slot = atomicAdd(&row_cnt[g], 1ull);
+            const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned int*>(&row_cnt[g]), 1u);   // (32-bit: twice the L2 atomic rate; T < 2^32)
             if (slot < IG_ROW_MUL * sizes[g] + 8ull) row_items[row_ptr[g] + slot] = item;
             else *overflow = 1ull;
         }
@@ -1508,11 +1538,13 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, bool partition_only
         g.m_lo = 0;
         if (fast2 && nbk) {
             const size_t smem2 = sizeof(G2Smem);
-            YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            // 5 CTAs per SM (48 registers, a 16-byte spill) against 4 (60 registers): test hook "group_ctas"
+            auto kern2 = ctx->group_ctas == 4 ? k2_group2<false, 4> : k2_group2<false, 5>;
+            YG_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             int occ2 = 1;
-            YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2_group2<false>, G2_THREADS, smem2));
+            YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, G2_THREADS, smem2));
             const int grid2 = (int)std::min<uint64_t>(nbk, (uint64_t)ctx->num_sms * std::max(occ2, 1));
-            k2_group2<false><<<grid2, G2_THREADS, smem2, st>>>(g);
+            kern2<<<grid2, G2_THREADS, smem2, st>>>(g);
             YG_CUDA(ctx, cudaGetLastError());
             ctx->tm.n_kernel_launches += 1;
             g.m_lo = G2_MAXM;
@@ -2147,11 +2179,11 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         for (int q = 0; q <= N; q++) g.row_bounds[q] = ctx->sh_row_bounds[q];
         g.icap = cap; g.item_region = (uint64_t)rank * cap; g.icursor = &ctx->d_sh_info[SHI_ICUR];
         const size_t smem2 = sizeof(G2Smem);
-        YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int occ2 = 1;
-        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2_group2<true>, G2_THREADS, smem2));
+        YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2_group2<true, 4>, G2_THREADS, smem2));
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[7], st));
-        k2_group2<true><<<ctx->num_sms * std::max(occ2, 1), G2_THREADS, smem2, st>>>(g);
+        k2_group2<true, 4><<<ctx->num_sms * std::max(occ2, 1), G2_THREADS, smem2, st>>>(g);
         YG_CUDA(ctx, cudaGetLastError());
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
         ctx->tm.n_kernel_launches += 1;

@@ -1538,8 +1538,8 @@ int msd_build(ygpu_ctx* ctx, ygpu_index_stats* S, int* used, bool partition_only
         g.m_lo = 0;
         if (fast2 && nbk) {
             const size_t smem2 = sizeof(G2Smem);
-            // 5 CTAs per SM (48 registers, a 16-byte spill) against 4 (60 registers): test hook "group_ctas"
-            auto kern2 = ctx->group_ctas == 4 ? k2_group2<false, 4> : k2_group2<false, 5>;
+            // 4 CTAs per SM (64 registers) against 5 (48 registers, spills 88 bytes: measured slower): test hook "group_ctas"
+            auto kern2 = ctx->group_ctas == 5 ? k2_group2<false, 5> : k2_group2<false, 4>;
             YG_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             int occ2 = 1;
             YG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern2, G2_THREADS, smem2));

@@ -42,6 +42,9 @@ def _context() -> _lib.GpuContext:
     return _ctx
 
 
+_last_counts = None      # (loaded database key, sample key, counts) of the last overlap probe
+
+
 def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str, num_threads: int) -> None:
     """Make the manifest's genomes (row order = genome id) resident on the device; cached per manifest."""
     global _loaded_key
@@ -57,9 +60,11 @@ def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str
     else:
         hashes, offsets, n_bad = _lib.read_signatures(paths, max(1, int(num_threads)))
         if n_bad:
-            _log("WARNING", f"{n_bad} reference signature file(s) could not be opened; they count as empty sketches")
-        else:
-            dbcache.store(path_to_genome_temp_dir, md5sums, hashes, offsets)
+            # the reference loads every manifest signature through load_signature_with_ksize and raises when one is missing
+            # (utils.py:43-50); an absent file must not silently become an empty sketch here
+            raise ValueError(f"{n_bad} reference signature file(s) of the manifest could not be opened under "
+                             f"{os.path.join(path_to_genome_temp_dir, 'signatures')}")
+        dbcache.store(path_to_genome_temp_dir, md5sums, hashes, offsets)
     _context().load_sketches(hashes, offsets)
     _loaded_key = key
 
@@ -87,11 +92,16 @@ def get_organisms_with_nonzero_overlap(manifest: pd.DataFrame, sample_file: str,
     ctx = _context()
     names: List[str] = []
     rows = []
+    global _last_counts
+    _last_counts = None
     for sf in sample_sig_files:
         for sig in sigio.parse_signature_json(sigio._open_text(sf), sf):
             if sig.ksize != ksize or sig.scaled != scale:
                 continue
             counts = ctx.exclusive_hashes(sig.mins)
+            # one probe of the reference serves both steps: with the nontrivial genomes = those with overlap (what
+            # hypothesis_recovery passes on), the exclusive-hash counts of get_exclusive_hashes are already in `counts`
+            _last_counts = (_loaded_key, sig.mins.tobytes() if len(sig.mins) < (1 << 22) else (len(sig.mins), int(sig.mins[0]), int(sig.mins[-1])), counts)
             hit = np.flatnonzero(counts["n_overlap"] > 0)
             for g in hit:
                 rows.append((sig.name, sig.md5sum, manifest["organism_name"].iloc[int(g)], manifest["md5sum"].iloc[int(g)],
@@ -116,7 +126,13 @@ def get_exclusive_hashes(manifest: pd.DataFrame, nontrivial_organism_names: List
     _load_manifest_sketches(manifest, path_to_genome_temp_dir, num_threads)
     mask = keep.to_numpy().astype(np.uint8)
     sample_hashes = sample_sig.mins if hasattr(sample_sig, "mins") else np.asarray(list(sample_sig.minhash.hashes), dtype=np.uint64)
-    counts = _context().exclusive_hashes(sample_hashes, mask)
+    sample_hashes = np.ascontiguousarray(sample_hashes, dtype=np.uint64)
+    skey = sample_hashes.tobytes() if len(sample_hashes) < (1 << 22) else (len(sample_hashes), int(sample_hashes[0]), int(sample_hashes[-1]))
+    if (_last_counts is not None and _last_counts[0] == _loaded_key and _last_counts[1] == skey
+            and np.array_equal(_last_counts[2]["nontrivial"].astype(np.uint8), mask)):
+        counts = _last_counts[2]          # same sample, same nontrivial set: the overlap probe already computed them
+    else:
+        counts = _context().exclusive_hashes(sample_hashes, mask)
     ids = np.flatnonzero(mask)
     info = [(int(counts["n_exclusive"][g]), int(counts["n_match"][g])) for g in ids]
     return info, sub_manifest

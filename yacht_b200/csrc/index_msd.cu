@@ -47,6 +47,10 @@ constexpr int NB_MAX = 2048;        // digits per partition level
 constexpr uint32_t A_TARGET = 900;  // average elements per used final bucket (k2_group2 takes buckets of <= 1022)
 
 enum { SCM_PCUR = 8, SCM_ICUR = 9, SCM_MAXB = 10, SCM_STREAM = 12 };   // extra slots of ctx->d_scalars (SCM_MAXB uses two)
+// sharded step: the first REP_WORDS slots of d_scalars are one rank's report to the others (statistics, largest bucket, posting-
+// stream length, and from REP_ICUR the number of work items it sent to every rank); ONE all-gather after the grouping carries it
+enum { REP_ICUR = 16, REP_WORDS = 32 };
+static_assert(REP_ICUR + YG_MAX_RANKS <= REP_WORDS, "the report holds one item counter per rank");
 
 struct MsdPlan {
     int hb, gb, d1, d2, kb1;
@@ -1151,13 +1155,14 @@ __global__ void __launch_bounds__(256) k2_big_groups(const uint64_t* __restrict_
 // row_ptr[g] with room for IG_ROW_MUL * |S_g| + 8 items (k2s_sizes), which cannot be exceeded without in-sketch duplicates; if it
 // is, *overflow is raised and the step is refused -- callers then run the database on one GPU.
 __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ items, const uint32_t* __restrict__ rows,
-                                                const unsigned long long* __restrict__ ilens, int n_regions, int me, uint64_t icap,
+                                                const unsigned long long* __restrict__ report, int n_regions, int me, uint64_t icap,
                                                 const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ sizes,
                                                 unsigned long long* __restrict__ row_cnt, uint64_t* __restrict__ row_items,
                                                 unsigned long long* __restrict__ overflow) {
-    for (int q = 0; q < n_regions; q++) {
+    {
+        const int q = blockIdx.y;                 // one grid row per sending rank: the regions are worked off side by side
         const uint64_t base = (uint64_t)q * icap;
-        const uint64_t len = min((uint64_t)ilens[(size_t)q * n_regions + me], icap);
+        const uint64_t len = min((uint64_t)report[(size_t)q * REP_WORDS + REP_ICUR + me], icap);
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
             const uint32_t g = rows[base + i];
             const uint64_t item = items[base + i];
@@ -1169,12 +1174,13 @@ __global__ void __launch_bounds__(256) k2_inbox(const uint64_t* __restrict__ ite
 }
 
 __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restrict__ gid, const unsigned short* __restrict__ rem,
-                                                        const unsigned long long* __restrict__ lens, int n_regions, uint64_t cap,
+                                                        const unsigned long long* __restrict__ report, int n_regions, uint64_t cap,
                                                         uint32_t row_begin, uint32_t row_end, int can_inline, const uint64_t* __restrict__ row_ptr,
                                                         const uint32_t* __restrict__ sizes, unsigned long long* __restrict__ row_cnt,
                                                         uint64_t* __restrict__ row_items, unsigned long long* __restrict__ overflow) {
-    for (int q = 0; q < n_regions; q++) {
-        const uint64_t base = (uint64_t)q * cap, len = lens[q];
+    {
+        const int q = blockIdx.y;
+        const uint64_t base = (uint64_t)q * cap, len = report[(size_t)q * REP_WORDS + SCM_STREAM];
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
             const uint64_t x = base + i;
             const uint32_t r = rem[x];
@@ -1203,7 +1209,7 @@ __global__ void __launch_bounds__(256) k2_items_regions(const uint32_t* __restri
 // the level-1 scatter can store them there directly.  For the digits this rank owns it also lays out level 2 (bucket
 // bases and tile prefix in the GLOBAL digit numbering: foreign digits are simply empty).
 // slots of ctx->d_sh_info (LENS: [nranks] posting-stream lengths; ICUR: [nranks] items sent to every rank; ILENS: [nranks][nranks] all-gathered)
-enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_TMAX = 5, SHI_LENS = 8, SHI_ICUR = 64, SHI_ILENS = 96, SHI_WORDS = 512 };
+enum { SHI_DLO = 0, SHI_DHI = 1, SHI_TMINE = 2, SHI_BLO = 3, SHI_BHI = 4, SHI_TMAX = 5, SHI_LENS = 8, SHI_ICUR = 64, SHI_ILENS = 96, SHI_WORDS = 1024 };
 
 __global__ void __launch_bounds__(1024) k2s_prep(const uint32_t* __restrict__ hist_all, uint32_t nb, int nranks, int rank, int d2,
                                                  uint32_t* __restrict__ owner, uint32_t* __restrict__ cursor, uint32_t* __restrict__ base,
@@ -2067,9 +2073,8 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     uint32_t* cursor = base2 + ((uint64_t)p.nfb + 2);
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_msd_aux, 0, aux_words * sizeof(uint32_t), st));
-    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, 16 * sizeof(unsigned long long), st));
+    YG_CUDA(ctx, cudaMemsetAsync(ctx->d_scalars, 0, REP_WORDS * sizeof(unsigned long long), st));
     YG_CUDA(ctx, cudaMemsetAsync(ctx->d_row_cnt, 0, ((uint64_t)n + 1) * sizeof(unsigned long long), st));
-    YG_CUDA(ctx, cudaMemsetAsync(&ctx->d_sh_info[SHI_ICUR], 0, (size_t)YG_MAX_RANKS * sizeof(unsigned long long), st));
 
     // ---- 1. level 1.  Genome-range residency: on the resident slice, every word stored into its owner's buffer (NVLink).
     //         Hash-range residency: purely local -- this rank already holds exactly the hashes of its range. ---------------------
@@ -2177,7 +2182,7 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
             g.peer_item[q] = (uint64_t*)ctx->sh_peer_item[q]; g.peer_row[q] = (uint32_t*)ctx->sh_peer_row[q];
         }
         for (int q = 0; q <= N; q++) g.row_bounds[q] = ctx->sh_row_bounds[q];
-        g.icap = cap; g.item_region = (uint64_t)rank * cap; g.icursor = &ctx->d_sh_info[SHI_ICUR];
+        g.icap = cap; g.item_region = (uint64_t)rank * cap; g.icursor = &ctx->d_scalars[REP_ICUR];
         const size_t smem2 = sizeof(G2Smem);
         YG_CUDA(ctx, cudaFuncSetAttribute(k2_group2<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         int occ2 = 1;
@@ -2188,41 +2193,29 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         YG_CUDA(ctx, cudaEventRecord(ctx->evp[8], st));
         ctx->tm.n_kernel_launches += 1;
     }
-    // stream lengths of all ranks (the all-gather is also the barrier behind the stream stores)
-    unsigned long long* d_lens = &ctx->d_sh_info[SHI_LENS];
-    YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_scalars[SCM_STREAM], d_lens, sizeof(unsigned long long)));
+    // ONE all-gather of every rank's report (statistics, largest bucket, posting-stream length, items sent to every rank): it is
+    // also the barrier behind the item / stream stores of the grouping kernels
+    unsigned long long* d_rep = &ctx->d_sh_info[SHI_ILENS];         // [N][REP_WORDS]
+    YG_CHECK(ygpu_comm_allgather(ctx, ctx->d_scalars, d_rep, (size_t)REP_WORDS * sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
 
     // ---- 3. work lists of this rank's rows: the items the ranks sent (+ those derived from the posting stream of the larger
-    //         groups), laid out by count -> scan -> fill; statistics over all ranks ------------------------------------------------
-    unsigned long long* d_ilens = &ctx->d_sh_info[SHI_ILENS];
-    YG_CHECK(ygpu_comm_allgather(ctx, &ctx->d_sh_info[SHI_ICUR], d_ilens, (size_t)N * sizeof(unsigned long long)));
-    YG_CUDA(ctx, cudaEventRecord(ctx->evp[10], st));
+    //         groups) are appended to the rows' lists -------------------------------------------------------------------------------
     const int can_inl = p.gb <= YG_ITEM_INLINE_BITS ? 1 : 0;
-    const int grid_in = grid_for(ctx, std::max<uint64_t>(Tg / (4ull * N), 1), 256, 16);
+    const dim3 grid_in((unsigned)std::max(1, grid_for(ctx, std::max<uint64_t>(Tg / (4ull * N * N), 1), 256, 16) / 1), (unsigned)N);
     unsigned long long* d_ovf = &ctx->d_sh_info[42];
     YG_CUDA(ctx, cudaMemsetAsync(d_ovf, 0, sizeof(unsigned long long), st));
-    k2_inbox<<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_ilens, N, rank, cap, ctx->d_row_begin_local, ctx->d_sizes, ctx->d_row_cnt,
+    k2_inbox<<<grid_in, 256, 0, st>>>(ctx->d_inbox_item, ctx->d_inbox_row, d_rep, N, rank, cap, ctx->d_row_begin_local, ctx->d_sizes, ctx->d_row_cnt,
                                       ctx->d_row_items, d_ovf);
     YG_CUDA(ctx, cudaGetLastError());
-    k2_items_regions<<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_lens, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_begin_local,
+    k2_items_regions<<<grid_in, 256, 0, st>>>(ctx->d_post, ctx->d_st_rem, d_rep, N, cap, ctx->g_begin, ctx->g_end, can_inl, ctx->d_row_begin_local,
                                               ctx->d_sizes, ctx->d_row_cnt, ctx->d_row_items, d_ovf);
     YG_CUDA(ctx, cudaGetLastError());
     YG_CUDA(ctx, cudaEventRecord(ctx->evp[11], st));
     ctx->tm.n_kernel_launches += 2;
-    // scalars 0..3 (heads, singles, dups, W) summed over the ranks; slot SCM_MAXB(+1) = largest bucket (max)
-    unsigned long long* d_tot = &ctx->d_sh_info[24];
-    YG_CHECK(ygpu_comm_allreduce_u64(ctx, ctx->d_scalars, d_tot, 4, false));
-    YG_CHECK(ygpu_comm_allreduce_u64(ctx, &ctx->d_scalars[SCM_MAXB], d_tot + 4, 2, true));
-    // refusals must be unanimous (a rank that stopped here would leave the others waiting in the pair gather): the overflow flag
-    // and the largest number of words any rank owns, over all ranks
-    YG_CUDA(ctx, cudaMemcpyAsync(d_ovf + 1, &ctx->d_sh_info[SHI_TMINE], sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    YG_CHECK(ygpu_comm_allreduce_u64(ctx, d_ovf, d_ovf, 2, true));
-    unsigned long long tot[6], info[8], ilens[YG_MAX_RANKS * YG_MAX_RANKS], my_items = 0;
-    YG_CUDA(ctx, cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_sh_info, sizeof info, cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaMemcpyAsync(ilens, d_ilens, (size_t)N * N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    unsigned long long ovf_tm[2] = {0, 0};
-    YG_CUDA(ctx, cudaMemcpyAsync(ovf_tm, d_ovf, sizeof ovf_tm, cudaMemcpyDeviceToHost, st));
+    unsigned long long tot[6] = {0, 0, 0, 0, 0, 0}, rep[YG_MAX_RANKS * REP_WORDS], my_ovf = 0;
+    YG_CUDA(ctx, cudaMemcpyAsync(rep, d_rep, (size_t)N * REP_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(&my_ovf, d_ovf, sizeof my_ovf, cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->tm.ms_sort += elapsed(ctx, 0, 1);
@@ -2236,12 +2229,16 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
         ctx->tm.ms_items += el(10, 11);
         ctx->tm.ms_sync += el(3, 9) + el(8, 10);       // waiting for the peers behind the two exchanges (+ the collectives themselves)
     }
-    for (int q = 0; q < N * N; q++)
-        if (ilens[q] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d sent %llu work items to rank %d, the inbox region holds %llu", q / N, ilens[q], q % N, (unsigned long long)cap);
-    my_items = ovf_tm[0];
-    info[SHI_TMINE] = ovf_tm[1];
-    if (my_items) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row received more work items than its list holds (sketches with repeated hashes): run this database on one GPU");
-    if (info[SHI_TMINE] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a rank owns %llu words, the exchange buffers hold %llu", info[SHI_TMINE], (unsigned long long)cap);
+    // every rank holds every report: sums / maxima and all refusals below are unanimous
+    for (int q = 0; q < N; q++) {
+        const unsigned long long* r = rep + (size_t)q * REP_WORDS;
+        tot[SC_HEADS] += r[SC_HEADS]; tot[SC_SINGLE] += r[SC_SINGLE]; tot[SC_DUPS] += r[SC_DUPS]; tot[SC_W] += r[SC_W];
+        tot[4] = std::max(tot[4], r[SCM_MAXB]); tot[5] = std::max<unsigned long long>(tot[5], (uint32_t)r[SCM_MAXB + 1]);
+        for (int d = 0; d < N; d++)
+            if (r[REP_ICUR + d] > cap)
+                return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: rank %d sent %llu work items to rank %d, the inbox region holds %llu", q, r[REP_ICUR + d], d, (unsigned long long)cap);
+        if (r[SCM_STREAM] > cap) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: the posting stream of rank %d overflows", q);
+    }
     const uint64_t largest = d2 ? (uint64_t)(uint32_t)tot[5] : tot[4];
     if (largest > G2_MAXM)
         return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a final bucket holds %llu words (> %u): skewed databases take the replicated build (ygpu_build_index)",
@@ -2268,14 +2265,22 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     ctx->skip_pair_sort = false;
     YG_CHECK(rc_pw);
     YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    unsigned long long mine = n_r, counts[YG_MAX_RANKS];
+    // pair counts of all ranks; the same gather carries every rank's "a row list overflowed" flag, so that refusal is unanimous too
+    unsigned long long mine[2] = {n_r, my_ovf}, both[2 * YG_MAX_RANKS], counts[YG_MAX_RANKS];
     unsigned long long* d_cnt = &ctx->d_sh_info[44];
-    YG_CUDA(ctx, cudaMemcpyAsync(d_cnt, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
-    YG_CHECK(ygpu_comm_allgather(ctx, d_cnt, d_cnt + 1, sizeof(unsigned long long)));
-    YG_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt + 1, (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaMemcpyAsync(d_cnt, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allgather(ctx, d_cnt, d_cnt + 2, 2 * sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaMemcpyAsync(both, d_cnt + 2, (size_t)N * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     YG_CUDA(ctx, cudaStreamSynchronize(st));
     uint64_t total = 0, mxc = 0;
-    for (int q = 0; q < N; q++) { total += counts[q]; mxc = std::max<uint64_t>(mxc, counts[q]); }
+    for (int q = 0; q < N; q++) {
+        counts[q] = both[2 * q];
+        if (both[2 * q + 1]) {
+            ctx->indexed = false;
+            return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row of rank %d received more work items than its list holds (sketches with repeated hashes): run this database on one GPU", q);
+        }
+        total += counts[q]; mxc = std::max<uint64_t>(mxc, counts[q]);
+    }
     if (total) {
         // padded all-gather, then the ranks' lists are squeezed together and ordered
         const uint64_t need_all = (uint64_t)N * mxc + total + 16;

@@ -240,6 +240,11 @@ int ygpu_load_sketches_hashrange_device(ygpu_ctx* ctx, const uint64_t* d_part_ha
                                         uint32_t n_genomes, uint32_t row_begin, uint32_t row_end);
 int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats /* may be NULL */, uint64_t* n_pairs_total);
 
+/* Replicated index, rows split by measured work (north_star's starting layout; the multi-GPU route for databases the
+ * sharded step refuses): every rank holds ALL sketches (ygpu_load_sketches) and builds the full index, rank r counts the
+ * rows of its work-balanced range, the pair lists are gathered.  Collective; afterwards ygpu_pairs_copy as above.    */
+int ygpu_train_step_replicated(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats /* may be NULL */, uint64_t* n_pairs_total);
+
 /* ---- run path ------------------------------------------------------------------------------ */
 /* sample: HOST pointer to the sample sketch hashes (any order).  Fills counts[n_genomes].
  * Step 1 (multisearch -t 0): n_overlap.  Step 2 (get_exclusive_hashes): among the genomes with

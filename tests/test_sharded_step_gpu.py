@@ -34,6 +34,10 @@ def _run_ranks(db, nranks, thr, residency):
                 sl = db.hashes[int(offsets[g0]):int(offsets[g1])]
                 ph, po = sharding.hashrange_share(db.hashes, offsets, int(cuts[r]), int(cuts[r + 1]), last=r == nranks - 1)
                 for rep in range(2):            # the second step reuses the shared exchange buffers
+                    if residency == "replicated":
+                        ctx.load_sketches(db.hashes, offsets)
+                        st, F = ctx.train_step_replicated(thr)
+                        continue
                     if residency == "genomes":
                         ctx.load_sketches_sharded(sl, offsets, g0, g1)
                     else:
@@ -56,7 +60,7 @@ def _run_ranks(db, nranks, thr, residency):
 
 def _check(db, nranks, thr):
     ref = to.oracle_train(db.hashes, db.offsets, thr)
-    for residency in ("hashes", "genomes"):
+    for residency in ("hashes", "genomes", "replicated"):
         _check_one(db, nranks, thr, residency, ref)
 
 
@@ -115,3 +119,25 @@ def test_sharded_step_edge_rows(nranks):
     db = synth.from_sketches(parts)
     _check(db, nranks, 0.0)
     _check(db, nranks, THR)
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_skewed_database_is_refused_unanimously_and_runs_replicated(nranks):
+    """A hash held by thousands of genomes overflows a shared-memory bucket: every rank refuses the sharded step with the
+    same error (nobody is left waiting in a collective), and the replicated step (full index on every rank, rows split by
+    measured work) gives the oracle's answer."""
+    if _lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    rng = np.random.default_rng(8)
+    base = synth.make_reference_db(5000, 41, mean_size=2500, sd_size=500)
+    parts = [base.sketch(g) for g in range(base.n)]
+    members = rng.choice(base.n, size=2500, replace=False)
+    common = rng.integers(0, synth.MAX_HASH, size=40, dtype=np.uint64)
+    for m in members:
+        parts[m] = np.unique(np.concatenate([parts[m], common]))
+    db = synth.from_sketches(parts)
+    ref = to.oracle_train(db.hashes, db.offsets, THR)
+    for residency in ("hashes", "genomes"):
+        with pytest.raises(_lib.YgpuError, match=r"\(-4\)"):
+            _run_ranks(db, nranks, THR, residency)
+    _check_one(db, nranks, THR, "replicated", ref)

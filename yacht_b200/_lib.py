@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
     "ygpu_comm_get_unique_id", "ygpu_comm_init", "ygpu_comm_destroy", "ygpu_load_sketches_sharded", "ygpu_load_sketches_sharded_device",
     "ygpu_train_step_sharded", "ygpu_upload_finish_sharded", "ygpu_load_sketches_hashrange", "ygpu_load_sketches_hashrange_device",
+    "ygpu_train_step_replicated",
 ]
 COMM_ID_BYTES = 128
 
@@ -128,6 +129,7 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_load_sketches_hashrange.argtypes = [vp, vp, vp, vp, u32, u32, u32]
     lib.ygpu_load_sketches_hashrange_device.argtypes = [vp, vp, vp, vp, u32, u32, u32]
     lib.ygpu_upload_finish_sharded.argtypes = [vp, vp, u32, vp, u32, u32, u32]
+    lib.ygpu_train_step_replicated.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     lib.ygpu_train_step_sharded.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)  # AttributeError here means the .so does not match include/yacht_gpu.h
@@ -282,6 +284,13 @@ class GpuContext:
         st = IndexStats()
         n_out = ctypes.c_uint64(0)
         self._check(self.lib.ygpu_train_step_sharded(self.h, float(threshold), ctypes.byref(st), ctypes.byref(n_out)), "ygpu_train_step_sharded")
+        return st.as_dict(), int(n_out.value)
+
+    def train_step_replicated(self, threshold: float) -> Tuple[dict, int]:
+        """Replicated index (every rank holds all sketches: load_sketches), rows split by work, pair lists gathered."""
+        st = IndexStats()
+        n_out = ctypes.c_uint64(0)
+        self._check(self.lib.ygpu_train_step_replicated(self.h, float(threshold), ctypes.byref(st), ctypes.byref(n_out)), "ygpu_train_step_replicated")
         return st.as_dict(), int(n_out.value)
 
     def pairs_host(self, n_pairs: int) -> np.ndarray:

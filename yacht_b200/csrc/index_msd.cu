@@ -1887,6 +1887,65 @@ extern "C" int ygpu_load_sketches_sharded_device(ygpu_ctx* ctx, const uint64_t* 
     return sharded_load(ctx, d_hashes_slice, offsets, n_genomes, g_begin, g_end, true);
 }
 
+// The per-rank pair lists (unsorted, in ctx->d_pairs) of all ranks on every rank, ordered by (i, j): all-gather of the counts
+// (the same gather carries a per-rank refusal flag so that every rank stops or goes on together), padded all-gather of the
+// lists, one sort on packed keys.  Leaves the complete list in ctx->d_pairs.
+static int gather_pairs(ygpu_ctx* ctx, uint64_t n_r, unsigned long long my_ovf, uint64_t* n_total) {
+    cudaStream_t st = ctx->stream;
+    const int N = ctx->comm->nranks, rank = ctx->comm->rank;
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    unsigned long long mine[2] = {n_r, my_ovf}, both[2 * YG_MAX_RANKS], counts[YG_MAX_RANKS];
+    unsigned long long* d_cnt = &ctx->d_sh_info[44];
+    YG_CUDA(ctx, cudaMemcpyAsync(d_cnt, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    YG_CHECK(ygpu_comm_allgather(ctx, d_cnt, d_cnt + 2, 2 * sizeof(unsigned long long)));
+    YG_CUDA(ctx, cudaMemcpyAsync(both, d_cnt + 2, (size_t)N * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    uint64_t total = 0, mxc = 0;
+    for (int q = 0; q < N; q++) {
+        counts[q] = both[2 * q];
+        if (both[2 * q + 1]) {
+            ctx->indexed = false;
+            return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row of rank %d received more work items than its list holds (sketches with repeated hashes): run this database on one GPU", q);
+        }
+        total += counts[q]; mxc = std::max<uint64_t>(mxc, counts[q]);
+    }
+    if (total) {
+        // padded all-gather, then the ranks' lists are squeezed together and ordered
+        const uint64_t need_all = (uint64_t)N * mxc + total + 16;
+        if (need_all > ctx->pairs_local_cap) {
+            if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);
+            ctx->d_pairs_local = nullptr; ctx->pairs_local_cap = 0;
+            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs_local, (need_all + need_all / 8 + 1024) * sizeof(ygpu_pair)));
+            ctx->pairs_local_cap = need_all + need_all / 8 + 1024;
+        }
+        ygpu_pair* pad = ctx->d_pairs_local;                 // [N][mxc] gathered, then [total] compact behind it
+        ygpu_pair* out = pad + (uint64_t)N * mxc;
+        if (n_r) YG_CUDA(ctx, cudaMemcpyAsync(pad + (uint64_t)rank * mxc, ctx->d_pairs, n_r * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+        YG_CHECK(ygpu_comm_allgather(ctx, pad + (uint64_t)rank * mxc, pad, (size_t)mxc * sizeof(ygpu_pair)));
+        uint64_t pos = 0;
+        for (int q = 0; q < N; q++) {
+            if (counts[q]) YG_CUDA(ctx, cudaMemcpyAsync(out + pos, pad + (uint64_t)q * mxc, counts[q] * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+            pos += counts[q];
+        }
+        YG_CUDA(ctx, cudaEventRecord(ctx->evp[12], st));
+        YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
+        if (total > ctx->pairs_cap) {
+            if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+            ctx->d_pairs = nullptr; ctx->pairs_cap = 0;
+            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs, (total + 1024) * sizeof(ygpu_pair)));
+            ctx->pairs_cap = total + 1024;
+        }
+        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, out, total * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
+    }
+    YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    YG_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->tm.ms_pairsort += elapsed(ctx, 2, 3);
+    if (total) { float g = 0.f; cudaEventElapsedTime(&g, ctx->ev[2], ctx->evp[12]); ctx->tm.ms_gather += g; }
+    ctx->n_pairs = total;
+    *n_total = total;
+    return 0;
+}
+
 // ---- hash-range residency: this rank holds, of EVERY sketch, the hashes that fall into its hash range ------------------------
 // (a sketch is sorted, so that share is one contiguous piece of it: the host cuts every sketch at the same N - 1 hash values).
 // Equal hashes then meet on one rank by construction: the index build needs no exchange at all before the grouping, and the
@@ -2264,56 +2323,35 @@ extern "C" int ygpu_train_step_sharded(ygpu_ctx* ctx, double threshold, ygpu_ind
     const int rc_pw = ygpu_pairwise_flag_device(ctx, threshold, ctx->g_begin, ctx->g_end, &n_r);
     ctx->skip_pair_sort = false;
     YG_CHECK(rc_pw);
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    // pair counts of all ranks; the same gather carries every rank's "a row list overflowed" flag, so that refusal is unanimous too
-    unsigned long long mine[2] = {n_r, my_ovf}, both[2 * YG_MAX_RANKS], counts[YG_MAX_RANKS];
-    unsigned long long* d_cnt = &ctx->d_sh_info[44];
-    YG_CUDA(ctx, cudaMemcpyAsync(d_cnt, mine, sizeof mine, cudaMemcpyHostToDevice, st));
-    YG_CHECK(ygpu_comm_allgather(ctx, d_cnt, d_cnt + 2, 2 * sizeof(unsigned long long)));
-    YG_CUDA(ctx, cudaMemcpyAsync(both, d_cnt + 2, (size_t)N * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
-    uint64_t total = 0, mxc = 0;
-    for (int q = 0; q < N; q++) {
-        counts[q] = both[2 * q];
-        if (both[2 * q + 1]) {
-            ctx->indexed = false;
-            return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_sharded: a query row of rank %d received more work items than its list holds (sketches with repeated hashes): run this database on one GPU", q);
-        }
-        total += counts[q]; mxc = std::max<uint64_t>(mxc, counts[q]);
-    }
-    if (total) {
-        // padded all-gather, then the ranks' lists are squeezed together and ordered
-        const uint64_t need_all = (uint64_t)N * mxc + total + 16;
-        if (need_all > ctx->pairs_local_cap) {
-            if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);
-            ctx->d_pairs_local = nullptr; ctx->pairs_local_cap = 0;
-            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs_local, (need_all + need_all / 8 + 1024) * sizeof(ygpu_pair)));
-            ctx->pairs_local_cap = need_all + need_all / 8 + 1024;
-        }
-        ygpu_pair* pad = ctx->d_pairs_local;                 // [N][mxc] gathered, then [total] compact behind it
-        ygpu_pair* out = pad + (uint64_t)N * mxc;
-        if (n_r) YG_CUDA(ctx, cudaMemcpyAsync(pad + (uint64_t)rank * mxc, ctx->d_pairs, n_r * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
-        YG_CHECK(ygpu_comm_allgather(ctx, pad + (uint64_t)rank * mxc, pad, (size_t)mxc * sizeof(ygpu_pair)));
-        uint64_t pos = 0;
-        for (int q = 0; q < N; q++) {
-            if (counts[q]) YG_CUDA(ctx, cudaMemcpyAsync(out + pos, pad + (uint64_t)q * mxc, counts[q] * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
-            pos += counts[q];
-        }
-        YG_CUDA(ctx, cudaEventRecord(ctx->evp[12], st));
-        YG_CHECK(ygpu_sort_pairs_device(ctx, out, total));
-        if (total > ctx->pairs_cap) {
-            if (ctx->d_pairs) cudaFree(ctx->d_pairs);
-            ctx->d_pairs = nullptr; ctx->pairs_cap = 0;
-            YG_CUDA(ctx, cudaMalloc(&ctx->d_pairs, (total + 1024) * sizeof(ygpu_pair)));
-            ctx->pairs_cap = total + 1024;
-        }
-        YG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, out, total * sizeof(ygpu_pair), cudaMemcpyDeviceToDevice, st));
-    }
-    YG_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    YG_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->tm.ms_pairsort += elapsed(ctx, 2, 3);
-    if (total) { float g = 0.f; cudaEventElapsedTime(&g, ctx->ev[2], ctx->evp[12]); ctx->tm.ms_gather += g; }
+    uint64_t total = 0;
+    YG_CHECK(gather_pairs(ctx, n_r, my_ovf, &total));
     ctx->n_pairs = total;
+    *n_pairs_total = total;
+    return 0;
+}
+
+// ---- replicated index, rows split by measured work: the layout north_star starts from, and the multi-GPU route for databases the
+// sharded step refuses (extreme skew: there the pairwise count dominates and splits cleanly by rows) --------------------------------
+// Every rank holds ALL sketches (ygpu_load_sketches) and builds the full index; rank r counts / flags the rows of its
+// work-balanced range; the pair lists are gathered like in the sharded step.
+extern "C" int ygpu_train_step_replicated(ygpu_ctx* ctx, double threshold, ygpu_index_stats* stats, uint64_t* n_pairs_total) {
+    if (!ctx || !n_pairs_total) return YGPU_ERR_ARG;
+    *n_pairs_total = 0;
+    if (!ctx->comm || ctx->sharded || !ctx->loaded) return ygpu_fail(ctx, YGPU_ERR_STATE, "train_step_replicated: ygpu_comm_init and ygpu_load_sketches (all sketches) first");
+    const int N = ctx->comm->nranks, rank = ctx->comm->rank;
+    ygpu_index_stats S{};
+    YG_CHECK(ygpu_build_index(ctx, &S));
+    if (stats) *stats = S;
+    std::vector<uint32_t> bounds((size_t)N + 1, 0);
+    YG_CHECK(ygpu_row_partition(ctx, (uint32_t)N, bounds.data()));      // same index on every rank => same bounds on every rank
+    uint64_t n_r = 0;
+    ctx->skip_pair_sort = true;
+    const int rc = ygpu_pairwise_flag_device(ctx, threshold, bounds[rank], bounds[rank + 1], &n_r);
+    ctx->skip_pair_sort = false;
+    YG_CHECK(rc);
+    YG_CHECK(dev_alloc(ctx, &ctx->d_sh_info, (uint64_t)SHI_WORDS));
+    uint64_t total = 0;
+    YG_CHECK(gather_pairs(ctx, n_r, 0ull, &total));
     *n_pairs_total = total;
     return 0;
 }

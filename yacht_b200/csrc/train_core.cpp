@@ -372,15 +372,26 @@ int main(int argc, char** argv) {
         bool refused = false, failed = false;
         for (int d = 0; d < ndev; d++) { if (res[d].rc == -4) refused = true; else if (res[d].rc) failed = true; }
         if (refused && !failed) {
+            // replicated index, rows split by measured work (ygpu_train_step_replicated): every GPU receives all sketches and
+            // builds the full index; for such databases the pairwise count dominates, and it splits cleanly by rows
             sharded_refused = true;
-            std::cout << "[multi-gpu] sharded step not applicable (" << res[0].err << "); running on GPU 0 alone" << std::endl;
-            DeviceResult& r = res[0];
-            r.rc = ygpu_load_sketch_blocks(ctxs[0], block_ptrs.data(), block_lens.data(), (uint32_t)nb, in.offsets.data(), n);
-            if (!r.rc) r.rc = ygpu_build_index(ctxs[0], &r.stats);
-            if (!r.rc) r.rc = ygpu_pairwise_flag(ctxs[0], args.containment_threshold, 0, n, &r.pairs, &r.n_pairs);
-            if (r.rc) r.err = ygpu_last_error(ctxs[0]);
-            ygpu_get_timings(ctxs[0], &r.tm);
-            for (int d = 1; d < ndev; d++) { res[d].rc = 0; res[d].n_pairs = 0; }
+            std::cout << "[multi-gpu] sharded step not applicable (" << res[0].err << "); replicated index, rows split over " << ndev << " GPUs" << std::endl;
+            std::vector<std::thread> th;
+            for (int d = 0; d < ndev; d++)
+                th.emplace_back([&, d]() {
+                    DeviceResult& r = res[d];
+                    ygpu_ctx* c = ctxs[d];
+                    r.n_pairs = 0;
+                    r.rc = ygpu_load_sketch_blocks(c, block_ptrs.data(), block_lens.data(), (uint32_t)nb, in.offsets.data(), n);
+                    if (!r.rc) r.rc = ygpu_train_step_replicated(c, args.containment_threshold, &r.stats, &r.n_pairs);
+                    if (!r.rc && d == 0 && r.n_pairs) {
+                        r.pairs = (ygpu_pair*)malloc(r.n_pairs * sizeof(ygpu_pair));
+                        r.rc = r.pairs ? ygpu_pairs_copy(c, r.pairs, 0) : -5;
+                    }
+                    if (r.rc) r.err = ygpu_last_error(c);
+                    ygpu_get_timings(c, &r.tm);
+                });
+            for (auto& t : th) t.join();
         }
     }
     for (int d = 0; d < ndev; d++)

@@ -119,6 +119,56 @@ def make_reference_db(n: int, seed: int, mean_size: float = 5000.0, sd_size: flo
     return from_sketches(parts, cluster[order])
 
 
+def make_skewed_db(n: int, seed: int, mean_size: float = 5000.0, sd_size: float = 1500.0, min_size: int = 50,
+                   p_cluster: float = 0.12, zipf_a: float = 1.3, zipf_cap: int = 20000, core_hashes: int = 200,
+                   core_lo: float = 0.01, core_hi: float = 0.10, ksize: int = 31) -> SketchDB:
+    """The "full-GTDB shape" of BASELINE.json configs[3] at full size (Zipf(1.3) cluster sizes capped at
+    `zipf_cap`, conserved core hashes each present in 1-10 % of all genomes), generated cluster by cluster with numpy
+    (make_reference_db(zipf_clusters=True) draws child by child in Python: 11 minutes at 400 000 genomes).  Same model,
+    its own random stream; the seeded golden cases keep using make_reference_db."""
+    rng = np.random.default_rng(seed)
+    sizes = np.clip(np.rint(rng.normal(mean_size, sd_size, size=n)), min_size, None).astype(np.int64)
+    cluster = np.full(n, -1, dtype=np.int64)
+    # every sketch is built as a row of a (genome, slot) table of width max size, then masked down to its own size
+    blocks: List[np.ndarray] = []      # per genome: sorted unique hashes
+    g = 0
+    cid = 0
+    starts = rng.random(n) < p_cluster
+    sketches: List[Optional[np.ndarray]] = [None] * n
+    while g < n:
+        if starts[g] and g + 1 < n:
+            s = int(min(max(2, rng.zipf(zipf_a) + 1), zipf_cap, n - g))
+            cluster[g:g + s] = cid
+            cid += 1
+            parent = np.unique(rng.integers(0, MAX_HASH, size=int(sizes[g]), dtype=np.uint64))
+            sketches[g] = parent
+            m = s - 1
+            ani = rng.choice(np.array(ANI_CHOICES), size=m) ** ksize
+            for c0 in range(0, m, 2048):                      # chunks of children: the keep matrix stays below ~100 MB
+                c1 = min(m, c0 + 2048)
+                keep = rng.random((c1 - c0, parent.shape[0])) < ani[c0:c1, None]
+                for k in range(c1 - c0):
+                    child = g + 1 + c0 + k
+                    kept = parent[keep[k]]
+                    n_fresh = max(0, int(sizes[child]) - kept.shape[0])
+                    fresh = rng.integers(0, MAX_HASH, size=n_fresh, dtype=np.uint64)
+                    merged = np.concatenate([kept, fresh])
+                    merged.sort()
+                    sketches[child] = merged                  # (a 55-bit collision between kept and fresh hashes has probability ~1e-9 per sketch)
+            g += s
+        else:
+            sketches[g] = np.unique(rng.integers(0, MAX_HASH, size=int(sizes[g]), dtype=np.uint64))
+            g += 1
+    if core_hashes > 0:
+        core = np.sort(rng.integers(0, MAX_HASH, size=core_hashes, dtype=np.uint64))
+        frac = rng.uniform(core_lo, core_hi, size=core_hashes)
+        member = rng.random((core_hashes, n)) < frac[:, None]          # 200 x 400 000 booleans
+        for m in np.flatnonzero(member.any(axis=0)):
+            sketches[m] = np.unique(np.concatenate([sketches[m], core[member[:, m]]]))
+    order = rng.permutation(n)
+    return from_sketches([sketches[int(o)] for o in order], cluster[order])
+
+
 def make_sample(db: SketchDB, seed: int, n_present: int, total_hashes: int,
                 cov_lo: float = 0.01, cov_hi: float = 1.0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Config-5 style metagenome sample: the union of ``n_present`` random reference genomes, each

@@ -7,6 +7,7 @@
  * src/yacht/hypothesis_recovery_src.py):
  *
  *   ygpu_read_signatures    read_min_hashes() / read_sketches()                main.cpp:62-124
+ *   ygpu_read_signatures_ksize   load_signature_with_ksize() per manifest row  utils.py:31-51, hypothesis_recovery_src.py:154-172
  *   ygpu_load_sketches      the in-memory result of read_sketches()            main.cpp:89-124
  *   ygpu_upload_begin / _block / _finish   the same, streamed while parsing        main.cpp:89-124
  *                           (vector<vector<hash_t>> sketches, :51) as one flat
@@ -161,6 +162,11 @@ int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
  * yields an empty sketch (main.cpp:68-71); malformed JSON is an error (text in errbuf).          */
 int ygpu_read_signatures(const char* const* paths, uint32_t n, int threads, ygpu_sketch_set* out,
                          char* errbuf, uint64_t errlen);
+/* The run side's rule instead (load_signature_with_ksize, utils.py:31-51): all records and sub-signatures of a file are
+ * candidates and exactly one must have k-mer size `ksize`; a file with none or several is an error ("Expected exactly one
+ * signature with ksize ...", text in errbuf), like in the reference.                                                    */
+int ygpu_read_signatures_ksize(const char* const* paths, uint32_t n, int threads, int ksize, ygpu_sketch_set* out,
+                               char* errbuf, uint64_t errlen);
 void ygpu_sketch_set_free(ygpu_sketch_set* s);
 
 /* ---- train path ---------------------------------------------------------------------------- */

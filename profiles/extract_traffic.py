@@ -4,8 +4,8 @@ every kernel of the train hot path, keyed the way bench.py's `rooflines` are.
 usage: python profiles/extract_traffic.py raw.csv genomes seed "<source description>" > profiles/traffic.json"""
 import csv, json, sys
 
-KEYS = [("k2_hist1", "part_hist1"), ("k2_scatter<1>", "part_scatter1"), ("k2_scatter<(int)1>", "part_scatter1"), ("k2_hist2", "part_hist2"),
-        ("k2_scatter<2>", "part_scatter2"), ("k2_scatter<(int)2>", "part_scatter2"), ("k2_group", "index_grouping"), ("k3_count_flag", "pairwise_count")]
+KEYS = [("k2_hist1", "part_hist1"), ("k2_scatter<1", "part_scatter1"), ("k2_scatter<(int)1", "part_scatter1"), ("k2_hist2", "part_hist2"),
+        ("k2_scatter<2", "part_scatter2"), ("k2_scatter<(int)2", "part_scatter2"), ("k2_group", "index_grouping"), ("k3_count_flag", "pairwise_count")]
 
 
 def to_bytes(v, unit):

@@ -89,3 +89,27 @@ def test_agrees_with_json_module_on_random_documents(tmp_path):
         want.append(json.loads(texts[-1])[0]["signatures"][0]["mins"])
     got, _ = _read(tmp_path, texts, threads=3)
     assert got == want
+
+
+def test_ksize_selecting_reader(tmp_path):
+    """ygpu_read_signatures_ksize: the run side's rule (reference utils.py:31-51) -- all records and sub-signatures are
+    candidates, exactly one must have the requested k-mer size."""
+    import json
+    from yacht_b200 import _lib
+    def sub(k, mins):
+        return {"num": 0, "ksize": k, "seed": 42, "max_hash": 18446744073709552, "mins": mins, "md5sum": "x", "molecule": "dna"}
+    a = tmp_path / "a.sig"
+    a.write_text(json.dumps([{"class": "sourmash_signature", "name": "a", "signatures": [sub(21, [1, 2, 3]), sub(31, [10, 20, 30, 40])], "version": 0.4}]))
+    b = tmp_path / "b.sig"     # "mins" before "ksize", second record holds the match
+    b.write_text(json.dumps([{"name": "b0", "signatures": [{"mins": [7], "ksize": 51}]},
+                             {"name": "b1", "signatures": [{"mins": [5, 6], "abundances": [1, 1], "ksize": 31}]}]))
+    h, off, bad = _lib.read_signatures([str(a), str(b)], 2, ksize=31)
+    assert bad == 0 and off.tolist() == [0, 4, 6] and h.tolist() == [10, 20, 30, 40, 5, 6]
+    h, off, bad = _lib.read_signatures([str(a), str(b)], 2)              # the train core's rule: first record, first sub-signature
+    assert off.tolist() == [0, 3, 4] and h.tolist() == [1, 2, 3, 7]
+    with pytest.raises(_lib.YgpuError, match="Expected exactly one signature with ksize 41, found 0"):
+        _lib.read_signatures([str(a)], 1, ksize=41)
+    c = tmp_path / "c.sig"
+    c.write_text(json.dumps([{"name": "c", "signatures": [sub(31, [1]), sub(31, [2])]}]))
+    with pytest.raises(_lib.YgpuError, match="found 2"):
+        _lib.read_signatures([str(c)], 1, ksize=31)

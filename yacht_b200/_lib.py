@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libyachtgpu.so")
 # every symbol include/yacht_gpu.h declares (tests check the library exports each of them)
 ABI_SYMBOLS = [
     "ygpu_device_count", "ygpu_ctx_create", "ygpu_ctx_destroy", "ygpu_last_error", "ygpu_free",
-    "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketch_blocks", "ygpu_load_sketches_device",
+    "ygpu_host_alloc", "ygpu_host_free", "ygpu_read_signatures", "ygpu_read_signatures_ksize", "ygpu_sketch_set_free", "ygpu_alt_mut_rate", "ygpu_reset_timers", "ygpu_get_timings", "ygpu_load_sketches", "ygpu_load_sketch_blocks", "ygpu_load_sketches_device",
     "ygpu_build_index", "ygpu_pairwise_flag", "ygpu_pairwise_flag_device", "ygpu_pairs_copy", "ygpu_row_partition",
     "ygpu_mark", "ygpu_elapsed_ms", "ygpu_set_option", "ygpu_exclusive_hashes",
     "ygpu_hyp_test",
@@ -99,6 +99,8 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_host_free.restype = None
     lib.ygpu_read_signatures.argtypes = [ctypes.POINTER(ctypes.c_char_p), u32, ctypes.c_int, ctypes.POINTER(SketchSet),
                                          ctypes.c_char_p, u64]
+    lib.ygpu_read_signatures_ksize.argtypes = [ctypes.POINTER(ctypes.c_char_p), u32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(SketchSet),
+                                               ctypes.c_char_p, u64]
     lib.ygpu_sketch_set_free.argtypes = [ctypes.POINTER(SketchSet)]
     lib.ygpu_sketch_set_free.restype = None
     lib.ygpu_alt_mut_rate.argtypes = [vp, vp, vp, u64, ctypes.c_int, ctypes.c_double, vp]
@@ -354,15 +356,19 @@ class GpuContext:
         return out
 
 
-def read_signatures(paths: Sequence[str], threads: int = 1) -> Tuple[np.ndarray, np.ndarray, int]:
+def read_signatures(paths: Sequence[str], threads: int = 1, ksize: int = 0) -> Tuple[np.ndarray, np.ndarray, int]:
     """Multi-threaded native ingest of uncompressed .sig files -> (hashes, offsets, n_unreadable).
-    Mirrors the reference core's reader (main.cpp:62-124): first record, first sub-signature."""
+    ksize = 0 mirrors the reference core's reader (main.cpp:62-124): first record, first sub-signature.  ksize > 0 mirrors
+    load_signature_with_ksize (utils.py:31-51): exactly one sub-signature of that k-mer size per file, else an error."""
     lib = load_library()
     n = len(paths)
     arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
     ss = SketchSet()
     err = ctypes.create_string_buffer(2048)
-    rc = lib.ygpu_read_signatures(arr, n, int(threads), ctypes.byref(ss), err, 2048)
+    if ksize > 0:
+        rc = lib.ygpu_read_signatures_ksize(arr, n, int(threads), int(ksize), ctypes.byref(ss), err, 2048)
+    else:
+        rc = lib.ygpu_read_signatures(arr, n, int(threads), ctypes.byref(ss), err, 2048)
     if rc != 0:
         raise YgpuError(f"ygpu_read_signatures failed ({rc}): {err.value.decode(errors='replace')}")
     try:

@@ -12,12 +12,25 @@
 #include <utility>
 #include <vector>
 
+static int read_signatures_impl(const char* const* paths, uint32_t n, int threads, int ksize, ygpu_sketch_set* out, char* errbuf, uint64_t errlen);
+
 extern "C" int ygpu_read_signatures(const char* const* paths, uint32_t n, int threads, ygpu_sketch_set* out,
                                     char* errbuf, uint64_t errlen) {
+    return read_signatures_impl(paths, n, threads, 0, out, errbuf, errlen);
+}
+
+extern "C" int ygpu_read_signatures_ksize(const char* const* paths, uint32_t n, int threads, int ksize, ygpu_sketch_set* out,
+                                          char* errbuf, uint64_t errlen) {
+    if (ksize < 1) return YGPU_ERR_ARG;
+    return read_signatures_impl(paths, n, threads, ksize, out, errbuf, errlen);
+}
+
+static int read_signatures_impl(const char* const* paths, uint32_t n, int threads, int ksize, ygpu_sketch_set* out, char* errbuf, uint64_t errlen) {
     if (!out || (n && !paths)) return YGPU_ERR_ARG;
     memset(out, 0, sizeof(*out));
     yingest::Ingest in;
     in.quiet = true;
+    in.ksize = ksize;
     in.names.reserve(n);
     for (uint32_t i = 0; i < n; i++) in.names.emplace_back(paths[i] ? paths[i] : "");
     yingest::read_sketches(in, threads < 1 ? 1 : threads);

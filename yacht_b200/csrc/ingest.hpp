@@ -43,6 +43,8 @@ struct Ingest {
     std::function<void(uint32_t)> on_block;
     bool fatal = false;
     bool quiet = false;              // library use: do not print the per-file message
+    int ksize = 0;                   // > 0: the run side's rule (utils.py:31-51) -- exactly one sub-signature of this k-mer size per file,
+                                     // searched in all records; 0: the train core's rule (main.cpp:78) -- [0]["signatures"][0]["mins"]
     std::atomic<uint32_t> n_unreadable{0};
     std::string fatal_msg;
 };
@@ -94,7 +96,13 @@ inline void read_sketches(Ingest& in, int threads, bool assemble_flat = true) {
             for (uint32_t f = f0; f < f1; f++) {
                 const size_t before = out.size();
                 std::string why;
-                const sigscan::Status st = sigscan::read_mins(in.names[f], buf, out, &why);
+                int n_match = 1;
+                sigscan::Status st = in.ksize > 0 ? sigscan::read_mins_ksize(in.names[f], in.ksize, buf, out, &why, &n_match)
+                                                  : sigscan::read_mins(in.names[f], buf, out, &why);
+                if (st == sigscan::OK && n_match != 1) {
+                    st = sigscan::MALFORMED;
+                    why = "Expected exactly one signature with ksize " + std::to_string(in.ksize) + ", found " + std::to_string(n_match);
+                }
                 if (st == sigscan::CANNOT_OPEN) {
                     if (!in.quiet) std::cerr << "Could not open the file!" << std::endl;  // main.cpp:69
                     in.n_unreadable.fetch_add(1);

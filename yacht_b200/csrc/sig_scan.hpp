@@ -209,6 +209,90 @@ inline Status parse_mins(const char* data, size_t len, std::vector<uint64_t>& ou
 }
 
 // Whole-file read into a reusable buffer, then parse_mins.
+// The run side of the reference loads every sketch through load_signature_with_ksize (src/yacht/utils.py:31-51): ALL records and
+// sub-signatures of the file are candidates, exactly one must carry the requested k-mer size.  Appends that one's mins to `out`;
+// *n_match = how many sub-signatures of that ksize the file holds (the caller raises unless it is 1, like the reference).
+inline Status parse_mins_ksize(const char* data, size_t len, int ksize, std::vector<uint64_t>& out, std::string* why, int* n_match) {
+    Scanner sc{data, data + len, {}};
+    auto bad = [&](const char* m) { if (why) *why = sc.why.empty() ? m : sc.why; return MALFORMED; };
+    *n_match = 0;
+    sc.ws();
+    if (sc.p >= sc.end || *sc.p != '[') return bad("document is not an array");
+    sc.p++;
+    const char* mins_at = nullptr;      // where the "mins" array of the first matching sub-signature starts
+    for (;;) {                          // records
+        sc.ws();
+        if (sc.p >= sc.end) return bad("unterminated document");
+        if (*sc.p == ']') break;
+        if (*sc.p == ',') { sc.p++; continue; }
+        bool stop = false;
+        auto on_rec = [&](const std::string& k) -> int {
+            if (k != "signatures") return 0;
+            if (sc.p >= sc.end || *sc.p != '[') { sc.fail("\"signatures\" is not an array"); return -1; }
+            sc.p++;
+            for (;;) {                  // sub-signatures
+                sc.ws();
+                if (sc.p >= sc.end) { sc.fail("unterminated \"signatures\""); return -1; }
+                if (*sc.p == ']') { sc.p++; return 1; }
+                if (*sc.p == ',') { sc.p++; continue; }
+                long long this_k = -1;
+                const char* this_mins = nullptr;
+                bool s2 = false;
+                auto on_sub = [&](const std::string& kk) -> int {
+                    if (kk == "ksize") {
+                        char* q = nullptr;
+                        this_k = strtoll(sc.p, &q, 10);
+                        if (q == sc.p) { sc.fail("bad \"ksize\""); return -1; }
+                        sc.p = q;
+                        return 1;
+                    }
+                    if (kk == "mins") { this_mins = sc.p; return 0; }      // remembered, skipped for now
+                    return 0;
+                };
+                if (!sc.object(on_sub, &s2)) return -1;
+                if (this_k == (long long)ksize) {
+                    if (*n_match == 0) mins_at = this_mins;
+                    (*n_match)++;
+                }
+            }
+        };
+        if (!sc.object(on_rec, &stop)) return bad("malformed record");
+    }
+    if (*n_match >= 1 && mins_at) {
+        Scanner m{mins_at, data + len, {}};
+        if (!m.uint_array(out)) { if (why) *why = m.why; return MALFORMED; }
+    }
+    return OK;
+}
+
+inline Status read_file(const std::string& path, std::vector<char>& buf, size_t* got_out) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return CANNOT_OPEN;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return CANNOT_OPEN; }
+    const size_t len = (size_t)st.st_size;
+    if (buf.size() < len + 1) buf.resize(len + 1);
+    size_t got = 0;
+    while (got < len) {
+        const ssize_t r = read(fd, buf.data() + got, len - got);
+        if (r < 0) { if (errno == EINTR) continue; close(fd); return CANNOT_OPEN; }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    buf[got] = 0;
+    *got_out = got;
+    return OK;
+}
+
+inline Status read_mins_ksize(const std::string& path, int ksize, std::vector<char>& buf, std::vector<uint64_t>& out, std::string* why, int* n_match) {
+    size_t got = 0;
+    *n_match = 0;
+    const Status st = read_file(path, buf, &got);
+    if (st != OK) return st;
+    return parse_mins_ksize(buf.data(), got, ksize, out, why, n_match);
+}
+
 inline Status read_mins(const std::string& path, std::vector<char>& buf, std::vector<uint64_t>& out, std::string* why) {
     const int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) return CANNOT_OPEN;

@@ -14,6 +14,7 @@
 
 #include <cub/cub.cuh>
 #include <cstdarg>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,7 @@
 #include <vector>
 
 static std::string g_create_err;
+static std::mutex g_err_mu;      // ygpu_upload_block is called from several threads at once: their failures must not race on the text
 
 int ygpu_fail(ygpu_ctx* ctx, int code, const char* fmt, ...) {
     char buf[1024];
@@ -29,6 +31,7 @@ int ygpu_fail(ygpu_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mu);
     if (ctx) ctx->err = buf;
     else g_create_err = buf;
     return code;

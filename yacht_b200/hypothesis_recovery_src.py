@@ -45,7 +45,7 @@ def _context() -> _lib.GpuContext:
 _last_counts = None      # (loaded database key, sample key, counts) of the last overlap probe
 
 
-def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str, num_threads: int) -> None:
+def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str, num_threads: int, ksize: int = 0) -> None:
     """Make the manifest's genomes (row order = genome id) resident on the device; cached per manifest."""
     global _loaded_key
     paths = [os.path.join(path_to_genome_temp_dir, "signatures", md5sum + SIG_SUFFIX) for md5sum in manifest["md5sum"]]
@@ -58,7 +58,9 @@ def _load_manifest_sketches(manifest: pd.DataFrame, path_to_genome_temp_dir: str
         hashes, offsets = cached
         _log("INFO", f"Packed sketch cache found ({len(md5sums)} genomes, {int(offsets[-1])} hashes): signature files are not parsed")
     else:
-        hashes, offsets, n_bad = _lib.read_signatures(paths, max(1, int(num_threads)))
+        # like the reference (load_signature_with_ksize per manifest row, hypothesis_recovery_src.py:154-172): the sub-signature of
+        # THIS k-mer size, exactly one per file -- a file with several ksizes must not contribute whichever comes first
+        hashes, offsets, n_bad = _lib.read_signatures(paths, max(1, int(num_threads)), ksize=int(ksize))
         if n_bad:
             # the reference loads every manifest signature through load_signature_with_ksize and raises when one is missing
             # (utils.py:43-50); an absent file must not silently become an empty sketch here
@@ -88,7 +90,7 @@ def get_organisms_with_nonzero_overlap(manifest: pd.DataFrame, sample_file: str,
 
     # every sample signature of this ksize is a query, like multisearch's query list
     result_file = os.path.join(path_to_sample_temp_dir, "sample_multisearch_result.csv")
-    _load_manifest_sketches(manifest, path_to_genome_temp_dir, num_threads)
+    _load_manifest_sketches(manifest, path_to_genome_temp_dir, num_threads, ksize)
     ctx = _context()
     names: List[str] = []
     rows = []
@@ -123,7 +125,7 @@ def get_exclusive_hashes(manifest: pd.DataFrame, nontrivial_organism_names: List
     sub-manifest order, and the sub-manifest."""
     keep = manifest["organism_name"].isin(nontrivial_organism_names)
     sub_manifest = manifest.loc[keep, :].reset_index(drop=True)
-    _load_manifest_sketches(manifest, path_to_genome_temp_dir, num_threads)
+    _load_manifest_sketches(manifest, path_to_genome_temp_dir, num_threads, ksize)
     mask = keep.to_numpy().astype(np.uint8)
     sample_hashes = sample_sig.mins if hasattr(sample_sig, "mins") else np.asarray(list(sample_sig.minhash.hashes), dtype=np.uint64)
     sample_hashes = np.ascontiguousarray(sample_hashes, dtype=np.uint64)

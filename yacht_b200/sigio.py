@@ -98,12 +98,14 @@ def parse_signature_json(text: str, path: str = "") -> List[Signature]:
             mins = np.array(sub.get("mins", []), dtype=np.uint64)
             ab = sub.get("abundances")
             out.append(Signature(
-                name=rec.get("name") or rec.get("filename") or "",
+                name=rec.get("name") or "",          # sourmash: sig.name is '' when the record carries no name (it does not fall back to the filename)
                 ksize=int(sub.get("ksize", 0)),
                 mins=mins,
                 abundances=None if ab is None else np.array(ab, dtype=np.int64),
                 max_hash=int(sub.get("max_hash", 0)),
-                md5sum=sub.get("md5sum", ""),
+                # the stored md5sum is trusted (recomputing it over ~5 000 decimal strings per sketch costs minutes of Python at
+                # GTDB size); a record without one gets sourmash's definition computed
+                md5sum=sub.get("md5sum") or compute_md5sum(int(sub.get("ksize", 0)), mins),
                 filename=rec.get("filename", ""),
                 molecule=sub.get("molecule", "dna"),
                 path=path,

@@ -170,6 +170,11 @@ def run_yacht_train_core(num_threads: int, ani_thresh: float, ksize: int, path_t
 
     containment_thresh = ani_thresh ** ksize
     total_sig_files = len(sig_files)
+    # the GPU core indexes hash slots with 32 bits (include/yacht_gpu.h): say so here, before anything is launched
+    total_hashes = sum(int(v[2]) for v in sig_info_dict.values())
+    if total_hashes >= 2 ** 32:
+        raise ValueError(f"The reference database holds {total_hashes} hashes; this build of run_yacht_train_core supports fewer than 2^32 "
+                         f"(about 850 000 genomes at scaled=1000). Split the database or raise --scaled.")
     if total_sig_files <= num_genome_threshold:
         passes = 1
     else:

@@ -184,10 +184,40 @@ def reference_plan(n: int, T: int):
     return passes, need, avail
 
 
+REF_CACHE = os.path.join(tempfile.gettempdir(), "yacht_b200_reference_arm_cache.json")
+
+
+def reference_cache_key(args, binary: str, cores: int) -> str:
+    try:
+        stamp = f"{os.path.getsize(binary)}:{int(os.path.getmtime(binary))}"
+    except OSError:
+        stamp = "?"
+    return f"genomes={args.genomes} seed={args.seed} cpu_sample={args.cpu_sample} thr={THR!r} cores={cores} binary={stamp}"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # The CPU arm does not depend on the number of GPUs, and one run of the reference core on the full configuration is ~7 minutes
+    # of CPU: when the driver asks for it again on the same box (same configuration, same binary, same cores -- e.g. at every N of
+    # a scaling run) the line of the first run is printed again, marked as such (--no-reference-cache measures again).
+    from oracle import train_oracle as to
+    binary0 = to.REF_BIN if to.reference_available() else to.PORT_BIN
+    key = reference_cache_key(args, binary0, os.cpu_count() or 1)
+    if not args.no_reference_cache and os.path.exists(REF_CACHE):
+        try:
+            with open(REF_CACHE) as f:
+                cache = json.load(f)
+            if key in cache:
+                line = cache[key]
+                line["n_gpus"] = args.gpus
+                line["cached"] = {"from": line.get("measured_at"), "why": "same box, same configuration, same binary: the CPU arm does not depend on "
+                                  "the GPU count; first measurement repeated verbatim (bench.py --no-reference-cache measures again)"}
+                print(json.dumps(line), flush=True)
+                return
+        except Exception:
+            pass
     db, gen_s = make_workload(args.genomes, args.seed)
     n, T = db.n, int(db.offsets[-1])
     cores = os.cpu_count() or 1
@@ -232,7 +262,18 @@ def run_reference_arm(args):
                 line["parity"] = check_digest(args, n, len(got.lines), lines=got.lines, selected=got.selected)
             except Exception as e:
                 line["parity"] = {"error": repr(e)}
+        line["measured_at"] = time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())
         print(json.dumps(line), flush=True)
+        try:
+            cache = {}
+            if os.path.exists(REF_CACHE):
+                with open(REF_CACHE) as f:
+                    cache = json.load(f)
+            cache[key] = line
+            with open(REF_CACHE, "w") as f:
+                json.dump(cache, f)
+        except Exception:
+            pass
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -569,6 +610,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="genomes in the CPU sample (cpu_baseline: 0 = size for ~15 s; --impl reference: 0 = the FULL configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cache", action="store_true",
+                    help="--impl reference: measure again even if this box already holds a measurement of the same configuration")
     ap.add_argument("--residency", default="hashes", choices=["hashes", "genomes"],
                     help="N > 1: what a rank holds -- its hash range of every sketch (default) or the sketches of its genome range")
     args = ap.parse_args()

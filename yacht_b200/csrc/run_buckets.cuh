@@ -32,6 +32,7 @@ struct RunBucketArgs {
 };
 
 constexpr int RB_SCAP = 1024;       // sample hashes of one bucket held in shared memory (more: the general path takes the sample)
+constexpr int RB_SMALL = 192;       // up to this many survivors per bucket are settled by a direct all-pairs scan (no sub-bucket machinery)
 
 struct __align__(16) RunSmem {
     uint64_t stage[G2_WIN];         // the bucket's reference words (bulk copy target)
@@ -42,8 +43,11 @@ struct __align__(16) RunSmem {
     uint32_t ext[G2_WIN];           // per candidate: sub-bucket start | size << 10 | sub-bucket digit << 20
     uint32_t sbits[G2_NSUB / 32];   // filter over the sub-bucket digits of the bucket's sample
     unsigned short start2[G2_NSUB + 8];
+    uint64_t lk[RB_SMALL];          // the survivors of a bucket with few of them: full key (sub-bucket digit and the bits below it) ...
+    uint32_t lg[RB_SMALL];          // ... and genome id
     uint32_t wsum[G2_THREADS / 32];
     uint32_t next[2][4];            // [parity]{first word, words, bucket id}
+    uint32_t nsurv;
     uint64_t mbar;
 };
 
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k5_bucket(const RunBucketArgs a
     };
     for (uint32_t i = tid; i < G2_NSUB; i += G2_THREADS) sm.cnt[i] = 0;
     if (tid < G2_NSUB / 32) sm.sbits[tid] = 0;
+    if (tid == 0) sm.nsurv = 0;
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
         mbar_init_fence();
@@ -122,11 +127,10 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k5_bucket(const RunBucketArgs a
             e[0] = (uint64_t)v0.x | ((uint64_t)v0.y << 32); e[1] = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
             e[2] = (uint64_t)v1.x | ((uint64_t)v1.y << 32); e[3] = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
         }
-        uint32_t sr[4];
+        uint32_t keepm = 0;                 // which of the four words survive
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t w = (k >> 1) * 512u + 2u * tid + (k & 1);
-            sr[k] = 0xFFFFFFFFu;
             if (w >= wlo && w < whi) {
                 const uint32_t s = (uint32_t)(e[k] >> a.sub_shift) & a.sub_mask;
                 bool keep;
@@ -136,11 +140,59 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k5_bucket(const RunBucketArgs a
                     const uint32_t g = (uint32_t)e[k] & gmask;
                     keep = (a.ntbits[g >> 5] >> (g & 31u)) & 1u;
                 }
-                if (keep) sr[k] = s | (atomicAdd(&sm.cnt[s], 1u) << 16);
+                if (keep) {
+                    keepm |= 1u << k;
+                    const uint32_t pos = atomicAdd(&sm.nsurv, 1u);
+                    if (pos < RB_SMALL) { sm.lk[pos] = (e[k] >> a.gb) & a.key_mask; sm.lg[pos] = (uint32_t)e[k] & gmask; }
+                }
             }
         }
         __syncthreads();
         if (tid == 0) advance(par ^ 1u);
+        const uint32_t nsv = sm.nsurv;
+        if (nsv <= RB_SMALL) {
+            // ---- few survivors (the rule: a sample overlaps a few hashes of a bucket, nontrivial genomes are a few per cent): one
+            //      thread per survivor scans them all -- no sub-bucket counting, no scan, three barriers less
+            if (tid < nsv) {
+                const uint64_t Kq = sm.lk[tid];
+                const uint32_t Gq = sm.lg[tid];
+                bool copy_before = false, same_before = false, other_genome = false;
+                for (uint32_t j = 0; j < nsv; j++) {
+                    const bool same = sm.lk[j] == Kq;
+                    const bool sameg = sm.lg[j] == Gq;
+                    // "before": the slot order is arbitrary but fixed for this bucket, which is all the first-copy rule needs
+                    copy_before |= same & sameg & (j < tid);
+                    same_before |= same & (j < tid);
+                    other_genome |= same & !sameg;
+                }
+                if (MODE == 0) {
+                    if (!copy_before) atomicAdd(&a.counts[Gq].n_overlap, 1u);
+                } else if (!same_before && !other_genome) {
+                    atomicAdd(&a.counts[Gq].n_exclusive, 1u);
+                    if (ns && in_sample(Kq, (uint32_t)(Kq >> a.rest_bits) & a.sub_mask, ns)) atomicAdd(&a.counts[Gq].n_match, 1u);
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < ns; i += G2_THREADS) {
+                const uint32_t sub = (uint32_t)(sm.skey[i] >> a.rest_bits) & a.sub_mask;
+                sm.sbits[sub >> 5] = 0;
+            }
+            if (tid == 0) sm.nsurv = 0;
+            __syncthreads();
+            par ^= 1u;
+            continue;
+        }
+        // ---- many survivors: the sub-bucket machinery of k2_group2 -------------------------------------------------------------
+        uint32_t sr[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sr[k] = 0xFFFFFFFFu;
+            if (keepm & (1u << k)) {
+                const uint32_t s = (uint32_t)(e[k] >> a.sub_shift) & a.sub_mask;
+                sr[k] = s | (atomicAdd(&sm.cnt[s], 1u) << 16);
+            }
+        }
+        __syncthreads();
         // ---- B: scan the sizes of sub-buckets with >= 2 survivors (counters back to zero) ----------------------------------
         {
             uint4* c4 = reinterpret_cast<uint4*>(&sm.cnt[8 * tid]);
@@ -218,6 +270,7 @@ __global__ void __launch_bounds__(G2_THREADS, 4) k5_bucket(const RunBucketArgs a
             const uint32_t sub = (uint32_t)(sm.skey[i] >> a.rest_bits) & a.sub_mask;
             sm.sbits[sub >> 5] = 0;
         }
+        if (tid == 0) sm.nsurv = 0;
         __syncthreads();
         par ^= 1u;
     }

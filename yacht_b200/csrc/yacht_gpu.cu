@@ -747,7 +747,8 @@ extern "C" int ygpu_build_index(ygpu_ctx* ctx, ygpu_index_stats* stats) {
 // ============================================================================================
 #define K3_THREADS 256
 #define K3_TOUCH_CAP 4096      // distinct columns tracked per (row, tile) before falling back to a dense scan
-#define K3_LONG_CAP 256        // posting segments longer than K3_LONG_LEN are expanded by the whole CTA
+#define K3_LONG_CAP 1024       // posting segments longer than K3_LONG_LEN are expanded by the whole CTA, chunk by chunk of the
+                               // work list (a chunk = one item per thread, so the queue can never overflow)
 #define K3_LONG_LEN 64
 
 struct K3Params {
@@ -920,53 +921,61 @@ __global__ void __launch_bounds__(1024) k3_count_flag(const K3Params p) {
         // upper triangle: only columns > row matter
         if (c1 > row + 1 && ie > ib) {
             // ---- accumulate -----------------------------------------------------------------
+            // The work list is walked in chunks of one item per thread.  Short posting segments are expanded by the thread that
+            // holds the item; long ones (a hash held by thousands of genomes: the dense clusters of a skewed database) are queued
+            // and expanded by the whole CTA after every chunk -- a row of such a cluster carries thousands of long segments, and
+            // a thread walking 5 000 postings alone is what made the count of config 4 take minutes.
             uint64_t item = item_cur;
-            for (uint64_t it = ib + threadIdx.x; it < ie;) {
-                const uint32_t inl = (uint32_t)item & 3u;
-                if (inl) {                                         // the following genome ids are inside the item
-                    for (uint32_t e = 0; e < inl; e++) {
-                        const uint32_t g = (uint32_t)(item >> (2 + YG_ITEM_INLINE_BITS * e)) & ((1u << YG_ITEM_INLINE_BITS) - 1u);
-                        if (g <= row || g < c0 || g >= c1) continue;
-                        if (acc_add<U16>(acc, g - c0) == 0) {
-                            const uint32_t k = atomicAdd(&s_nt, 1u);
-                            if (k < K3_TOUCH_CAP) touched[k] = g;
-                        }
-                    }
-                } else {
-                    const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
-                    bool queued = false;
-                    if (len > K3_LONG_LEN) {
-                        const uint32_t q = atomicAdd(&s_nlong, 1u);
-                        if (q < K3_LONG_CAP) { longq[q] = item; queued = true; }
-                    }
-                    if (!queued)
-                        for (uint32_t e = 0; e < len; e++) {
-                            const uint32_t g = p.post[start + e];
-                            if (g <= row || g < c0 || g >= c1) continue;   // g == row: duplicate hash inside the sketch
+            uint32_t long_done = 0;
+            for (uint64_t base = ib; base < ie; base += NT) {
+                const uint64_t it = base + threadIdx.x;
+                if (it < ie) {
+                    const uint32_t inl = (uint32_t)item & 3u;
+                    if (inl) {                                         // the following genome ids are inside the item
+                        for (uint32_t e = 0; e < inl; e++) {
+                            const uint32_t g = (uint32_t)(item >> (2 + YG_ITEM_INLINE_BITS * e)) & ((1u << YG_ITEM_INLINE_BITS) - 1u);
+                            if (g <= row || g < c0 || g >= c1) continue;
                             if (acc_add<U16>(acc, g - c0) == 0) {
                                 const uint32_t k = atomicAdd(&s_nt, 1u);
                                 if (k < K3_TOUCH_CAP) touched[k] = g;
                             }
                         }
-                }
-                it += NT;
-                if (it < ie) item = p.row_items[it];
-            }
-            __syncthreads();
-            const uint32_t nlong = min(s_nlong, (uint32_t)K3_LONG_CAP);
-            for (uint32_t q = 0; q < nlong; q++) {
-                const uint64_t litem = longq[q];
-                const uint32_t start = (uint32_t)(litem >> 32), len = (uint32_t)(litem >> 2) & 0x3FFFFFFFu;
-                for (uint32_t e = threadIdx.x; e < len; e += NT) {
-                    const uint32_t g = p.post[start + e];
-                    if (g <= row || g < c0 || g >= c1) continue;
-                    if (acc_add<U16>(acc, g - c0) == 0) {
-                        const uint32_t k = atomicAdd(&s_nt, 1u);
-                        if (k < K3_TOUCH_CAP) touched[k] = g;
+                    } else {
+                        const uint32_t start = (uint32_t)(item >> 32), len = (uint32_t)(item >> 2) & 0x3FFFFFFFu;
+                        if (len > K3_LONG_LEN) {
+                            longq[(atomicAdd(&s_nlong, 1u) - long_done) & (K3_LONG_CAP - 1)] = item;      // at most NT <= K3_LONG_CAP per chunk
+                        } else {
+                            for (uint32_t e = 0; e < len; e++) {
+                                const uint32_t g = p.post[start + e];
+                                if (g <= row || g < c0 || g >= c1) continue;   // g == row: duplicate hash inside the sketch
+                                if (acc_add<U16>(acc, g - c0) == 0) {
+                                    const uint32_t k = atomicAdd(&s_nt, 1u);
+                                    if (k < K3_TOUCH_CAP) touched[k] = g;
+                                }
+                            }
+                        }
                     }
+                    if (it + NT < ie) item = p.row_items[it + NT];
+                }
+                __syncthreads();
+                const uint32_t nlong = s_nlong - long_done;
+                if (nlong) {                                           // uniform
+                    for (uint32_t q = 0; q < nlong; q++) {
+                        const uint64_t litem = longq[q];
+                        const uint32_t start = (uint32_t)(litem >> 32), len = (uint32_t)(litem >> 2) & 0x3FFFFFFFu;
+                        for (uint32_t e = threadIdx.x; e < len; e += NT) {
+                            const uint32_t g = p.post[start + e];
+                            if (g <= row || g < c0 || g >= c1) continue;
+                            if (acc_add<U16>(acc, g - c0) == 0) {
+                                const uint32_t k = atomicAdd(&s_nt, 1u);
+                                if (k < K3_TOUCH_CAP) touched[k] = g;
+                            }
+                        }
+                    }
+                    long_done += nlong;
+                    __syncthreads();                                   // the queue slots are reused by the next chunk
                 }
             }
-            if (nlong) __syncthreads();
             // ---- threshold + compaction (K4), and reset of the accumulator ---------------------
             const uint32_t nt = s_nt;
             if (nt <= K3_TOUCH_CAP) {

@@ -13,11 +13,17 @@ Restates reference src/yacht/hypothesis_recovery_src.py:
   * get_exclusive_hashes (:116-206): python-set semantics -- among the nontrivial organisms a hash
     is exclusive if it occurs in exactly one organism; per organism (n_exclusive, n_exclusive in
     sample), in sub-manifest order (:160-163).
+    PINNED: tests/test_run_reference_golden.py checks it against 200 calls of the reference's OWN
+    get_exclusive_hashes over 50 seeded databases (tests/golden/make_run_reference_golden.py imports
+    the unmodified hypothesis_recovery_src.py + utils.py with a stand-in for the absent sourmash
+    package and commits inputs + outputs as tests/golden/run_reference_golden.npz).
   * get_alt_mut_rate (:209-230) and single_hyp_test (:233-306): restated verbatim on top of scipy
     (``binom.ppf/cdf``, ``betaincinv``), the same library calls the reference makes.
     PINNED: tests/test_oracle_pinned.py checks this restatement against the golden rows extracted
     from the reference's checked-in result workbooks (tests/golden/make_run_golden.py) and the
-    reference's own known-answer tests (tests/test_unit.py:11-20, tests/test_unittests.py:86-111).
+    reference's own known-answer tests (tests/test_unit.py:11-20, tests/test_unittests.py:86-111),
+    and tests/test_run_reference_golden.py against 24,340 evaluations of the reference's own
+    single_hyp_test (same generator).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 """

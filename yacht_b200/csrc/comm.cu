@@ -4,10 +4,11 @@
 //   * NCCL (dlopen'ed: libnccl.so.2, no link-time dependency, so single-GPU users never load it) carries the small
 //     control exchanges -- histograms, stream lengths, statistics, the pair lists -- and doubles as the cross-rank
 //     barrier between phases;
-//   * the two bulk exchanges of the sharded index build (packed words after the level-1 partition, group streams after
-//     the grouping) are NOT collectives: the producing kernels store straight into the peers' buffers over NVLink
-//     (index_msd.cu).  This file hands them the peer pointers: cudaIpc handles between processes, plain pointers plus
-//     cudaDeviceEnablePeerAccess between threads of one process.
+//   * the bulk exchanges of the sharded step (work items and the posting stream of large groups out of the grouping
+//     kernel; with genome-range residency also the packed words of the level-1 partition) are NOT collectives: the
+//     producing kernels store straight into the peers' buffers over NVLink (index_msd.cu).  This file hands them the peer
+//     pointers: cudaIpc handles between processes, plain pointers plus cudaDeviceEnablePeerAccess between threads of one
+//     process.
 //
 // The reference has no counterpart: its only parallelism is std::thread row chunks (src/cpp/main.cpp:338-349).
 #include "common.cuh"

@@ -97,6 +97,7 @@ typedef struct {
     /* sharded step: work-list build from the complete stream (k2_items_regions), the control collectives + cross-rank
      * waits between the phases, and the gather of the pair lists (inside ms_index / ms_pairsort)            */
     double ms_items, ms_sync, ms_gather;
+    double ms_sketch;       /* ygpu_sketch_sequences: the k-mer hashing kernel                                   */
 } ygpu_timings;
 
 /* Per reference genome, from ygpu_exclusive_hashes (hypothesis_recovery_src.py:194-204). */
@@ -266,6 +267,29 @@ int ygpu_alt_mut_rate(ygpu_ctx* ctx, const int64_t* nu, const int64_t* thresh, u
 int ygpu_hyp_test(ygpu_ctx* ctx, const int64_t* n_exclusive, const int64_t* n_match, uint64_t n,
                   int ksize, double significance, double ani_thresh, const double* min_coverage,
                   int n_cov, ygpu_hyp_row* rows);
+
+/* ---- sketching --------------------------------------------------------------- */
+/* What the reference delegates to `sourmash sketch dna -p k=K,scaled=S,abund` (src/yacht/sketch_ref_genomes.py:25,61;
+ * src/yacht/sketch_sample.py:32,49): FracMinHash sketches of DNA sequences.
+ * bases: HOST pointer, the records one after another, any case; whatever is not A/C/G/T (N, IUPAC codes, the separator
+ * byte the caller puts between two records -- '\n' will do) invalidates the windows that contain it.  Sketch s is made
+ * from bases[sketch_offsets[s] .. sketch_offsets[s+1]) (a window must lie inside one sketch's range).  Every window of
+ * `ksize` valid bases -> canonical k-mer (the smaller of the window and its reverse complement) -> first 64 bits of
+ * MurmurHash3_x64_128(k-mer, seed) -> kept when <= max_hash.  seed = 42 and max_hash = round((2^64 - 1) / scaled)
+ * (18446744073709552 at scaled = 1000) give sourmash's "0.murmur64" sketches.
+ * out: per sketch the distinct kept hashes, ascending (= "mins"), and how often each occurred (= "abundances");
+ * library-owned, release with ygpu_sketch_result_free.                                                               */
+typedef struct {
+    uint64_t* hashes;       /* [offsets[n_sketches]]                                            */
+    uint32_t* abundances;   /* [offsets[n_sketches]]                                            */
+    uint64_t* offsets;      /* [n_sketches + 1]                                                 */
+    uint32_t n_sketches;
+    uint32_t _pad;
+    uint64_t n_kmers;       /* valid windows hashed                                             */
+} ygpu_sketch_result;
+int ygpu_sketch_sequences(ygpu_ctx* ctx, const uint8_t* bases, uint64_t n_bases, const uint64_t* sketch_offsets,
+                          uint32_t n_sketches, int ksize, uint64_t max_hash, uint32_t seed, ygpu_sketch_result* out);
+void ygpu_sketch_result_free(ygpu_sketch_result* r);
 
 #ifdef __cplusplus
 }

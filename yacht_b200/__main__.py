@@ -1,10 +1,10 @@
-"""`python -m yacht_b200 train|run ...` -- the two sub-commands of the reference CLI that sit on the
-hot path (reference src/yacht/__init__.py:54-136); the other sub-commands (sketch, download,
-convert) are out of scope."""
+"""`python -m yacht_b200 train|run|sketch ...` -- the sub-commands of the reference CLI that sit on the
+hot path (reference src/yacht/__init__.py:54-136) plus `sketch ref|sample` (:106-121); the
+download and convert sub-commands are out of scope."""
 import argparse
 import sys
 
-from . import make_training_data_from_sketches, run_YACHT
+from . import make_training_data_from_sketches, run_YACHT, sketch_ref_genomes, sketch_sample
 from .utils import __version__
 
 
@@ -18,6 +18,14 @@ def main(argv=None):
     p_run = sub.add_parser("run", description="Run the YACHT algorithm")
     run_YACHT.add_arguments(p_run)
     p_run.set_defaults(func=run_YACHT.main)
+    p_sketch = sub.add_parser("sketch", description="Sketch reference genomes or metagenomics samples")
+    sk_sub = p_sketch.add_subparsers(dest="sketch_subcommand")
+    p_ref = sk_sub.add_parser("ref", description="Sketch fasta files and make them as references")
+    sketch_ref_genomes.add_arguments(p_ref)
+    p_ref.set_defaults(func=sketch_ref_genomes.main)
+    p_sample = sk_sub.add_parser("sample", description="Sketch metagenomics samples")
+    sketch_sample.add_arguments(p_sample)
+    p_sample.set_defaults(func=sketch_sample.main)
     args = parser.parse_args(argv)
     if "func" not in args:
         parser.print_help(file=sys.stderr)

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "ygpu_upload_begin", "ygpu_upload_block", "ygpu_upload_finish", "ygpu_greedy_select",
     "ygpu_comm_get_unique_id", "ygpu_comm_init", "ygpu_comm_destroy", "ygpu_load_sketches_sharded", "ygpu_load_sketches_sharded_device",
     "ygpu_train_step_sharded", "ygpu_upload_finish_sharded", "ygpu_load_sketches_hashrange", "ygpu_load_sketches_hashrange_device",
-    "ygpu_train_step_replicated",
+    "ygpu_train_step_replicated", "ygpu_sketch_sequences", "ygpu_sketch_result_free",
 ]
 COMM_ID_BYTES = 128
 
@@ -50,10 +50,17 @@ class Timings(ctypes.Structure):
                 ("n_kernel_launches", ctypes.c_uint64), ("n_library_launches", ctypes.c_uint64),
                 ("ms_hist1", ctypes.c_double), ("ms_scatter1", ctypes.c_double), ("ms_hist2", ctypes.c_double),
                 ("ms_scatter2", ctypes.c_double), ("ms_group", ctypes.c_double), ("ms_sample_kernels", ctypes.c_double),
-                ("ms_items", ctypes.c_double), ("ms_sync", ctypes.c_double), ("ms_gather", ctypes.c_double)]
+                ("ms_items", ctypes.c_double), ("ms_sync", ctypes.c_double), ("ms_gather", ctypes.c_double),
+                ("ms_sketch", ctypes.c_double)]
 
     def as_dict(self) -> dict:
         return {k: (float(getattr(self, k)) if t is ctypes.c_double else int(getattr(self, k))) for k, t in self._fields_}
+
+
+class SketchResult(ctypes.Structure):
+    _fields_ = [("hashes", ctypes.POINTER(ctypes.c_uint64)), ("abundances", ctypes.POINTER(ctypes.c_uint32)),
+                ("offsets", ctypes.POINTER(ctypes.c_uint64)), ("n_sketches", ctypes.c_uint32), ("_pad", ctypes.c_uint32),
+                ("n_kmers", ctypes.c_uint64)]
 
 
 class SketchSet(ctypes.Structure):
@@ -133,6 +140,9 @@ def load_library() -> ctypes.CDLL:
     lib.ygpu_upload_finish_sharded.argtypes = [vp, vp, u32, vp, u32, u32, u32]
     lib.ygpu_train_step_replicated.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
     lib.ygpu_train_step_sharded.argtypes = [vp, ctypes.c_double, ctypes.POINTER(IndexStats), ctypes.POINTER(u64)]
+    lib.ygpu_sketch_sequences.argtypes = [vp, vp, u64, vp, u32, ctypes.c_int, u64, u32, ctypes.POINTER(SketchResult)]
+    lib.ygpu_sketch_result_free.argtypes = [ctypes.POINTER(SketchResult)]
+    lib.ygpu_sketch_result_free.restype = None
     for name in ABI_SYMBOLS:
         getattr(lib, name)  # AttributeError here means the .so does not match include/yacht_gpu.h
     _lib = lib
@@ -319,6 +329,29 @@ class GpuContext:
         b = np.zeros(nparts + 1, dtype=np.uint32)
         self._check(self.lib.ygpu_row_partition(self.h, int(nparts), b.ctypes.data), "ygpu_row_partition")
         return b
+
+    # -- sketching ----------------------------------------------------------------------------
+    def sketch_sequences(self, bases, sketch_offsets: Sequence[int], ksize: int, max_hash: int, seed: int = 42):
+        """FracMinHash sketches of bases[sketch_offsets[s]:sketch_offsets[s+1]] (bytes / uint8 array; anything that is not
+        A/C/G/T, e.g. the '\\n' between two records, breaks the windows).  Returns (hashes, abundances, offsets, n_kmers):
+        per sketch the distinct kept hashes ascending and how often each occurred."""
+        arr = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray, memoryview)) else np.ascontiguousarray(bases, dtype=np.uint8)
+        off = np.ascontiguousarray(sketch_offsets, dtype=np.uint64)
+        res = SketchResult()
+        self._check(self.lib.ygpu_sketch_sequences(self.h, arr.ctypes.data if arr.size else None, arr.size, off.ctypes.data, off.shape[0] - 1,
+                                                   int(ksize), int(max_hash), int(seed), ctypes.byref(res)), "ygpu_sketch_sequences")
+        try:
+            ns = int(res.n_sketches)
+            offsets = np.ctypeslib.as_array(res.offsets, shape=(ns + 1,)).copy()
+            total = int(offsets[-1])
+            if total:
+                hashes = np.ctypeslib.as_array(res.hashes, shape=(total,)).copy()
+                abund = np.ctypeslib.as_array(res.abundances, shape=(total,)).copy()
+            else:
+                hashes, abund = np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+            return hashes, abund, offsets, int(res.n_kmers)
+        finally:
+            self.lib.ygpu_sketch_result_free(ctypes.byref(res))
 
     # -- run path -----------------------------------------------------------------------------
     def exclusive_hashes(self, sample: np.ndarray, mask: Optional[np.ndarray] = None) -> np.ndarray:

@@ -131,6 +131,7 @@ struct ygpu_ctx {
 
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
     void* upload = nullptr;         // streaming ingest state (yacht_gpu.cu: ygpu_upload_*)
+    void* sketch_scratch = nullptr; // sketching buffers (sketch.cu)
 
     ygpu_timings tm = {};
 };
@@ -228,4 +229,6 @@ int ygpu_run_counts_buckets(ygpu_ctx* ctx, const uint64_t* d_sample, uint64_t n_
 void ygpu_part_release(ygpu_ctx* ctx);
 // run path (run_kernels.cu)
 void ygpu_run_release(ygpu_ctx* ctx);
+// sketching (sketch.cu)
+void ygpu_sketch_release(ygpu_ctx* ctx);
 void ygpu_upload_release(ygpu_ctx* ctx);

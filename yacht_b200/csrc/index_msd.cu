@@ -860,10 +860,11 @@ __global__ void __launch_bounds__(G2_THREADS, MIN_CTAS) k2_group2(const GroupArg
             const uint32_t ex = wp + inc - sum;
             uint32_t px = ex & 0xffffu, py = nx + (ex >> 16);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                uint32_t v = 0;
-                if (c[i] == 2) { v = px | (2u << 16); px += 2; }
-                else if (c[i] >= 3) { v = py | (c[i] << 16); py += c[i]; }
+            for (int i = 0; i < 8; i++) {                            // branch-free: the lanes of a warp see every mix of sizes
+                const bool two = c[i] == 2, more = c[i] >= 3;
+                const uint32_t v = two ? (px | (2u << 16)) : (more ? (py | (c[i] << 16)) : 0u);
+                px += two ? 2u : 0u;
+                py += more ? c[i] : 0u;
                 c[i] = v;
             }
             c4[0] = make_uint4(c[0], c[1], c[2], c[3]);

@@ -142,6 +142,7 @@ extern "C" void ygpu_ctx_destroy(ygpu_ctx* ctx) {
     free_all(ctx);
     ygpu_run_release(ctx);
     ygpu_part_release(ctx);
+    ygpu_sketch_release(ctx);
     ygpu_upload_release(ctx);
     ygpu_comm_destroy(ctx);
     if (ctx->d_pairs_local) cudaFree(ctx->d_pairs_local);

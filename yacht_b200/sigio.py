@@ -215,6 +215,22 @@ def write_signature(path: str, name: str, mins: Sequence[int], ksize: int = 31,
     return compute_md5sum(ksize, [int(x) for x in mins])
 
 
+def write_signatures(path: str, sketches: Sequence[dict], ksize: int = 31, max_hash: int = MAX_HASH_SCALED_1000) -> None:
+    """One JSON signature file holding several sketches (what ``sourmash sketch dna -o x.sig`` writes for several
+    records); gzip when ``path`` ends in .gz.  ``sketches``: dicts with ``name``, ``mins`` and optional ``abundances``,
+    ``filename``."""
+    recs = []
+    for sk in sketches:
+        recs.extend(json.loads(signature_json(sk["name"], sk["mins"], ksize, sk.get("abundances"), max_hash, sk.get("filename", ""))))
+    data = json.dumps(recs, separators=(",", ":")).encode()
+    if path.endswith(".gz"):
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(data)
+    else:
+        with open(path, "wb") as f:
+            f.write(data)
+
+
 def write_sig_zip(zip_path: str, sketches: Sequence[dict], ksize: int = 31,
                   max_hash: int = MAX_HASH_SCALED_1000) -> None:
     """Write a sourmash-style zip database (manifest + signatures/<md5>.sig.gz).

@@ -113,3 +113,35 @@ def test_exe_real_signature_layout(tmp_path):
     got = to.parse_core_outputs(wd, paths, sel, cp.stdout)
     assert got.lines == ["0,1,0.5,0.666667,0.666667", "1,0,0.5,0.666667,0.666667"]
     assert (got.n_distinct, got.n_singleton, got.n_index) == (4, 2, 2)
+
+
+def _n_gpus():
+    from yacht_b200 import _lib
+    return _lib.load_library().ygpu_device_count()
+
+
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+def test_exe_multi_gpu_output_equals_single_gpu(ngpu, tmp_path):
+    """YACHT_NUM_GPUS=k: threads as ranks, hash-range residency, sharded step (the replicated step when the database does not
+    qualify) -- the files must be byte-identical to the single-GPU run's."""
+    if _n_gpus() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    from yacht_b200 import synth
+    outs = {}
+    for label, seed_db in (("clustered", synth.make_reference_db(3000, 5, mean_size=1500, sd_size=300)),
+                           ("skewed", synth.make_skewed_db(1500, seed=9, mean_size=600, sd_size=100, zipf_cap=900, core_hashes=40))):
+        for k in (1, ngpu):
+            wd = str(tmp_path / f"{label}_{k}")
+            os.makedirs(wd)
+            to.write_sig_dir(seed_db.hashes, seed_db.offsets, wd)
+            cp, sel = run_exe(wd, 0.95 ** 31, 4, 2, {"YACHT_NUM_GPUS": str(k)})
+            assert cp.returncode == 0, cp.stderr
+            files = {}
+            for fn in sorted(glob.glob(os.path.join(wd, "*_*.txt"))):
+                with open(fn) as f:
+                    files[os.path.basename(fn)] = f.read()
+            with open(sel) as f:
+                files["selected"] = [os.path.basename(x) for x in f.read().split()]
+            outs[(label, k)] = files
+        assert outs[(label, 1)] == outs[(label, ngpu)], label
+        assert sum(len(v) for kf, v in outs[(label, 1)].items() if kf != "selected") > 0

@@ -119,3 +119,80 @@ def test_reader_and_oracle_reader_agree(tmp_path):
         b = sketch.read_records(path)
         assert [(n, s) for n, s in a] == [(n, s) for n, s in b], path
         assert [(n, s) for n, s in a] == recs, path
+
+
+class _OracleBackedContext:
+    """Stands in for the GPU context so that the HOST logic of yacht_b200/sketch.py (record separators, batching, merging of
+    partial sketches, writers) can be exercised on CPU; the device call itself is covered by tests/test_sketch_gpu.py."""
+    def __init__(self):
+        self.calls = []
+
+    def sketch_sequences(self, bases, offsets, ksize, max_hash, seed=42):
+        bases = bytes(bases)
+        self.calls.append(len(bases))
+        hs, ab, off = [], [], [0]
+        lib = so._load()
+        for s in range(len(offsets) - 1):
+            chunk = bases[int(offsets[s]):int(offsets[s + 1])]
+            n = len(chunk)
+            kept = np.empty(max(n, 1), dtype=np.uint64)
+            buf = np.frombuffer(chunk, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+            got = lib.so_sketch_record(buf.ctypes.data, n, ksize, seed, max_hash, kept.ctypes.data, n) if n >= ksize else 0
+            m, a = np.unique(kept[:got], return_counts=True)
+            hs.append(m.astype(np.uint64)); ab.append(a.astype(np.uint32)); off.append(off[-1] + len(m))
+        return np.concatenate(hs), np.concatenate(ab), np.array(off, np.uint64), 0
+
+
+def test_host_batching_and_merging(monkeypatch):
+    from yacht_b200 import sketch
+    fake = _OracleBackedContext()
+    monkeypatch.setattr(sketch, "_context", lambda: fake)
+    monkeypatch.setattr(sketch, "BATCH_BASES", 50_000)
+    rng = np.random.default_rng(23)
+    unit = _random_sequence(rng, 30_000, p_bad=0.0)
+    groups = [[unit, unit[:10_000], _random_sequence(rng, 45_000), unit], [_random_sequence(rng, 5_000)], [], [_random_sequence(rng, 70_000)],
+              [b"ACGT"], [_random_sequence(rng, 20_000), _random_sequence(rng, 20_000), _random_sequence(rng, 20_000)]]
+    got = sketch.sketch_record_groups(groups, 31, 50)
+    assert len(fake.calls) >= 4 and len(got) == len(groups)
+    for g, (mins, ab) in zip(groups, got):
+        em, ea = so.sketch_records([s.replace(b"\n", b"N") for s in g], 31, 50)
+        assert np.array_equal(mins, em) and np.array_equal(ab, ea)
+
+
+def test_sketch_ref_and_sample_writers(tmp_path, monkeypatch):
+    import argparse
+    from yacht_b200 import sigio, sketch, sketch_ref_genomes, sketch_sample
+    monkeypatch.setattr(sketch, "_context", lambda: _OracleBackedContext())
+    rng = np.random.default_rng(5)
+    folder = tmp_path / "g"
+    folder.mkdir()
+    recs = {}
+    for g, ext in enumerate([".fna.gz", ".fa", ".fasta"]):
+        rs = [(f"c{g}_{c}", _random_sequence(rng, 30_000).replace(b"\n", b"N").replace(b"*", b"N")) for c in range(2)]
+        path = folder / f"G{g}{ext}"
+        opener = gzip.open if ext.endswith(".gz") else open
+        with opener(path, "wb") as f:
+            for n, s in rs:
+                f.write(b">" + n.encode() + b"\n" + s + b"\n")
+        recs[f"G{g}"] = rs
+    out = tmp_path / "ref.sig.zip"
+    sketch_ref_genomes.main(argparse.Namespace(infile=str(folder), kmer=31, scaled=100, outfile=str(out)))
+    sigs = {s.name: s for s in sigio.read_sig_zip(str(out))}
+    assert sorted(sigs) == sorted(recs)
+    for name, rs in recs.items():
+        em, ea = so.sketch_records([s for _, s in rs], 31, 100)
+        assert np.array_equal(np.asarray(sigs[name].mins, np.uint64), em)
+        assert np.array_equal(np.asarray(sigs[name].abundances, np.uint32), ea)
+        assert sigs[name].scaled == 100 and sigs[name].ksize == 31
+    # the zip a `yacht train` run starts from: loadable per k-mer size like any sourmash database
+    fq = tmp_path / "s.fq"
+    with open(fq, "wb") as f:
+        for n, s in recs["G1"]:
+            f.write(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    out2 = tmp_path / "sample.sig.zip"
+    sketch_sample.main(argparse.Namespace(infile=[str(fq)], kmer=31, scaled=100, outfile=str(out2)))
+    sig = sigio.load_signature_with_ksize(str(out2), 31)
+    em, ea = so.sketch_records([s for _, s in recs["G1"]], 31, 100)
+    assert np.array_equal(np.asarray(sig.mins, np.uint64), em) and np.array_equal(np.asarray(sig.abundances, np.uint32), ea)
+    with pytest.raises(ValueError):
+        sketch_sample.main(argparse.Namespace(infile=["a", "b", "c"], kmer=31, scaled=100, outfile=str(out2)))

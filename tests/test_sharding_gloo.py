@@ -184,3 +184,38 @@ def test_exchange_plan_properties():
             _check_plan(_Db, world, hists, plan)
     z = sharding.exchange_plan(np.zeros((2, 4), dtype=np.int64))
     assert z["count"].tolist() == [0, 0] and z["total"] == 0
+
+
+def test_hash_range_shares_partition_every_sketch():
+    """hash-range residency (ygpu_load_sketches_hashrange): the ranks' shares are disjoint, cover every sketch, keep the order,
+    and equal hashes land on one rank."""
+    from yacht_b200 import sharding, synth
+    db = synth.make_reference_db(300, 17, mean_size=400, sd_size=120)
+    offsets = np.asarray(db.offsets)
+    for nranks in (1, 2, 3, 8):
+        cuts = sharding.hash_cuts(int(db.hashes.max()), nranks)
+        assert len(cuts) == nranks + 1 and cuts[0] == 0 and int(cuts[-1]) == 2 ** 64 - 1
+        assert all(int(cuts[r]) <= int(cuts[r + 1]) for r in range(nranks))
+        shares = [sharding.hashrange_share(db.hashes, offsets, int(cuts[r]), int(cuts[r + 1]), last=r == nranks - 1) for r in range(nranks)]
+        assert sum(len(h) for h, _ in shares) == len(db.hashes)
+        for g in range(0, db.n, 7):
+            pieces = [h[int(o[g]):int(o[g + 1])] for h, o in shares]
+            whole = db.hashes[int(offsets[g]):int(offsets[g + 1])]
+            assert np.array_equal(np.concatenate(pieces), whole)          # sketches are sorted: the pieces concatenate back
+            for r, piece in enumerate(pieces):
+                if len(piece):
+                    assert int(piece.min()) >= int(cuts[r])
+                    assert int(piece.max()) < int(cuts[r + 1]) or r == nranks - 1
+        sizes = [len(h) for h, _ in shares]
+        assert max(sizes) - min(sizes) <= 0.1 * len(db.hashes) / nranks + 50      # uniform hashes: equal-width ranges balance
+
+
+def test_hash_range_share_keeps_the_largest_hash_on_the_last_rank():
+    from yacht_b200 import sharding
+    hashes = np.array([0, 5, 2 ** 64 - 1, 7, 2 ** 64 - 1], dtype=np.uint64)
+    offsets = np.array([0, 3, 5], dtype=np.uint64)
+    cuts = sharding.hash_cuts(2 ** 64 - 1, 2)
+    a = sharding.hashrange_share(hashes, offsets, int(cuts[0]), int(cuts[1]))
+    b = sharding.hashrange_share(hashes, offsets, int(cuts[1]), int(cuts[2]), last=True)
+    assert a[0].tolist() == [0, 5, 7] and a[1].tolist() == [0, 2, 3]
+    assert b[0].tolist() == [2 ** 64 - 1, 2 ** 64 - 1] and b[1].tolist() == [0, 1, 2]

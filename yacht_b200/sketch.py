@@ -125,13 +125,22 @@ def sketch_record_groups(groups: Sequence[Sequence[bytes]], ksize: int, scaled: 
     return [o if o is not None else empty for o in out]
 
 
-def sketch_files(paths: Sequence[str], ksize: int, scaled: int, singleton: bool = False, names: Optional[Sequence[str]] = None):
+def sketch_files(paths: Sequence[str], ksize: int, scaled: int, singleton: bool = False, names: Optional[Sequence[str]] = None,
+                 threads: Optional[int] = None):
     """Sketch dicts ({name, filename, mins, abundances}) ready for sigio.write_sig_zip: one per file (all records together,
     like ``sourmash sketch fromfile`` / ``sketch dna``) or, with ``singleton``, one per record (``--singleton``)."""
     groups: List[List[bytes]] = []
     meta: List[Tuple[str, str]] = []
+    # gunzip + splitting release the GIL for most of their time: read the files on a few host threads, in order
+    threads = max(1, min(len(paths), int(threads or os.cpu_count() or 1)))
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as pool:
+            all_recs = list(pool.map(read_records, paths))
+    else:
+        all_recs = [read_records(p) for p in paths]
     for i, path in enumerate(paths):
-        recs = read_records(path)
+        recs = all_recs[i]
         if singleton:
             for name, seq in recs:
                 groups.append([seq])

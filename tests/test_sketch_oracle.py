@@ -176,6 +176,7 @@ def test_sketch_ref_and_sample_writers(tmp_path, monkeypatch):
                 f.write(b">" + n.encode() + b"\n" + s + b"\n")
         recs[f"G{g}"] = rs
     out = tmp_path / "ref.sig.zip"
+    monkeypatch.setattr(sketch, "CHUNK_FILE_BYTES", 40_000)          # forces several read-ahead chunks
     sketch_ref_genomes.main(argparse.Namespace(infile=str(folder), kmer=31, scaled=100, outfile=str(out)))
     sigs = {s.name: s for s in sigio.read_sig_zip(str(out))}
     assert sorted(sigs) == sorted(recs)

@@ -17,6 +17,7 @@ from . import _lib, sigio
 
 SEED = 42                       # "seed": 42 in every sourmash DNA signature
 BATCH_BASES = 1 << 31           # bases per device call (2 GiB of sequence + separators)
+CHUNK_FILE_BYTES = 1 << 29      # on-disk bytes of sequence files read ahead of the device (gzip expands ~3.5x)
 _ctx = None
 
 
@@ -128,29 +129,40 @@ def sketch_record_groups(groups: Sequence[Sequence[bytes]], ksize: int, scaled: 
 def sketch_files(paths: Sequence[str], ksize: int, scaled: int, singleton: bool = False, names: Optional[Sequence[str]] = None,
                  threads: Optional[int] = None):
     """Sketch dicts ({name, filename, mins, abundances}) ready for sigio.write_sig_zip: one per file (all records together,
-    like ``sourmash sketch fromfile`` / ``sketch dna``) or, with ``singleton``, one per record (``--singleton``)."""
-    groups: List[List[bytes]] = []
-    meta: List[Tuple[str, str]] = []
-    # gunzip + splitting release the GIL for most of their time: read the files on a few host threads, in order
-    threads = max(1, min(len(paths), int(threads or os.cpu_count() or 1)))
-    if threads > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(threads) as pool:
-            all_recs = list(pool.map(read_records, paths))
-    else:
-        all_recs = [read_records(p) for p in paths]
-    for i, path in enumerate(paths):
-        recs = all_recs[i]
-        if singleton:
-            for name, seq in recs:
-                groups.append([seq])
-                meta.append((name, path))
+    like ``sourmash sketch fromfile`` / ``sketch dna``) or, with ``singleton``, one per record (``--singleton``).
+    Files are taken in chunks of ~CHUNK_FILE_BYTES on disk so that a large collection never sits in host memory at once."""
+    threads = max(1, int(threads or os.cpu_count() or 1))
+    out: List[dict] = []
+    i = 0
+    while i < len(paths):
+        j, size = i, 0
+        while j < len(paths) and (j == i or size + os.path.getsize(paths[j]) <= CHUNK_FILE_BYTES):
+            size += os.path.getsize(paths[j])
+            j += 1
+        chunk = list(paths[i:j])
+        # gunzip + splitting release the GIL for most of their time: read the chunk's files on host threads, in order
+        if threads > 1 and len(chunk) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(min(threads, len(chunk))) as pool:
+                all_recs = list(pool.map(read_records, chunk))
         else:
-            groups.append([seq for _, seq in recs])
-            meta.append((names[i] if names is not None else "", path))
-    sketches = sketch_record_groups(groups, ksize, scaled)
-    return [{"name": name, "filename": filename, "mins": mins, "abundances": ab}
-            for (name, filename), (mins, ab) in zip(meta, sketches)]
+            all_recs = [read_records(p) for p in chunk]
+        groups: List[List[bytes]] = []
+        meta: List[Tuple[str, str]] = []
+        for k, (path, recs) in enumerate(zip(chunk, all_recs)):
+            if singleton:
+                for name, seq in recs:
+                    groups.append([seq])
+                    meta.append((name, path))
+            else:
+                groups.append([seq for _, seq in recs])
+                meta.append((names[i + k] if names is not None else "", path))
+        del all_recs
+        sketches = sketch_record_groups(groups, ksize, scaled)
+        out.extend({"name": name, "filename": filename, "mins": mins, "abundances": ab}
+                   for (name, filename), (mins, ab) in zip(meta, sketches))
+        i = j
+    return out
 
 
 def write_sketches(outfile: str, sketches: Sequence[dict], ksize: int, scaled: int) -> None:

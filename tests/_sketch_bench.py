@@ -33,6 +33,14 @@ def main():
             print(f"rep {rep}: kernel {tm['ms_sketch']:.3f} ms, h2d {tm['ms_h2d']:.1f} ms, wall {wall * 1e3:.1f} ms, {len(h)} distinct hashes, {n_kmers} k-mers", flush=True)
         res.update({"kernel_ms": tm["ms_sketch"], "h2d_ms": tm["ms_h2d"], "wall_ms": wall * 1e3, "kmers": n_kmers, "distinct_hashes": int(len(h)),
                     "kernel_kmers_per_s": n_kmers / (tm["ms_sketch"] * 1e-3), "kernel_GBps_bases": n / (tm["ms_sketch"] * 1e-3) / 1e9})
+        ctx.set_option("sketch_kernel", 2)          # A/B: the byte-wise kernel (any k) on the same input
+        for rep in range(2):
+            ctx.reset_timers()
+            h2, a2, _, _ = ctx.sketch_sequences(bases, [0, n], 31, mh)
+            tm2 = ctx.timings()
+        ctx.set_option("sketch_kernel", 0)
+        print(f"byte-wise kernel: {tm2['ms_sketch']:.3f} ms, same result: {bool(np.array_equal(h, h2) and np.array_equal(a, a2))}", flush=True)
+        res.update({"kernel_ms_bytewise": tm2["ms_sketch"], "bytewise_same_result": bool(np.array_equal(h, h2) and np.array_equal(a, a2))})
         m = 1 << 24
         t0 = time.perf_counter()
         em, ea = so.sketch_records([bases[:m].tobytes()], 31, 1000)

@@ -47,6 +47,25 @@ def test_one_sketch_matches_oracle(gpu_ctx, k, scaled):
     assert 0 < n_kmers <= n - k + 1
 
 
+@pytest.mark.parametrize("k,scaled", [(31, 100), (21, 10), (32, 50), (5, 1)])
+def test_bytewise_kernel_forced_for_small_k(gpu_ctx, k, scaled):
+    """k <= 32 normally takes the packed-word kernel; the byte-wise one (any k) must agree with it and with the oracle"""
+    rng = np.random.default_rng(300 + k)
+    n = 200_000 if scaled >= 10 else 30_000
+    bases = _random_sequence(rng, n, p_bad=0.01)
+    offsets = [0, 1234, 1234, 77_777 if n > 77_777 else 5000, n]
+    packed = gpu_ctx.sketch_sequences(bases, offsets, k, so.max_hash_for_scaled(scaled))
+    gpu_ctx.set_option("sketch_kernel", 2)
+    try:
+        bytewise = gpu_ctx.sketch_sequences(bases, offsets, k, so.max_hash_for_scaled(scaled))
+        _check(gpu_ctx, bases, offsets, k, scaled)
+    finally:
+        gpu_ctx.set_option("sketch_kernel", 0)
+    for a, b in zip(packed, bytewise):
+        assert np.array_equal(a, b)
+    _check(gpu_ctx, bases, offsets, k, scaled)
+
+
 def test_repeats_give_abundances(gpu_ctx):
     rng = np.random.default_rng(7)
     unit = _random_sequence(rng, 50_000, p_bad=0.0)

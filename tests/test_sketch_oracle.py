@@ -66,6 +66,10 @@ def host_hash(tmp_path_factory):
     lib = ctypes.CDLL(str(out))
     lib.hh_hash_windows.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]
     lib.hh_hash_windows.restype = ctypes.c_uint64
+    lib.hh_hash_windows_packed.argtypes = lib.hh_hash_windows.argtypes
+    lib.hh_hash_windows_packed.restype = ctypes.c_uint64
+    lib.hh_tile_walk_packed.argtypes = lib.hh_hash_windows.argtypes
+    lib.hh_tile_walk_packed.restype = ctypes.c_uint64
     return lib
 
 
@@ -82,6 +86,39 @@ def test_device_hash_code_matches_oracle(host_hash, k):
     n_got = host_hash.hh_hash_windows(buf.ctypes.data, n, k, 42, got.ctypes.data)
     assert n_got == n_exp and n_exp > 1000
     assert np.array_equal(got[:n_got], exp[:n_exp])
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_device_packed_hash_code_matches_oracle(host_hash, k):
+    """the k <= 32 path of the kernel: window = one 64-bit word of 2-bit codes"""
+    rng = np.random.default_rng(1000 + k)
+    seq = _random_sequence(rng, 6000) + b"ACGT" * 12 + b"AATT" * 10 + b"A" * 40 + b"GAATTC" * 8
+    lib = so._load()
+    n = len(seq)
+    buf = np.frombuffer(seq, dtype=np.uint8)
+    exp = np.empty(n, dtype=np.uint64)
+    got = np.empty(n, dtype=np.uint64)
+    for seed in (42, 0, 0xFFFFFFFF):
+        n_exp = lib.so_sketch_record(buf.ctypes.data, n, k, seed, 2 ** 64 - 1, exp.ctypes.data, n)
+        n_got = host_hash.hh_hash_windows_packed(buf.ctypes.data, n, k, seed, got.ctypes.data)
+        assert n_got == n_exp and n_exp > 100
+        assert np.array_equal(got[:n_got], exp[:n_exp]), (k, seed)
+
+
+@pytest.mark.parametrize("k,n", [(31, 20000), (32, 9000), (21, 4096 * 2), (1, 4097), (16, 4095), (31, 4096 + 30), (31, 31), (31, 30), (7, 12345)])
+def test_packed_tile_walk_matches_oracle(host_hash, k, n):
+    """the packed kernel's shared-memory layout and per-thread window extraction, walked on the host with the kernel's own helpers"""
+    rng = np.random.default_rng(k * 100003 + n)
+    for p_bad in (0.0, 0.01, 0.2):
+        seq = _random_sequence(rng, n, p_bad=p_bad)
+        lib = so._load()
+        buf = np.frombuffer(seq, dtype=np.uint8)
+        exp = np.empty(n + 1, dtype=np.uint64)
+        got = np.empty(n + 1, dtype=np.uint64)
+        n_exp = lib.so_sketch_record(buf.ctypes.data, n, k, 42, 2 ** 64 - 1, exp.ctypes.data, n)
+        n_got = host_hash.hh_tile_walk_packed(buf.ctypes.data, n, k, 42, got.ctypes.data)
+        assert n_got == n_exp, (k, n, p_bad)
+        assert np.array_equal(got[:n_got], exp[:n_exp]), (k, n, p_bad)
 
 
 def test_device_hash_code_palindromes_and_seed(host_hash):

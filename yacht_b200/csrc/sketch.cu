@@ -4,7 +4,9 @@
 // src/yacht/sketch_sample.py:32,49): every window of K valid bases of every record -> canonical k-mer -> murmur64(seed) ->
 // kept when <= max_hash; per sketch the distinct kept hashes, ascending, with their abundances.
 //
-//   k_sketch_hash : one CTA per tile of 4 096 window starts.  The tile (+ K - 1 bytes) is brought into shared memory with
+//   k_sketch_hash_packed (k <= 32) : the same tile as 2-bit codes; windows are 64-bit words, canonical choice and ASCII
+//                   expansion are word operations (ysk_canonical_hash_packed).  Three conflict-free loads per 16 windows.
+//   k_sketch_hash (any k <= 256) : one CTA per tile of 4 096 window starts.  The tile (+ K - 1 bytes) is brought into shared memory with
 //                   16-byte loads and reduced to 2-bit codes on the way; a thread walks 16 consecutive starts with a rolling
 //                   "valid bases so far" counter, so a window costs one code load for validity, ~1.3 compares for the
 //                   canonical choice and the hash itself.  Integer-ALU bound (a few hundred instructions per window,
@@ -26,6 +28,7 @@ constexpr int SK_NT = 256;
 constexpr int SK_PER = 16;                      // consecutive window starts per thread
 constexpr int SK_TILE = SK_NT * SK_PER;         // 4096
 constexpr int SK_KMAX = 256;                    // largest supported k-mer size
+static_assert(SK_PER == 16 && SK_NT == 256, "the packed kernel's span layout (sketch_hash.cuh) assumes 16 windows per thread");
 constexpr int SK_PAD = SK_TILE + SK_KMAX + 16;  // zero bytes behind the bases: the last tile is loaded without bounds checks
 
 struct SketchScratch {
@@ -104,6 +107,65 @@ __global__ void __launch_bounds__(SK_NT) k_sketch_hash(const uint8_t* __restrict
     if ((tid & 31) == 0 && valid_kmers) atomicAdd(&cnt[1], valid_kmers);
 }
 
+// k <= 32: the tile lives in shared memory as 2-bit codes (16 bases per word) plus one "not A/C/G/T" bit per base.  A thread
+// reads its 48-base span with three conflict-free word loads, a window is one funnel shift away, and canonical choice and
+// ASCII expansion work on whole words (bit reversal, PRMT) -- see ysk_canonical_hash_packed.
+__global__ void __launch_bounds__(SK_NT) k_sketch_hash_packed(const uint8_t* __restrict__ bases, uint64_t n_bases,
+                                                              const uint64_t* __restrict__ sk_off, uint32_t n_sketches, int k, uint32_t seed,
+                                                              uint64_t max_hash, uint64_t* __restrict__ out_key, uint32_t* __restrict__ out_sid,
+                                                              uint64_t cap, unsigned long long* __restrict__ cnt) {
+    __shared__ uint32_t s_code[SK_TILE / 16 + 2];            // + 32 bases behind the tile (k - 1 <= 31 are needed)
+    __shared__ uint32_t s_bad[SK_TILE / 32 + 2];
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (n_bases + SK_TILE - 1) / SK_TILE;
+    unsigned long long valid_kmers = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * SK_TILE;
+        const uint4* g = (const uint4*)(bases + base);       // 16-byte aligned; the allocation is zero-padded behind n_bases
+        __syncthreads();                                     // the previous tile's readers are done
+        {
+            uint32_t code, bad;
+            const uint4 v = g[tid];
+            ysk_pack16(v.x, v.y, v.z, v.w, code, bad);
+            s_code[tid] = code;
+            const uint32_t up = __shfl_down_sync(0xffffffffu, bad, 1);
+            if (!(tid & 1)) s_bad[tid >> 1] = bad | (up << 16);
+            if (tid == 0) {                                  // the 32 bases behind the tile
+                uint32_t c0, b0, c1, b1;
+                const uint4 t0 = g[SK_TILE / 16], t1 = g[SK_TILE / 16 + 1];
+                ysk_pack16(t0.x, t0.y, t0.z, t0.w, c0, b0);
+                ysk_pack16(t1.x, t1.y, t1.z, t1.w, c1, b1);
+                s_code[SK_TILE / 16] = c0;
+                s_code[SK_TILE / 16 + 1] = c1;
+                s_bad[SK_TILE / 32] = b0 | (b1 << 16);
+            }
+        }
+        __syncthreads();
+        uint64_t lo, hi, badbits;
+        ysk_thread_span(s_code, s_bad, tid, lo, hi, badbits);
+        const uint64_t p0 = base + (uint64_t)tid * SK_PER;
+#pragma unroll 1
+        for (int i = 0; i < SK_PER; i++) {
+            const uint64_t p = p0 + i;
+            uint64_t w;
+            if (!ysk_span_window(lo, hi, badbits, i, k, w) || p + (uint64_t)k > n_bases) continue;
+            valid_kmers++;
+            const uint64_t h = ysk_canonical_hash_packed(w, k, seed);
+            if (h > max_hash) continue;
+            uint32_t a = 0, b = n_sketches;                  // sk_off[a] <= p < sk_off[b]
+            while (b - a > 1) {
+                const uint32_t mid = (a + b) >> 1;
+                if (sk_off[mid] <= p) a = mid; else b = mid;
+            }
+            if (p < sk_off[a] || p + (uint64_t)k > sk_off[a + 1]) continue;
+            const unsigned long long slot = atomicAdd(&cnt[0], 1ull);
+            if (slot < cap) { out_key[slot] = h; out_sid[slot] = a; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) valid_kmers += __shfl_down_sync(0xffffffffu, valid_kmers, o);
+    if ((tid & 31) == 0 && valid_kmers) atomicAdd(&cnt[1], valid_kmers);
+}
+
 __global__ void __launch_bounds__(256) k_sketch_heads(const uint64_t* __restrict__ key, const uint32_t* __restrict__ sid, uint64_t m,
                                                        uint32_t* __restrict__ flag) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
@@ -178,7 +240,10 @@ extern "C" int ygpu_sketch_sequences(ygpu_ctx* ctx, const uint8_t* bases, uint64
         YG_CHECK(dev_alloc(ctx, &S->d_key, cap));
         YG_CHECK(dev_alloc(ctx, &S->d_sid, cap));
         YG_CUDA(ctx, cudaMemsetAsync(S->d_cnt, 0, 2 * sizeof(unsigned long long), st));
-        k_sketch_hash<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
+        if (ksize <= 32 && ctx->sketch_kernel != 2)
+            k_sketch_hash_packed<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
+        else
+            k_sketch_hash<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
         YG_CUDA(ctx, cudaGetLastError());
         ctx->tm.n_kernel_launches++;
         YG_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));

@@ -64,3 +64,100 @@ YSK_HD uint64_t ysk_canonical_hash(const uint8_t* s, int k, uint32_t seed) {
     h1 += h2;
     return h1;
 }
+
+// ---- k <= 32: the window as one 64-bit word of 2-bit codes (base j in bits [2j+1 : 2j]) -----------------------------------
+YSK_HD uint64_t ysk_brev64(uint64_t x) {              // reverse all 64 bits
+#ifdef __CUDA_ARCH__
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    return (x >> 32) | (x << 32);
+#endif
+}
+YSK_HD uint32_t ysk_ascii4(uint32_t codes) {           // low 8 bits = 4 bases -> their 4 ASCII bytes, base 0 in the low byte
+    uint32_t s = codes & 0xFFu;
+    s = (s | (s << 4)) & 0x0F0Fu;
+    s = (s | (s << 2)) & 0x3333u;                      // nibble i = code of base i: a byte selector
+#ifdef __CUDA_ARCH__
+    return __byte_perm(0x54474341u, 0u, s);            // PRMT: byte i = "ACGT"[nibble i]
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= ((0x54474341u >> (8u * ((s >> (4 * i)) & 3u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+YSK_HD uint64_t ysk_ascii8(uint64_t c, int q) {        // bytes 8q .. 8q+7 of the k-mer held in c
+    return (uint64_t)ysk_ascii4((uint32_t)(c >> (16 * q))) | ((uint64_t)ysk_ascii4((uint32_t)(c >> (16 * q + 8))) << 32);
+}
+YSK_HD uint64_t ysk_low_bytes(int n) { return n >= 8 ? ~0ULL : ((1ULL << (8 * n)) - 1ULL); }
+
+// Same result as ysk_canonical_hash for a window of k <= 32 valid bases given as packed codes.
+YSK_HD uint64_t ysk_canonical_hash_packed(uint64_t w, int k, uint32_t seed) {
+    const uint64_t mask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+    const int sh = 64 - 2 * k;
+    w &= mask;
+    uint64_t fwm = ysk_brev64(w);                                                       // bits reversed: code j in group 31 - j, its two bits swapped
+    fwm = ((fwm & 0x5555555555555555ULL) << 1) | ((fwm >> 1) & 0x5555555555555555ULL);  // base 0 in the top two bits: integer order = string order
+    const uint64_t rcm = (~w & mask) << sh;                                             // the reverse complement, packed the same way
+    const uint64_t rcl = ~(fwm >> sh) & mask;                                           // ... and with its base 0 in the low bits
+    const uint64_t c = (fwm <= rcm) ? w : rcl;                                          // canonical k-mer, byte i = base i
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    const int nblocks = k >> 4;
+    for (int blk = 0; blk < nblocks; blk++) {
+        uint64_t k1 = ysk_ascii8(c, 2 * blk), k2 = ysk_ascii8(c, 2 * blk + 1);
+        k1 *= c1; k1 = ysk_rotl(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = ysk_rotl(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = ysk_rotl(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = ysk_rotl(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const int t = k & 15;
+    if (t > 8) {
+        uint64_t k2 = ysk_ascii8(c, 2 * nblocks + 1) & ysk_low_bytes(t - 8);
+        k2 *= c2; k2 = ysk_rotl(k2, 33); k2 *= c1; h2 ^= k2;
+    }
+    if (t > 0) {
+        uint64_t k1 = ysk_ascii8(c, 2 * nblocks) & ysk_low_bytes(t);
+        k1 *= c1; k1 = ysk_rotl(k1, 31); k1 *= c2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
+    h1 += h2; h2 += h1;
+    h1 = ysk_fmix(h1); h2 = ysk_fmix(h2);
+    h1 += h2;
+    return h1;
+}
+
+// ---- tile layout of the packed kernel: 16 bases per code word, one "not A/C/G/T" bit per base ------------------------------
+YSK_HD void ysk_pack16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t& code, uint32_t& bad) {   // 16 sequence bytes
+    const uint32_t x[4] = {x0, x1, x2, x3};
+    code = 0; bad = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; q++)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int b = 0; b < 4; b++) {
+            const uint32_t c = ysk_code((uint8_t)(x[q] >> (8 * b)));
+            code |= (c & 3u) << (2 * (4 * q + b));
+            bad |= (c >> 2) << (4 * q + b);
+        }
+}
+// What thread `tid` (16 window starts from base 16 * tid of the tile) needs: the codes of 48 bases and their "bad" bits.
+YSK_HD void ysk_thread_span(const uint32_t* s_code, const uint32_t* s_bad, int tid, uint64_t& lo, uint64_t& hi, uint64_t& badbits) {
+    lo = (uint64_t)s_code[tid] | ((uint64_t)s_code[tid + 1] << 32);                     // bases 16 tid .. 16 tid + 31
+    hi = (uint64_t)s_code[tid + 2];                                                      // bases 16 tid + 32 .. 16 tid + 47
+    badbits = ((uint64_t)s_bad[tid >> 1] | ((uint64_t)s_bad[(tid >> 1) + 1] << 32)) >> ((tid & 1) * 16);    // >= 48 bits from base 16 tid on
+}
+// Window i (0..15) of the span: false when it holds a base that is not A/C/G/T; else w = its codes (garbage above bit 2k).
+YSK_HD bool ysk_span_window(uint64_t lo, uint64_t hi, uint64_t badbits, int i, int k, uint64_t& w) {
+    const uint64_t kmask = (k >= 64) ? ~0ULL : ((1ULL << k) - 1ULL);
+    if (((badbits >> i) & kmask) != 0) return false;
+    w = i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo;
+    return true;
+}

@@ -1406,6 +1406,7 @@ extern "C" int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "big_buckets")) { ctx->big_buckets = (int)value; return 0; }
     if (!strcmp(name, "group_kernel")) { ctx->group_kernel = (int)value; return 0; }
     if (!strcmp(name, "run_path")) { ctx->run_path = (int)value; return 0; }
+    if (!strcmp(name, "sketch_kernel")) { ctx->sketch_kernel = (int)value; return 0; }
     if (!strcmp(name, "group_ctas")) { ctx->group_ctas = (int)value; return 0; }
     if (!strcmp(name, "count_thresholds")) { ctx->count_thresholds = (int)value; return 0; }
     return ygpu_fail(ctx, YGPU_ERR_ARG, "unknown option %s", name);

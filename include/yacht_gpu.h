@@ -155,7 +155,7 @@ int ygpu_elapsed_ms(ygpu_ctx* ctx, int slot_a, int slot_b, double* ms);
  * "run_path" = 0 forces the general sort-based run path (default 1: probe the partitioned reference);
  * "count_thresholds" = 0 evaluates the containment expression per pair in fp64 inside the count kernel (default 1: the
  * smallest passing count per genome is found with that expression once, the kernel compares integers);
- * "sketch_kernel" = 2 forces the byte-wise sketching kernel for every k-mer size (default 0: k <= 32 uses packed words).  */
+ * "sketch_kernel" = 2 forces the byte-wise sketching kernel for every k-mer size (default 0: k <= 64 uses packed words).  */
 int ygpu_set_option(ygpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- ingest (host side of the path) ------------------------------------------------------------ */

@@ -41,6 +41,12 @@ def main():
         ctx.set_option("sketch_kernel", 0)
         print(f"byte-wise kernel: {tm2['ms_sketch']:.3f} ms, same result: {bool(np.array_equal(h, h2) and np.array_equal(a, a2))}", flush=True)
         res.update({"kernel_ms_bytewise": tm2["ms_sketch"], "bytewise_same_result": bool(np.array_equal(h, h2) and np.array_equal(a, a2))})
+        for rep in range(2):                         # k = 51 (two-word windows)
+            ctx.reset_timers()
+            ctx.sketch_sequences(bases, [0, n], 51, mh)
+            tm3 = ctx.timings()
+        print(f"k=51: {tm3['ms_sketch']:.3f} ms", flush=True)
+        res["kernel_ms_k51"] = tm3["ms_sketch"]
         m = 1 << 24
         t0 = time.perf_counter()
         em, ea = so.sketch_records([bases[:m].tobytes()], 31, 1000)

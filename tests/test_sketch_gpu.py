@@ -47,9 +47,9 @@ def test_one_sketch_matches_oracle(gpu_ctx, k, scaled):
     assert 0 < n_kmers <= n - k + 1
 
 
-@pytest.mark.parametrize("k,scaled", [(31, 100), (21, 10), (32, 50), (5, 1)])
+@pytest.mark.parametrize("k,scaled", [(31, 100), (21, 10), (32, 50), (5, 1), (51, 100), (33, 10), (64, 20), (48, 50)])
 def test_bytewise_kernel_forced_for_small_k(gpu_ctx, k, scaled):
-    """k <= 32 normally takes the packed-word kernel; the byte-wise one (any k) must agree with it and with the oracle"""
+    """k <= 64 normally takes the packed-word kernels; the byte-wise one (any k) must agree with them and with the oracle"""
     rng = np.random.default_rng(300 + k)
     n = 200_000 if scaled >= 10 else 30_000
     bases = _random_sequence(rng, n, p_bad=0.01)
@@ -88,6 +88,8 @@ def test_many_sketches_with_empty_and_short_ranges(gpu_ctx):
     bases = np.concatenate(parts)
     _check(gpu_ctx, bases, offsets, 31, 20)
     _check(gpu_ctx, bases, offsets, 21, 1)
+    _check(gpu_ctx, bases, offsets, 51, 10)
+    _check(gpu_ctx, bases, offsets, 64, 1)
 
 
 def test_windows_do_not_cross_sketch_boundaries(gpu_ctx):
@@ -103,6 +105,15 @@ def test_tile_edges(gpu_ctx, n):
     rng = np.random.default_rng(n)
     bases = _random_sequence(rng, n, p_bad=0.0)
     _check(gpu_ctx, bases, [0, n], 31, 1)
+
+
+@pytest.mark.parametrize("n", [4096 * 3, 4096 * 3 + 1, 4096 * 3 - 1, 4096 * 2 + 50, 4096 * 2 + 63, 51, 50, 64])
+def test_tile_edges_two_word_windows(gpu_ctx, n):
+    rng = np.random.default_rng(n + 7)
+    bases = _random_sequence(rng, n, p_bad=0.0)
+    _check(gpu_ctx, bases, [0, n], 51, 1)
+    if n >= 64:
+        _check(gpu_ctx, bases, [0, n], 64, 1)
 
 
 def test_second_pass_when_survivors_exceed_the_estimate(gpu_ctx):

@@ -70,6 +70,9 @@ def host_hash(tmp_path_factory):
     lib.hh_hash_windows_packed.restype = ctypes.c_uint64
     lib.hh_tile_walk_packed.argtypes = lib.hh_hash_windows.argtypes
     lib.hh_tile_walk_packed.restype = ctypes.c_uint64
+    for fn in (lib.hh_hash_windows_packed2, lib.hh_tile_walk_packed2):
+        fn.argtypes = lib.hh_hash_windows.argtypes
+        fn.restype = ctypes.c_uint64
     return lib
 
 
@@ -117,6 +120,38 @@ def test_packed_tile_walk_matches_oracle(host_hash, k, n):
         got = np.empty(n + 1, dtype=np.uint64)
         n_exp = lib.so_sketch_record(buf.ctypes.data, n, k, 42, 2 ** 64 - 1, exp.ctypes.data, n)
         n_got = host_hash.hh_tile_walk_packed(buf.ctypes.data, n, k, 42, got.ctypes.data)
+        assert n_got == n_exp, (k, n, p_bad)
+        assert np.array_equal(got[:n_got], exp[:n_exp]), (k, n, p_bad)
+
+
+@pytest.mark.parametrize("k", list(range(33, 65)))
+def test_device_packed2_hash_code_matches_oracle(host_hash, k):
+    """the 33 <= k <= 64 path of the kernel: window = two 64-bit words of 2-bit codes"""
+    rng = np.random.default_rng(2000 + k)
+    seq = _random_sequence(rng, 8000, p_bad=0.004) + b"ACGT" * 40 + b"AATT" * 40 + b"A" * 100 + b"GAATTC" * 30
+    lib = so._load()
+    n = len(seq)
+    buf = np.frombuffer(seq, dtype=np.uint8)
+    exp = np.empty(n, dtype=np.uint64)
+    got = np.empty(n, dtype=np.uint64)
+    for seed in (42, 7):
+        n_exp = lib.so_sketch_record(buf.ctypes.data, n, k, seed, 2 ** 64 - 1, exp.ctypes.data, n)
+        n_got = host_hash.hh_hash_windows_packed2(buf.ctypes.data, n, k, seed, got.ctypes.data)
+        assert n_got == n_exp and n_exp > 100
+        assert np.array_equal(got[:n_got], exp[:n_exp]), (k, seed)
+
+
+@pytest.mark.parametrize("k,n", [(51, 20000), (64, 9000), (33, 4096 * 2), (48, 4097), (47, 4095), (51, 4096 + 50), (51, 51), (51, 50), (63, 12345)])
+def test_packed2_tile_walk_matches_oracle(host_hash, k, n):
+    rng = np.random.default_rng(k * 100003 + n)
+    for p_bad in (0.0, 0.005, 0.1):
+        seq = _random_sequence(rng, n, p_bad=p_bad)
+        lib = so._load()
+        buf = np.frombuffer(seq, dtype=np.uint8)
+        exp = np.empty(n + 1, dtype=np.uint64)
+        got = np.empty(n + 1, dtype=np.uint64)
+        n_exp = lib.so_sketch_record(buf.ctypes.data, n, k, 42, 2 ** 64 - 1, exp.ctypes.data, n)
+        n_got = host_hash.hh_tile_walk_packed2(buf.ctypes.data, n, k, 42, got.ctypes.data)
         assert n_got == n_exp, (k, n, p_bad)
         assert np.array_equal(got[:n_got], exp[:n_exp]), (k, n, p_bad)
 

@@ -132,7 +132,7 @@ struct ygpu_ctx {
     void* run_scratch = nullptr;    // run-path buffers (run_kernels.cu)
     void* upload = nullptr;         // streaming ingest state (yacht_gpu.cu: ygpu_upload_*)
     void* sketch_scratch = nullptr; // sketching buffers (sketch.cu)
-    int sketch_kernel = 0;          // 0 = by k-mer size (packed words up to k = 32), 2 = always the byte-wise kernel (test hook)
+    int sketch_kernel = 0;          // 0 = by k-mer size (packed words up to k = 64), 2 = always the byte-wise kernel (test hook)
 
     ygpu_timings tm = {};
 };

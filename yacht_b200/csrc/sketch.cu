@@ -6,6 +6,7 @@
 //
 //   k_sketch_hash_packed (k <= 32) : the same tile as 2-bit codes; windows are 64-bit words, canonical choice and ASCII
 //                   expansion are word operations (ysk_canonical_hash_packed).  Three conflict-free loads per 16 windows.
+//   k_sketch_hash_packed2 (33 <= k <= 64, YACHT's k = 51) : the same with two-word windows.
 //   k_sketch_hash (any k <= 256) : one CTA per tile of 4 096 window starts.  The tile (+ K - 1 bytes) is brought into shared memory with
 //                   16-byte loads and reduced to 2-bit codes on the way; a thread walks 16 consecutive starts with a rolling
 //                   "valid bases so far" counter, so a window costs one code load for validity, ~1.3 compares for the
@@ -166,6 +167,64 @@ __global__ void __launch_bounds__(SK_NT) k_sketch_hash_packed(const uint8_t* __r
     if ((tid & 31) == 0 && valid_kmers) atomicAdd(&cnt[1], valid_kmers);
 }
 
+// 33 <= k <= 64 (YACHT's k = 51): the same layout, a window is two 64-bit words, the span of a thread 80 bases.
+__global__ void __launch_bounds__(SK_NT) k_sketch_hash_packed2(const uint8_t* __restrict__ bases, uint64_t n_bases,
+                                                               const uint64_t* __restrict__ sk_off, uint32_t n_sketches, int k, uint32_t seed,
+                                                               uint64_t max_hash, uint64_t* __restrict__ out_key, uint32_t* __restrict__ out_sid,
+                                                               uint64_t cap, unsigned long long* __restrict__ cnt) {
+    __shared__ uint32_t s_code[SK_TILE / 16 + 4];            // + 64 bases behind the tile (k - 1 <= 63 are needed)
+    __shared__ uint32_t s_bad[SK_TILE / 32 + 4];
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (n_bases + SK_TILE - 1) / SK_TILE;
+    unsigned long long valid_kmers = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * SK_TILE;
+        const uint4* g = (const uint4*)(bases + base);
+        __syncthreads();
+        {
+            uint32_t code, bad;
+            const uint4 v = g[tid];
+            ysk_pack16(v.x, v.y, v.z, v.w, code, bad);
+            s_code[tid] = code;
+            const uint32_t up = __shfl_down_sync(0xffffffffu, bad, 1);
+            if (!(tid & 1)) s_bad[tid >> 1] = bad | (up << 16);
+            if (tid < 2) {                                   // the 64 bases behind the tile: two threads, 32 bases each
+                uint32_t c0, b0, c1, b1;
+                const uint4 t0 = g[SK_TILE / 16 + 2 * tid], t1 = g[SK_TILE / 16 + 2 * tid + 1];
+                ysk_pack16(t0.x, t0.y, t0.z, t0.w, c0, b0);
+                ysk_pack16(t1.x, t1.y, t1.z, t1.w, c1, b1);
+                s_code[SK_TILE / 16 + 2 * tid] = c0;
+                s_code[SK_TILE / 16 + 2 * tid + 1] = c1;
+                s_bad[SK_TILE / 32 + tid] = b0 | (b1 << 16);
+                s_bad[SK_TILE / 32 + 2 + tid] = 0;           // read by the last threads' spans, never used
+            }
+        }
+        __syncthreads();
+        uint64_t s0, s1, s2, b0, b1;
+        ysk_thread_span2(s_code, s_bad, tid, s0, s1, s2, b0, b1);
+        const uint64_t p0 = base + (uint64_t)tid * SK_PER;
+#pragma unroll 1
+        for (int i = 0; i < SK_PER; i++) {
+            const uint64_t p = p0 + i;
+            uint64_t w0, w1;
+            if (!ysk_span_window2(s0, s1, s2, b0, b1, i, k, w0, w1) || p + (uint64_t)k > n_bases) continue;
+            valid_kmers++;
+            const uint64_t h = ysk_canonical_hash_packed2(w0, w1, k, seed);
+            if (h > max_hash) continue;
+            uint32_t a = 0, b = n_sketches;                  // sk_off[a] <= p < sk_off[b]
+            while (b - a > 1) {
+                const uint32_t mid = (a + b) >> 1;
+                if (sk_off[mid] <= p) a = mid; else b = mid;
+            }
+            if (p < sk_off[a] || p + (uint64_t)k > sk_off[a + 1]) continue;
+            const unsigned long long slot = atomicAdd(&cnt[0], 1ull);
+            if (slot < cap) { out_key[slot] = h; out_sid[slot] = a; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) valid_kmers += __shfl_down_sync(0xffffffffu, valid_kmers, o);
+    if ((tid & 31) == 0 && valid_kmers) atomicAdd(&cnt[1], valid_kmers);
+}
+
 __global__ void __launch_bounds__(256) k_sketch_heads(const uint64_t* __restrict__ key, const uint32_t* __restrict__ sid, uint64_t m,
                                                        uint32_t* __restrict__ flag) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
@@ -242,6 +301,8 @@ extern "C" int ygpu_sketch_sequences(ygpu_ctx* ctx, const uint8_t* bases, uint64
         YG_CUDA(ctx, cudaMemsetAsync(S->d_cnt, 0, 2 * sizeof(unsigned long long), st));
         if (ksize <= 32 && ctx->sketch_kernel != 2)
             k_sketch_hash_packed<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
+        else if (ksize <= 64 && ctx->sketch_kernel != 2)
+            k_sketch_hash_packed2<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
         else
             k_sketch_hash<<<grid, SK_NT, 0, st>>>(S->d_bases, n_bases, S->d_off, n_sketches, ksize, seed, max_hash, S->d_key, S->d_sid, cap, S->d_cnt);
         YG_CUDA(ctx, cudaGetLastError());

@@ -161,3 +161,67 @@ YSK_HD bool ysk_span_window(uint64_t lo, uint64_t hi, uint64_t badbits, int i, i
     w = i ? ((lo >> (2 * i)) | (hi << (64 - 2 * i))) : lo;
     return true;
 }
+
+// ---- 33 <= k <= 64: the window as two 64-bit words (w1:w0), base j in bits [2j+1 : 2j] of the 128-bit value ----------------
+YSK_HD uint64_t ysk_rev2(uint64_t x) {                 // reverse the order of the 32 two-bit groups
+    x = ysk_brev64(x);
+    return ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);
+}
+YSK_HD uint64_t ysk_ascii8w(uint64_t c0, uint64_t c1, int q) {      // bytes 8q .. 8q+7 of the k-mer held in (c1:c0), q = 0..7
+    return q < 4 ? ysk_ascii8(c0, q) : ysk_ascii8(c1, q - 4);
+}
+YSK_HD uint64_t ysk_canonical_hash_packed2(uint64_t w0, uint64_t w1, int k, uint32_t seed) {
+    const uint64_t mask1 = (k >= 64) ? ~0ULL : ((1ULL << (2 * k - 64)) - 1ULL);          // k >= 33: the low word is full
+    const int sh = 128 - 2 * k;                                                         // 0 .. 62
+    w1 &= mask1;
+    const uint64_t f1 = ysk_rev2(w0), f0 = ysk_rev2(w1);                                // (f1:f0): base 0 in the top two bits, zero fill below
+    const uint64_t n0 = ~w0, n1 = ~w1 & mask1;                                          // complement of every base
+    const uint64_t r1 = sh ? ((n1 << sh) | (n0 >> (64 - sh))) : n1, r0 = n0 << sh;      // (r1:r0) = reverse complement, packed like (f1:f0)
+    const bool fw = (f1 < r1) || (f1 == r1 && f0 <= r0);
+    const uint64_t g0 = sh ? ((f0 >> sh) | (f1 << (64 - sh))) : f0, g1 = f1 >> sh;      // (f1:f0) >> sh: the window reversed, base 0 low
+    const uint64_t c0 = fw ? w0 : ~g0, c1 = fw ? w1 : (~g1 & mask1);                    // canonical k-mer, byte i = base i
+    const uint64_t m1 = 0x87c37b91114253d5ULL, m2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    const int nblocks = k >> 4;
+    for (int blk = 0; blk < nblocks; blk++) {
+        uint64_t k1 = ysk_ascii8w(c0, c1, 2 * blk), k2 = ysk_ascii8w(c0, c1, 2 * blk + 1);
+        k1 *= m1; k1 = ysk_rotl(k1, 31); k1 *= m2; h1 ^= k1;
+        h1 = ysk_rotl(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= m2; k2 = ysk_rotl(k2, 33); k2 *= m1; h2 ^= k2;
+        h2 = ysk_rotl(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const int t = k & 15;
+    if (t > 8) {
+        uint64_t k2 = ysk_ascii8w(c0, c1, 2 * nblocks + 1) & ysk_low_bytes(t - 8);
+        k2 *= m2; k2 = ysk_rotl(k2, 33); k2 *= m1; h2 ^= k2;
+    }
+    if (t > 0) {
+        uint64_t k1 = ysk_ascii8w(c0, c1, 2 * nblocks) & ysk_low_bytes(t);
+        k1 *= m1; k1 = ysk_rotl(k1, 31); k1 *= m2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
+    h1 += h2; h2 += h1;
+    h1 = ysk_fmix(h1); h2 = ysk_fmix(h2);
+    h1 += h2;
+    return h1;
+}
+// Thread `tid`'s 80-base span (16 window starts, up to 63 bases behind the last one) and its "bad" bits.
+YSK_HD void ysk_thread_span2(const uint32_t* s_code, const uint32_t* s_bad, int tid, uint64_t& s0, uint64_t& s1, uint64_t& s2,
+                             uint64_t& b0, uint64_t& b1) {
+    s0 = (uint64_t)s_code[tid] | ((uint64_t)s_code[tid + 1] << 32);
+    s1 = (uint64_t)s_code[tid + 2] | ((uint64_t)s_code[tid + 3] << 32);
+    s2 = (uint64_t)s_code[tid + 4];
+    const int idx = tid >> 1, sh = (tid & 1) * 16;
+    const uint64_t raw0 = (uint64_t)s_bad[idx] | ((uint64_t)s_bad[idx + 1] << 32);
+    const uint64_t raw1 = (uint64_t)s_bad[idx + 2] | ((uint64_t)s_bad[idx + 3] << 32);
+    b0 = sh ? ((raw0 >> 16) | (raw1 << 48)) : raw0;        // bases 16 tid .. 16 tid + 63
+    b1 = raw1 >> sh;                                        // bases 16 tid + 64 .. (at least 48 of them; 15 are needed)
+}
+YSK_HD bool ysk_span_window2(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t b0, uint64_t b1, int i, int k, uint64_t& w0, uint64_t& w1) {
+    const uint64_t kmask = (k >= 64) ? ~0ULL : ((1ULL << k) - 1ULL);
+    const uint64_t bad = i ? ((b0 >> i) | (b1 << (64 - i))) : b0;       // "bad" bits of bases i .. i + 63 of the span
+    if ((bad & kmask) != 0) return false;
+    w0 = i ? ((s0 >> (2 * i)) | (s1 << (64 - 2 * i))) : s0;
+    w1 = i ? ((s1 >> (2 * i)) | (s2 << (64 - 2 * i))) : s1;
+    return true;
+}

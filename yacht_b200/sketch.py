@@ -28,6 +28,15 @@ def _context() -> _lib.GpuContext:
     return _ctx
 
 
+def add_cli_arguments(parser, infile_help: str, nargs=None) -> None:
+    """The four options both `yacht sketch` sub-commands take (names and defaults of the reference's wrappers)."""
+    kw = {"nargs": nargs} if nargs else {}
+    parser.add_argument("--infile", help=infile_help, required=True, **kw)
+    for flag, default, text in (("--kmer", 31, "K-mer size."), ("--scaled", 1000, "Scaled factor.")):
+        parser.add_argument(flag, type=int, default=default, help=text)
+    parser.add_argument("--outfile", help="Output file name.", required=True)
+
+
 def max_hash_for_scaled(scaled: int) -> int:
     """sourmash's rule: round((2^64 - 1) / scaled) in double arithmetic (18446744073709552 at scaled = 1000)."""
     if scaled == 0:

@@ -570,6 +570,16 @@ def run_b200_arm(args):
         except Exception as e:
             line["parity"] = {"parity_digest_ok": False, "error": repr(e)}
         line["parity_digest_ok"] = line["parity"].get("parity_digest_ok")
+        # ---- the run path (configs[4]) beside it: never allowed to take the train numbers down ------------
+        if world == 1 and not args.no_run_path:
+            try:
+                if not ctx.n:
+                    ctx.load_sketches(db.hashes, db.offsets)
+                rp, rp_roof, rp_e2e = measure_run_path(ctx, lib, db, args, rl)
+                line["run_path"], line["run_e2e"] = rp, rp_e2e
+                rooflines["run_k5"] = rp_roof
+            except Exception as e:
+                line["run_path"] = {"error": repr(e)}
         # ---- CPU baseline: bounded sample on this box's host cores -------------------------------------
         if not args.no_cpu_baseline:
             try:
@@ -599,6 +609,74 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def measure_run_path(ctx, lib, db, args, rl):
+    """BASELINE.json configs[4] beside the train step (N = 1 only): a synthetic 10 M-hash sample against the resident reference,
+    min_coverage_list 1 0.6 0.2 0.1, significance 0.99 -- sample membership + exclusive hashes (K5, one call) and the hypothesis
+    statistics (K6), through the C ABI from host buffers.  The CPU figure is the python-set RESTATEMENT of the reference's
+    get_exclusive_hashes / single_hyp_test (oracle/run_oracle.py; sourmash's multisearch is not in this image) on a few genomes."""
+    import ctypes
+    from yacht_b200 import synth
+    covs = [1.0, 0.6, 0.2, 0.1]
+    n, T = db.n, int(db.offsets[-1])
+    t0 = time.perf_counter()
+    sample, _, _ = synth.make_sample(db, 5, n_present=min(2000, max(1, n // 4)), total_hashes=args.run_sample_hashes)
+    gen_s = time.perf_counter() - t0
+    hp = lib.ygpu_host_alloc(max(len(sample), 1) * 8)          # page-locked, as a host that read the sample from disk would stage it
+    try:
+        pinned = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_uint64)), shape=(max(len(sample), 1),))[: len(sample)]
+        pinned[:] = sample
+        best = None
+        for rep in range(4):                                     # the first call also builds what the run path keeps resident
+            ctx.reset_timers()
+            t0 = time.perf_counter()
+            counts = ctx.exclusive_hashes(pinned)
+            w5 = time.perf_counter() - t0
+            nt = np.flatnonzero(counts["nontrivial"])
+            t0 = time.perf_counter()
+            rows = ctx.hyp_test(counts["n_exclusive"][nt], counts["n_match"][nt], 31, 0.99, 0.95, covs)
+            w6 = time.perf_counter() - t0
+            tm = ctx.timings()
+            cur = {"k5_ms": tm["ms_sample"], "k5_kernels_ms": tm["ms_sample_kernels"], "k5_wall_ms": w5 * 1e3, "k6_ms": tm["ms_stats"],
+                   "k6_wall_ms": w6 * 1e3, "first_call_setup_ms": tm["ms_sort"]}
+            if rep and (best is None or cur["k5_wall_ms"] + cur["k6_wall_ms"] < best["k5_wall_ms"] + best["k6_wall_ms"]):
+                best = cur
+        nbytes = 12 * T + 8 * len(sample)
+        roof = rl("k5s_hist + k5s_scatter + k5_bucket<0> + k5_bucket<1> (K5: sample membership + exclusive hashes on the partitioned reference)",
+                  nbytes, best["k5_kernels_ms"], "8*T_ref + 4*T_ref + 8*T_sample (SURVEY.md 8d)")
+        roof["share_of_step"] = None
+        e2e_ms = best["k5_wall_ms"] + best["k6_wall_ms"]
+        out = {"workload": f"BASELINE.json configs[4]: {len(sample)}-hash synthetic sample vs the {n} resident reference genomes ({T} hashes), "
+                           f"min_coverage_list {covs}, significance 0.99, k=31, ani_thresh=0.95",
+               "nontrivial_genomes": int(len(nt)), "in_sample_at_cov1": int(rows["in_sample_est"][0].sum()), "k6_evaluations": int(len(nt) * len(covs)),
+               **best, "sample_gen_seconds": gen_s}
+        run_e2e = {"value": n / (e2e_ms * 1e-3), "unit": "reference genomes tested/s", "ms_per_sample": e2e_ms,
+                   "h2d_bytes_per_step": 8 * len(sample) + 16 * len(nt), "d2h_bytes_per_step": 16 * n + 64 * len(nt) * len(covs),
+                   "what": "ygpu_exclusive_hashes + ygpu_hyp_test from host buffers, wall clock around the two C-ABI calls"}
+        # CPU restatement on a bounded sample + parity of the GPU counts against it
+        if not args.no_cpu_baseline:
+            from oracle import run_oracle as ro
+            ns = min(n, args.run_cpu_genomes)
+            sub = db.subset(range(ns))
+            t0 = time.perf_counter()
+            exp = ro.exclusive_counts(sub.hashes, sub.offsets, sample)
+            cpu5 = time.perf_counter() - t0
+            ids = np.flatnonzero(exp["nontrivial"])[:64]
+            t0 = time.perf_counter()
+            for g in ids:
+                for c in covs:
+                    ro.single_hyp_test((int(exp["n_exclusive"][g]), int(exp["n_match"][g])), 31, 0.99, 0.95, c)
+            cpu6 = time.perf_counter() - t0
+            ctx.load_sketches(sub.hashes, sub.offsets)
+            got = ctx.exclusive_hashes(pinned)
+            out["cpu_restated"] = {"kind": "port (python sets / scipy, like the reference's get_exclusive_hashes and single_hyp_test)", "cores": 1,
+                                   "sample": f"first {ns} reference genomes, {len(ids)} nontrivial x {len(covs)} coverages",
+                                   "exclusive_genomes_per_s": ns / max(cpu5, 1e-9), "hyp_evals_per_s": len(ids) * len(covs) / max(cpu6, 1e-9),
+                                   "parity_on_sample": bool(all(np.array_equal(got[f], exp[f]) for f in ("n_overlap", "n_exclusive", "n_match")))}
+        return out, roof, run_e2e
+    finally:
+        lib.ygpu_host_free(hp)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -610,6 +688,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="genomes in the CPU sample (cpu_baseline: 0 = size for ~15 s; --impl reference: 0 = the FULL configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-run-path", action="store_true", help="skip the yacht-run measurement (configs[4]) that follows the train step at N = 1")
+    ap.add_argument("--run-sample-hashes", type=int, default=10_000_000, help="hashes in the synthetic sample of the run-path measurement")
+    ap.add_argument("--run-cpu-genomes", type=int, default=24, help="reference genomes in the CPU restatement of the run path (~0.4 s each)")
     ap.add_argument("--no-reference-cache", action="store_true",
                     help="--impl reference: measure again even if this box already holds a measurement of the same configuration")
     ap.add_argument("--residency", default="hashes", choices=["hashes", "genomes"],

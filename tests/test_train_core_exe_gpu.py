@@ -120,7 +120,7 @@ def _n_gpus():
     return _lib.load_library().ygpu_device_count()
 
 
-@pytest.mark.parametrize("ngpu", [2, 4, 8])
+@pytest.mark.parametrize("ngpu", [2])      # larger rank counts of the same library entry points: tests/test_sharded_step_gpu.py
 def test_exe_multi_gpu_output_equals_single_gpu(ngpu, tmp_path):
     """YACHT_NUM_GPUS=k: threads as ranks, hash-range residency, sharded step (the replicated step when the database does not
     qualify) -- the files must be byte-identical to the single-GPU run's."""

@@ -62,3 +62,21 @@ def test_zip_database(tmp_path):
     back = sigio.read_sig_zip(zp)
     assert [s.name for s in back] == ["g0", "g1", "g2", "g3"]
     assert back[2].mean_abundance == 2.0 and list(back[2].mins) == [3, 102, 1002]
+
+
+def test_write_signatures_round_trip(tmp_path):
+    """several sketches in one JSON signature file (what `sourmash sketch dna -o x.sig` writes for several records)"""
+    import numpy as np
+    from yacht_b200 import sigio
+    sketches = [dict(name="rec one", filename="a.fa", mins=np.array([3, 17, 99], np.uint64), abundances=np.array([1, 4, 2], np.uint32)),
+                dict(name="", filename="a.fa", mins=np.array([5], np.uint64), abundances=None),
+                dict(name="empty", filename="a.fa", mins=np.zeros(0, np.uint64), abundances=np.zeros(0, np.uint32))]
+    for fn in ("many.sig", "many.sig.gz"):
+        path = str(tmp_path / fn)
+        sigio.write_signatures(path, sketches, ksize=21, max_hash=sigio.MAX_HASH_SCALED_1000)
+        back = sigio.parse_signature_json(sigio._open_text(path), path)
+        assert [s.name for s in back] == ["rec one", "", "empty"]
+        assert [list(map(int, s.mins)) for s in back] == [[3, 17, 99], [5], []]
+        assert list(map(int, back[0].abundances)) == [1, 4, 2] and back[1].abundances is None
+        assert all(s.ksize == 21 and s.scaled == 1000 for s in back)
+        assert back[0].md5sum == sigio.compute_md5sum(21, [3, 17, 99])
